@@ -1,0 +1,10 @@
+"""hslabs_b200 -- B200-native gait evaluation (IK + inverse dynamics + contact solve) behind a C ABI.
+
+The compute path is libhsl_b200.so (hand-written sm_100a CUDA, see csrc/); this package is the thin
+ctypes host layer that mirrors the reference's evaluation interface.  There is no CPU fallback.
+"""
+from .api import (HSL_FLAG_IGNORE_REACH, HSL_NPARAM, HslError, Model, lib_path, load_preset, make_params, model_path,
+                  measure_cot, measure_cot_sweep)
+
+__all__ = ["Model", "HslError", "make_params", "load_preset", "model_path", "measure_cot", "measure_cot_sweep", "lib_path",
+           "HSL_NPARAM", "HSL_FLAG_IGNORE_REACH"]

@@ -1,0 +1,228 @@
+"""ctypes host layer over include/hsl.h.
+
+Names follow the reference's evaluation interface: a candidate is the scalar content of
+``pgsconfigparams`` (pergen.h:137-146), ``measure_cot`` / ``measure_cot_sweep`` are
+``modelplayer::measure_cot(_sweep)`` (player.cpp:269-285, 311-321) evaluated in one batch on the GPU,
+``Model.eval_gaits_detail`` exposes what ``periodic`` keeps per frame (trajectory, joint force/torque
+vector x, contact forces z, motor torques; periodic.cpp:77-96, 361-391).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+HSL_NPARAM = 13
+HSL_FLAG_IGNORE_REACH = 1
+ST_BAD_PARAMS, ST_UNREACHABLE, ST_SOLVER, ST_FEW_CONTACTS = 1, 2, 4, 8
+SWEEP_NAMES = {"step_duration": 6, "period": 7, "step_length": 8, "step_height": 9}  # pergen.cpp:423
+
+_lib = None
+
+
+class HslError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(HERE, "lib", "libhsl_b200.so")
+
+
+def model_path(name):
+    """Path of a bundled model input ('hexapod' -> .../models/hexapod.xml)."""
+    if not name.endswith(".xml"):
+        name += ".xml"
+    return os.path.join(HERE, "models", name)
+
+
+def _load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise HslError("libhsl_b200.so is not built (%s); run `python hslabs_b200/build.py` -- there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    lib.hsl_last_error.restype = C.c_char_p
+    lib.hsl_model_rcap.restype = C.c_double
+    lib.hsl_model_pod.restype = C.c_size_t
+    lib.hsl_launch_count.restype = C.c_int64
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.hsl_model_load_xml.argtypes = [C.c_char_p, C.POINTER(vp)]
+    lib.hsl_model_free.argtypes = [vp]
+    lib.hsl_model_dims.argtypes = [vp, vp]
+    lib.hsl_model_rcap.argtypes = [vp]
+    lib.hsl_model_pod.argtypes = [vp, vp, C.c_size_t]
+    lib.hsl_eval_gaits.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.hsl_eval_gaits_host.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, vp, vp]
+    lib.hsl_eval_gaits_detail_host.argtypes = [vp, i64, i32, vp, i32] + [vp] * 10
+    lib.hsl_eval_trajectories_host.argtypes = [vp, i64, i32] + [vp] * 9
+    lib.hsl_solve_frames_host.argtypes = [vp, i64] + [vp] * 11
+    lib.hsl_set_tuning.argtypes = [vp, i32, i32]
+    lib.hsl_launch_count.argtypes = [vp]
+    lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
+    return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
+            "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_set_tuning", "hsl_launch_count",
+            "hsl_dfma_probe"]
+
+
+def _check(rc):
+    if rc != 0:
+        raise HslError("hsl error %d: %s" % (rc, _load().hsl_last_error().decode()))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_params(torso_pos=(0, 0, 0), torso_angles=(0, 0, 0), step_duration=1.0, period=3.0, step_length=0.5,
+                step_height=0.1, curvature=0.0, shift_type=-1, shift_value=0.0):
+    """One candidate row (13 doubles), the scalars of the reference's pgsconfigparams."""
+    return np.array(list(torso_pos) + list(torso_angles) + [step_duration, period, step_length, step_height, curvature,
+                                                             shift_type, shift_value], dtype=np.float64)
+
+
+def load_preset(config_fname, setup_id):
+    """modelplayer::get_rec_str + get_pgs_config_params (player.cpp:170-208, 230-244): preset row -> (params, xml name)."""
+    with open(config_fname) as f:
+        for line in f:
+            tok = line.split()
+            if not tok or int(tok[0]) != setup_id:
+                continue
+            kw, xml, i = {}, None, 1
+            while i < len(tok):
+                key = tok[i]
+                if key == "xml_file":
+                    xml = tok[i + 1]; i += 2
+                elif key in ("torso_pos", "torso_angles"):
+                    kw[key] = tuple(float(v) for v in tok[i + 1:i + 4]); i += 4
+                elif key in ("step_duration", "period", "step_length", "step_height", "curvature"):
+                    kw[key] = float(tok[i + 1]); i += 2
+                elif key == "lateral_foot_shift":
+                    kw["shift_type"], kw["shift_value"] = 0, float(tok[i + 1]); i += 2
+                elif key == "radial_foot_shift":
+                    kw["shift_type"], kw["shift_value"] = 1, float(tok[i + 1]); i += 2
+                else:
+                    raise HslError("ERROR: unknown key " + key)
+            return make_params(**kw), xml
+    raise HslError("ERROR: no string with rec_id = %d" % setup_id)
+
+
+class Model:
+    """kinematicmodel + liksolver + periodic's static data, flattened and resident for the kernels."""
+
+    def __init__(self, xml_path):
+        lib = _load()
+        h = C.c_void_p()
+        _check(lib.hsl_model_load_xml(os.fspath(xml_path).encode(), C.byref(h)))
+        self._h = h
+        d = np.zeros(6, np.int32)
+        _check(lib.hsl_model_dims(h, _p(d)))
+        self.n, self.nf, self.nmj, self.config_dim, self.ntrunk, self.lik_index = (int(v) for v in d)
+        self.rcap = lib.hsl_model_rcap(h)
+        self.xml_path = os.fspath(xml_path)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _load().hsl_model_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- measurement helpers
+    def set_tuning(self, fb=32, minb=2):
+        _check(_load().hsl_set_tuning(self._h, fb, minb))
+
+    def launch_count(self):
+        return int(_load().hsl_launch_count(self._h))
+
+    def pod_bytes(self):
+        size = _load().hsl_model_pod(self._h, None, 0)
+        buf = np.zeros(size, np.uint8)
+        _load().hsl_model_pod(self._h, _p(buf), size)
+        return buf
+
+    # ---- batch evaluation, host buffers (the reference-facing call)
+    def eval_gaits(self, params, n_t, flags=0):
+        params = np.ascontiguousarray(params, np.float64).reshape(-1, HSL_NPARAM)
+        c = params.shape[0]
+        out = dict(cot=np.empty(c), work=np.empty(c), min_cfz=np.empty(c), max_mu=np.empty(c), status=np.empty(c, np.int32))
+        _check(_load().hsl_eval_gaits_host(self._h, c, n_t, _p(params), flags, _p(out["cot"]), _p(out["work"]),
+                                           _p(out["min_cfz"]), _p(out["max_mu"]), _p(out["status"])))
+        return out
+
+    def eval_gaits_detail(self, params, n_t, flags=0):
+        params = np.ascontiguousarray(params, np.float64).reshape(-1, HSL_NPARAM)
+        c = params.shape[0]
+        out = dict(cot=np.empty(c), work=np.empty(c), min_cfz=np.empty(c), max_mu=np.empty(c), status=np.empty(c, np.int32),
+                   traj=np.empty((c, n_t + 4, self.config_dim)), x=np.empty((c, n_t, 6 * self.n)),
+                   z=np.empty((c, n_t, 3 * self.nf)), tau=np.empty((c, n_t, self.nmj)),
+                   contacts=np.empty((c, n_t, self.nf), np.uint8))
+        _check(_load().hsl_eval_gaits_detail_host(self._h, c, n_t, _p(params), flags, *[_p(out[k]) for k in (
+            "cot", "work", "min_cfz", "max_mu", "status", "traj", "x", "z", "tau", "contacts")]))
+        return out
+
+    def eval_trajectories(self, traj, dt, n_t):
+        traj = np.ascontiguousarray(traj, np.float64).reshape(-1, n_t + 5, self.config_dim)
+        c = traj.shape[0]
+        dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, np.float64), (c,)))
+        out = dict(work=np.empty(c), min_cfz=np.empty(c), max_mu=np.empty(c), status=np.empty(c, np.int32),
+                   x=np.empty((c, n_t, 6 * self.n)), z=np.empty((c, n_t, 3 * self.nf)), tau=np.empty((c, n_t, self.nmj)))
+        _check(_load().hsl_eval_trajectories_host(self._h, c, n_t, _p(traj), _p(dt), _p(out["work"]), _p(out["min_cfz"]),
+                                                  _p(out["max_mu"]), _p(out["status"]), _p(out["x"]), _p(out["z"]), _p(out["tau"])))
+        return out
+
+    def solve_frames(self, pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos, contacts):
+        """forcetorquesolver::solve_forcetorques + get_motor_torques on populated dynrecords."""
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos)]
+        contacts = np.ascontiguousarray(contacts, np.uint8)
+        f = arrs[0].shape[0]
+        out = dict(x=np.empty((f, 6 * self.n)), z=np.empty((f, 3 * self.nf)), tau=np.empty((f, self.nmj)),
+                   status=np.empty(f, np.int32))
+        _check(_load().hsl_solve_frames_host(self._h, f, *[_p(a) for a in arrs], _p(contacts), _p(out["x"]), _p(out["z"]),
+                                             _p(out["tau"]), _p(out["status"])))
+        return out
+
+    # ---- device-pointer entry (inputs already in HBM); arguments are integer device addresses
+    def eval_gaits_device(self, n_cand, n_t, d_params, d_cot=0, d_work=0, d_min_cfz=0, d_max_mu=0, d_status=0, flags=0,
+                          stream=0):
+        _check(_load().hsl_eval_gaits(self._h, n_cand, n_t, d_params, flags, d_cot or None, d_work or None,
+                                      d_min_cfz or None, d_max_mu or None, d_status or None, stream or None))
+
+
+def dfma_probe(blocks=148 * 8, threads=256, iters=4096):
+    """Measured FP64 FMA throughput of the current device in TFLOP/s (roofline denominator of this path)."""
+    tf = C.c_double()
+    ms = C.c_float()
+    _check(_load().hsl_dfma_probe(blocks, threads, iters, C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value
+
+
+def measure_cot(model, params, n_t, flags=0):
+    """modelplayer::measure_cot (player.cpp:269-285) for one candidate."""
+    r = model.eval_gaits(params, n_t, flags)
+    return float(r["cot"][0])
+
+
+def measure_cot_sweep(model, params, n_t, param_name, val0, val1, n_val, flags=0, verbose=False):
+    """modelplayer::measure_cot_sweep (player.cpp:311-321) with pgssweeper::sweep/next (pergen.cpp:417-449):
+    n_val+1 candidates val0 + i*(val1-val0)/n_val, evaluated as one batch."""
+    if param_name not in SWEEP_NAMES:
+        raise HslError("ERROR: cannot sweep over " + param_name)
+    delval = (val1 - val0) / n_val
+    vals = np.array([val0 + i * delval for i in range(n_val + 1)])
+    batch = np.tile(np.asarray(params, np.float64), (n_val + 1, 1))
+    batch[:, SWEEP_NAMES[param_name]] = vals
+    r = model.eval_gaits(batch, n_t, flags)
+    if verbose:
+        for v, c in zip(vals, r["cot"]):
+            print("val = %g COT = %g" % (v, c))
+    return vals, r["cot"]

@@ -1,0 +1,352 @@
+// C ABI of libhsl_b200.so (include/hsl.h): model handle, device workspace, host/device entry points.
+// No CPU fallback exists: every compute entry needs a CUDA device and fails with HSL_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hsl.h"
+#include "hsl_internal.h"
+
+namespace {
+thread_local char g_err[512] = "";
+
+int set_err(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof g_err, fmt, a);
+  return code;
+}
+#define HSL_CUDA(call)                                                            \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) return set_err(HSL_ERR_CUDA, "CUDA: %s", cudaGetErrorString(e_)); \
+  } while (0)
+
+struct DevBuf {  // grow-only device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct PinBuf {  // grow-only pinned host buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t need(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMallocHost(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+struct HslModel {
+  HslModelPod pod;
+  double total_mass;
+  int fb = 32, minb = 2;
+  int64_t launches = 0;
+  // workspace
+  DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b;
+  PinBuf pin_in, pin_out;
+  cudaStream_t stream = nullptr;
+  ~HslModel() {
+    DevBuf* all[] = {&cand, &ttab, &wframe, &fmin, &fmax, &status, &params, &out4, &dump_x, &dump_z, &dump_tau, &dump_q, &dump_c, &in_a, &in_b};
+    for (DevBuf* b : all) b->release();
+    pin_in.release();
+    pin_out.release();
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+extern "C" {
+
+const char* hsl_last_error(void) { return g_err; }
+
+int hsl_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+int hsl_model_load_xml(const char* xml_path, HslModel** out) {
+  if (!xml_path || !out) return set_err(HSL_ERR_ARG, "null argument");
+  HslModel* m = new HslModel;
+  char err[400] = "";
+  int rc = hsl_build_model_pod(xml_path, &m->pod, err, sizeof err);
+  if (rc != 0) {
+    delete m;
+    return set_err(rc, "%s", err);
+  }
+  m->total_mass = 0;  // periodic::get_total_mass, periodic.cpp:320-325 (DFS order)
+  std::vector<double> mass(m->pod.n, 0.0);
+  for (int t = 0; t < m->pod.ntrunk; t++) mass[m->pod.trunk[t].body] = m->pod.trunk[t].mass;
+  for (int l = 0; l < m->pod.nf; l++)
+    for (int h = 0; h < 3; h++) mass[m->pod.limb[l].h[h].body] = m->pod.limb[l].h[h].mass;
+  for (int i = 0; i < m->pod.n; i++) m->total_mass += mass[i];
+  *out = m;
+  return HSL_OK;
+}
+void hsl_model_free(HslModel* m) { delete m; }
+int hsl_model_dims(const HslModel* m, int32_t d[6]) {
+  if (!m) return set_err(HSL_ERR_ARG, "null model");
+  d[0] = m->pod.n; d[1] = m->pod.nf; d[2] = m->pod.nmj; d[3] = m->pod.config_dim; d[4] = m->pod.ntrunk; d[5] = m->pod.lik_index;
+  return HSL_OK;
+}
+double hsl_model_rcap(const HslModel* m) { return m ? m->pod.rcap : 0.0; }
+size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap) {
+  if (m && dst) memcpy(dst, &m->pod, cap < sizeof(HslModelPod) ? cap : sizeof(HslModelPod));
+  return sizeof(HslModelPod);
+}
+int hsl_set_tuning(HslModel* m, int fb, int minb) {
+  if (!m || (fb != 32 && fb != 64) || minb < 1 || minb > 3) return set_err(HSL_ERR_ARG, "frames per block must be 32 or 64, blocks per SM 1..3");
+  m->fb = fb;
+  m->minb = minb;
+  return HSL_OK;
+}
+int64_t hsl_launch_count(const HslModel* m) { return m ? m->launches : 0; }
+
+// ---------------------------------------------------------------- device-pointer entry
+static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                          double* d_min, double* d_max, int32_t* d_status, bool dump, cudaStream_t st) {
+  if (!m || C < 1 || n_t < 1 || !d_params) return set_err(HSL_ERR_ARG, "bad argument");
+  const int64_t nfr = C * n_t;
+  HSL_CUDA(m->cand.need(sizeof(HslCand) * C));
+  HSL_CUDA(m->ttab.need(sizeof(double) * C * (n_t + 4)));
+  HSL_CUDA(m->wframe.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmin.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmax.need(sizeof(double) * nfr));
+  int32_t* st_buf = d_status;
+  if (!st_buf) { HSL_CUDA(m->status.need(sizeof(int32_t) * C)); st_buf = (int32_t*)m->status.p; }
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.flags = flags; A.n_frames = nfr;
+  A.cand = (const HslCand*)m->cand.p; A.ttab = (const double*)m->ttab.p;
+  A.wframe = (double*)m->wframe.p; A.fmin_cfz = (double*)m->fmin.p; A.fmax_mu = (double*)m->fmax.p;
+  A.status = st_buf;
+  if (dump) {
+    const HslModelPod& P = m->pod;
+    HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * nfr));
+    HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * nfr));
+    HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * nfr));
+    HSL_CUDA(m->dump_q.need(sizeof(double) * P.config_dim * C * (n_t + 4)));
+    HSL_CUDA(m->dump_c.need((size_t)P.nf * nfr));
+    A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
+    A.q_out = (double*)m->dump_q.p; A.contacts = (uint8_t*)m->dump_c.p;
+  }
+  HSL_CUDA(hsl_launch_setup(m->pod, C, n_t, d_params, (HslCand*)m->cand.p, (double*)m->ttab.p, st_buf, st));
+  HSL_CUDA(hsl_launch_frames(m->pod, A, HSL_MODE_GAIT, dump, m->fb, m->minb, st));
+  HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, (const HslCand*)m->cand.p, nullptr, A.wframe, A.fmin_cfz, A.fmax_mu, st_buf,
+                             d_cot, d_work, d_min, d_max, st));
+  m->launches += 3;
+  return HSL_OK;
+}
+
+int hsl_eval_gaits(HslModel* m, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                   double* d_min_cfz, double* d_max_mu, int32_t* d_status, void* stream) {
+  return eval_gaits_dev(m, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, false, (cudaStream_t)stream);
+}
+
+static int ensure_stream(HslModel* m) {
+  if (!m->stream) HSL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+  return HSL_OK;
+}
+
+// transposes a component-major device dump [comp][nfr] into the caller's row-major [nfr][comp] host array
+static int fetch_transposed(HslModel* m, const void* dsrc, int comps, int64_t nfr, double* dst, cudaStream_t st) {
+  if (!dst) return HSL_OK;
+  const size_t bytes = sizeof(double) * comps * nfr;
+  HSL_CUDA(m->pin_out.need(bytes));
+  HSL_CUDA(cudaMemcpyAsync(m->pin_out.p, dsrc, bytes, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
+  const double* src = (const double*)m->pin_out.p;
+  for (int c = 0; c < comps; c++)
+    for (int64_t f = 0; f < nfr; f++) dst[f * comps + c] = src[(size_t)c * nfr + f];
+  return HSL_OK;
+}
+
+static int eval_gaits_host_impl(HslModel* m, int64_t C, int n_t, const double* params, int flags, double* cot, double* work,
+                                double* min_cfz, double* max_mu, int32_t* status, bool dump, double* traj, double* x, double* z,
+                                double* tau, uint8_t* contacts) {
+  if (!m || C < 1 || n_t < 1 || !params) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const size_t pbytes = sizeof(double) * HSL_NPARAM * C;
+  HSL_CUDA(m->pin_in.need(pbytes));
+  HSL_CUDA(m->params.need(pbytes));
+  HSL_CUDA(m->out4.need(sizeof(double) * 4 * C + sizeof(int32_t) * C));
+  memcpy(m->pin_in.p, params, pbytes);
+  HSL_CUDA(cudaMemcpyAsync(m->params.p, m->pin_in.p, pbytes, cudaMemcpyHostToDevice, st));
+  double* d4 = (double*)m->out4.p;
+  int32_t* dst = (int32_t*)(d4 + 4 * C);
+  rc = eval_gaits_dev(m, C, n_t, (const double*)m->params.p, flags, d4, d4 + C, d4 + 2 * C, d4 + 3 * C, dst, dump, st);
+  if (rc) return rc;
+  const size_t obytes = sizeof(double) * 4 * C + sizeof(int32_t) * C;
+  HSL_CUDA(m->pin_out.need(obytes));
+  HSL_CUDA(cudaMemcpyAsync(m->pin_out.p, d4, obytes, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
+  const double* h4 = (const double*)m->pin_out.p;
+  if (cot) memcpy(cot, h4, sizeof(double) * C);
+  if (work) memcpy(work, h4 + C, sizeof(double) * C);
+  if (min_cfz) memcpy(min_cfz, h4 + 2 * C, sizeof(double) * C);
+  if (max_mu) memcpy(max_mu, h4 + 3 * C, sizeof(double) * C);
+  if (status) memcpy(status, h4 + 4 * C, sizeof(int32_t) * C);
+  if (dump) {
+    const HslModelPod& P = m->pod;
+    const int64_t nfr = C * n_t;
+    if ((rc = fetch_transposed(m, m->dump_x.p, 6 * P.n, nfr, x, st))) return rc;
+    if ((rc = fetch_transposed(m, m->dump_z.p, 3 * P.nf, nfr, z, st))) return rc;
+    if ((rc = fetch_transposed(m, m->dump_tau.p, P.nmj, nfr, tau, st))) return rc;
+    if ((rc = fetch_transposed(m, m->dump_q.p, P.config_dim, C * (n_t + 4), traj, st))) return rc;
+    if (contacts) {
+      std::vector<uint8_t> tmp((size_t)P.nf * nfr);
+      HSL_CUDA(cudaMemcpy(tmp.data(), m->dump_c.p, tmp.size(), cudaMemcpyDeviceToHost));
+      for (int l = 0; l < P.nf; l++)
+        for (int64_t f = 0; f < nfr; f++) contacts[f * P.nf + l] = tmp[(size_t)l * nfr + f];
+    }
+  }
+  return HSL_OK;
+}
+
+int hsl_eval_gaits_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, double* cot, double* work,
+                        double* min_cfz, double* max_mu, int32_t* status) {
+  return eval_gaits_host_impl(m, n_cand, n_t, params, flags, cot, work, min_cfz, max_mu, status, false, nullptr, nullptr, nullptr,
+                              nullptr, nullptr);
+}
+int hsl_eval_gaits_detail_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, double* cot, double* work,
+                               double* min_cfz, double* max_mu, int32_t* status, double* traj, double* x, double* z, double* tau,
+                               uint8_t* contacts) {
+  return eval_gaits_host_impl(m, n_cand, n_t, params, flags, cot, work, min_cfz, max_mu, status, true, traj, x, z, tau, contacts);
+}
+
+int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* traj, const double* dt, double* work, double* min_cfz,
+                               double* max_mu, int32_t* status, double* x, double* z, double* tau) {
+  if (!m || C < 1 || n_t < 1 || !traj || !dt) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const int64_t nfr = C * n_t;
+  const size_t tbytes = sizeof(double) * C * (n_t + 5) * P.config_dim;
+  HSL_CUDA(m->in_a.need(tbytes));
+  HSL_CUDA(m->in_b.need(sizeof(double) * C));
+  HSL_CUDA(cudaMemcpyAsync(m->in_a.p, traj, tbytes, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(m->in_b.p, dt, sizeof(double) * C, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(m->wframe.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmin.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmax.need(sizeof(double) * nfr));
+  HSL_CUDA(m->status.need(sizeof(int32_t) * C));
+  HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * C, st));
+  HSL_CUDA(m->out4.need(sizeof(double) * 4 * C));
+  HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * nfr));
+  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * nfr));
+  HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * nfr));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.n_frames = nfr;
+  A.traj = (const double*)m->in_a.p; A.dt_in = (const double*)m->in_b.p;
+  A.wframe = (double*)m->wframe.p; A.fmin_cfz = (double*)m->fmin.p; A.fmax_mu = (double*)m->fmax.p;
+  A.status = (int32_t*)m->status.p;
+  A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
+  HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_TRAJ, true, 32, 1, st));
+  double* d4 = (double*)m->out4.p;
+  HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, nullptr, A.dt_in, A.wframe, A.fmin_cfz, A.fmax_mu, A.status, nullptr, d4 + C,
+                             d4 + 2 * C, d4 + 3 * C, st));
+  m->launches += 2;
+  HSL_CUDA(m->pin_in.need(sizeof(double) * 4 * C + sizeof(int32_t) * C));
+  double* h4 = (double*)m->pin_in.p;
+  HSL_CUDA(cudaMemcpyAsync(h4, d4, sizeof(double) * 4 * C, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaMemcpyAsync(h4 + 4 * C, m->status.p, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
+  if (work) memcpy(work, h4 + C, sizeof(double) * C);
+  if (min_cfz) memcpy(min_cfz, h4 + 2 * C, sizeof(double) * C);
+  if (max_mu) memcpy(max_mu, h4 + 3 * C, sizeof(double) * C);
+  if (status) memcpy(status, h4 + 4 * C, sizeof(int32_t) * C);
+  if ((rc = fetch_transposed(m, m->dump_x.p, 6 * P.n, nfr, x, st))) return rc;
+  if ((rc = fetch_transposed(m, m->dump_z.p, 3 * P.nf, nfr, z, st))) return rc;
+  if ((rc = fetch_transposed(m, m->dump_tau.p, P.nmj, nfr, tau, st))) return rc;
+  return HSL_OK;
+}
+
+int hsl_solve_frames_host(HslModel* m, int64_t F, const double* pos, const double* jpos, const double* jzaxis, const double* mom_rate,
+                          const double* ang_mom_rate, const double* fpos, const uint8_t* contacts, double* x, double* z, double* tau,
+                          int32_t* status) {
+  if (!m || F < 1 || !pos || !jpos || !jzaxis || !mom_rate || !ang_mom_rate || !fpos || !contacts)
+    return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const size_t nb = sizeof(double) * F * P.n * 3, fb = sizeof(double) * F * P.nf * 3, cb = (size_t)F * P.nf;
+  HSL_CUDA(m->in_a.need(5 * nb + fb + cb));
+  char* base = (char*)m->in_a.p;
+  const void* srcs[5] = {pos, jpos, jzaxis, mom_rate, ang_mom_rate};
+  for (int k = 0; k < 5; k++) HSL_CUDA(cudaMemcpyAsync(base + k * nb, srcs[k], nb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(base + 5 * nb, fpos, fb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(base + 5 * nb + fb, contacts, cb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(m->status.need(sizeof(int32_t) * F));
+  HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * F, st));
+  HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * F));
+  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * F));
+  HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * F));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = F;  // status is per frame in this mode (slot.c is forced to the frame below)
+  A.n_t = 1; A.n_frames = F;
+  A.f_pos = (const double*)(base); A.f_jpos = (const double*)(base + nb); A.f_jz = (const double*)(base + 2 * nb);
+  A.f_momrate = (const double*)(base + 3 * nb); A.f_angrate = (const double*)(base + 4 * nb);
+  A.f_fpos = (const double*)(base + 5 * nb); A.f_contacts = (const uint8_t*)(base + 5 * nb + fb);
+  A.status = (int32_t*)m->status.p;
+  A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
+  HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_FIELDS, true, 32, 1, st));
+  m->launches += 1;
+  if (status) {
+    HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
+    HSL_CUDA(cudaStreamSynchronize(st));
+  }
+  if ((rc = fetch_transposed(m, m->dump_x.p, 6 * P.n, F, x, st))) return rc;
+  if ((rc = fetch_transposed(m, m->dump_z.p, 3 * P.nf, F, z, st))) return rc;
+  if ((rc = fetch_transposed(m, m->dump_tau.p, P.nmj, F, tau, st))) return rc;
+  return HSL_OK;
+}
+
+int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms) {
+  double* d = nullptr;
+  HSL_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  HSL_CUDA(cudaEventCreate(&e0));
+  HSL_CUDA(cudaEventCreate(&e1));
+  HSL_CUDA(hsl_launch_dfma_probe(d, blocks, threads, iters, nullptr));  // warm-up
+  HSL_CUDA(cudaDeviceSynchronize());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; rep++) {
+    HSL_CUDA(cudaEventRecord(e0, nullptr));
+    HSL_CUDA(hsl_launch_dfma_probe(d, blocks, threads, iters, nullptr));
+    HSL_CUDA(cudaEventRecord(e1, nullptr));
+    HSL_CUDA(cudaEventSynchronize(e1));
+    float t = 0;
+    HSL_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    if (t < best) best = t;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (ms) *ms = best;
+  if (tflops) *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  return HSL_OK;
+}
+
+}  // extern "C"

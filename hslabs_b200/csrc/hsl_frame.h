@@ -1,0 +1,948 @@
+// Per-thread frame math of the fused gait-evaluation kernel (host + device).
+//
+// One thread owns one (frame, role) pair: role 0..NF-1 is a limb (its three
+// hinge bodies), role NF is the trunk (torso + jointless bodies).  The work of
+// one frame is split in phases separated by block barriers; each phase is a
+// function below so that hsl_kernels.cu (device) and tests/hostcheck (a serial
+// CPU emulation used to validate the very same code without a GPU) share it.
+//
+//   phase A  gait target + closed-form IK + FK of the role's bodies   (a2,a3,a5,a6)
+//            -> publish COM positions, u*sin(theta) vectors, joint angles
+//   ---- barrier ----
+//   phase B  5-point finite differences from the neighbour frames       (a7)
+//            recursive Newton-Euler pass up the limb                    (a8,a9)
+//            per-contact 3x3 level-1 block                              (a10,a11)
+//            -> publish limb wrench + contact block
+//   ---- barrier ----
+//   phase C  (trunk) level-0 6x6 Schur system over the contacts         (a11)
+//            -> publish the multiplier
+//   ---- barrier ----
+//   phase D  contact force, motor torques, positive work of the limb    (a12-a14)
+//   ---- barrier ----
+//   phase E  (trunk) per-frame work and contact statistics
+//
+// References (file:line in /root/reference): pergen.cpp:62-94,160-198,225-239,
+// 386-397; lik.cpp:151-223,316-347; model.cpp:37-62,183-201; dynrec.cpp:134-155,
+// 175-224,227-344; ftsolver.cpp:78-146,185-246; periodic.cpp:261-357.
+// The reference builds the 6n x 6n force-torque matrix B and factorises it
+// twice per frame with a sparse QR; because the bodies form a tree, B^-1 f is
+// the backward Newton-Euler recursion, and the null space added by the contact
+// columns is {dF_j = -lambda_c, dT_j = -(fpos_c - jpos_j) x lambda_c for j on the
+// chain foot -> root}.  With both torso penalties on, level 0 is "torso wrench
+// = 0" (6 equations in the contact forces) and the level-1 Hessian is block
+// diagonal 3x3 per contact, so the lexicographic least-squares solution is a
+// 6x6 symmetric solve plus one 3x3 solve per contact.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "hsl_model.h"
+
+#if defined(__CUDACC__)
+#define HSL_HD __host__ __device__ __forceinline__
+#else
+#define HSL_HD inline
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+#define HSL_MODE_GAIT 0    // candidates -> cost            (a1-a14)
+#define HSL_MODE_TRAJ 1    // joint trajectories -> cost    (a5-a14)
+#define HSL_MODE_FIELDS 2  // per-frame dynrec fields -> x,z,tau (a8-a13)
+
+#define HSL_FLAG_IGNORE_REACH 1
+
+struct HslFrameArgs {
+  int64_t n_cand;
+  int32_t n_t, flags;
+  int64_t n_frames;         // n_cand * n_t solved frames (FIELDS mode: number of frames)
+  const HslCand* cand;      // [C]            (GAIT)
+  const double* ttab;       // [C][n_t+4]     (GAIT) accumulated frame times, periodic.cpp:87-91
+  const double* traj;       // [C][n_t+5][config_dim] (TRAJ)
+  const double* dt_in;      // [C]            (TRAJ)
+  // FIELDS mode inputs, reference dynrecord layout [frame][body][3]
+  const double *f_pos, *f_jpos, *f_jz, *f_momrate, *f_angrate, *f_fpos;
+  const uint8_t* f_contacts;  // [frame][nf]
+  // per-frame outputs reduced by the finishing kernel
+  double *wframe, *fmin_cfz, *fmax_mu;  // [C][n_t]
+  int32_t* status;                      // [C], OR of HSL_ST_*
+  // optional dumps, component-major [comp][n_frames] (NULL = not written)
+  double *x, *z, *tau;
+  double* q_out;       // [config_dim][C*(n_t+4)] generated joint values (GAIT)
+  uint8_t* contacts;   // [nf][n_frames]
+};
+
+// ------------------------------------------------------------------ small vector helpers
+HSL_HD void v3_cross(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+HSL_HD void v3_cross_add(const double* a, const double* b, double* c) {
+  c[0] += a[1] * b[2] - a[2] * b[1];
+  c[1] += a[2] * b[0] - a[0] * b[2];
+  c[2] += a[0] * b[1] - a[1] * b[0];
+}
+HSL_HD double v3_dot(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+// C = A*B, column-major 3x3
+HSL_HD void m3_mul(const double* A, const double* B, double* C) {
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) C[3 * j + i] = A[i] * B[3 * j] + A[3 + i] * B[3 * j + 1] + A[6 + i] * B[3 * j + 2];
+}
+// y = A*x + t
+HSL_HD void m3_affine(const double* A, const double* x, const double* t, double* y) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) y[i] = A[i] * x[0] + A[3 + i] * x[1] + A[6 + i] * x[2] + t[i];
+}
+// Rotation the reference gets from ODE's dRFromEulerAngles copied raw into its column-major
+// affine (model.cpp:45-47, visualization.cpp:62-69): Rz(psi) Ry(theta) Rx(phi).
+HSL_HD void euler_to_R(double phi, double theta, double psi, double* R) {
+  double sphi, cphi, sth, cth, spsi, cpsi;
+  sincos(phi, &sphi, &cphi);
+  sincos(theta, &sth, &cth);
+  sincos(psi, &spsi, &cpsi);
+  R[0] = cpsi * cth;                      R[1] = spsi * cth;                      R[2] = -sth;
+  R[3] = cpsi * sth * sphi - spsi * cphi; R[4] = spsi * sth * sphi + cpsi * cphi; R[5] = cth * sphi;
+  R[6] = cpsi * sth * cphi + spsi * sphi; R[7] = spsi * sth * cphi - cpsi * sphi; R[8] = cth * cphi;
+}
+HSL_HD void wrap_pm_pi(double& a) {  // visualization.cpp:73-79
+  if (a < -M_PI) { while (a < -M_PI) a += 2 * M_PI; }
+  else if (a > M_PI) { while (a > M_PI) a -= 2 * M_PI; }
+}
+
+// ------------------------------------------------------------------ gait generator (a2)
+// Torso joint values (position + Euler angles) at time t: pergensetup::turn_torso, pergen.cpp:386-397.
+// Returns true when the orientation is unchanged from the candidate's (straight walking).
+HSL_HD bool torso_values(const HslCand& cd, double t, double* qt, double* eul) {
+  const double tv = t * cd.v;
+  double psi = 0;
+  if (cd.curvature != 0) {
+    const int s = (cd.curvature > 0) ? 1 : -1;
+    psi = s * tv / cd.max_radius;
+  }
+  if (psi == 0) {
+    qt[0] = cd.tp0[0] + tv; qt[1] = cd.tp0[1]; qt[2] = cd.tp0[2];
+    eul[0] = cd.eul[0]; eul[1] = cd.eul[1]; eul[2] = cd.eul[2];
+    return true;
+  }
+  // curved path: compose the turn with the candidate orientation and re-extract Euler angles
+  // (pergen.cpp:187-198, 377-383; visualization.cpp:81-101)
+  const double rc = 1. / cd.curvature;
+  double sp, cp;
+  sincos(psi, &sp, &cp);
+  const double tA[3] = {rc * sp, rc * (1 - cp), 0};
+  double RA[9], R1[9];
+  euler_to_R(0, 0, psi, RA);
+  m3_mul(RA, cd.R0, R1);
+  m3_affine(RA, cd.tp0, tA, qt);
+  const double th = -asin(R1[2]), ct = cos(th);
+  eul[0] = atan2(R1[5] / ct, R1[8] / ct);
+  eul[1] = th;
+  eul[2] = atan2(R1[1] / ct, R1[0] / ct);
+  return false;
+}
+// Torso body frame from its joint values: model.cpp:183-195 with the free joint (model.cpp:40-48).
+HSL_HD void torso_frame(const HslModelPod& M, const double* qt, const double* R0, double* t0) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) t0[i] = R0[i] * M.Qt[0] + R0[3 + i] * M.Qt[1] + R0[6 + i] * M.Qt[2] + (qt[i] + M.Pt[i]);
+}
+// Foot target of one limb at time t: periodicgenerator::limb_positions / turn_position, pergen.cpp:62-94,160-183.
+HSL_HD void foot_target(const HslCand& cd, int limb, double t, double* p) {
+  const double tr = t / cd.period;
+  const int t_int = (int)tr;
+  const double tf = tr - t_int;
+  const double tl = cd.ts[limb];
+  double sf;
+  if (tf < tl) sf = 0;
+  else if (tf < tl + cd.t_step) sf = (tf - tl) / cd.t_step;
+  else sf = 1;
+  double sn, cs;
+  sincos(M_PI * sf, &sn, &cs);
+  double dx = (t_int + cd.xs[limb] + (1 - cs) / 2) * cd.step_length;
+  double dy = 0;
+  const double dz = sn * sn * cd.step_height;
+  if (cd.curvature != 0) {
+    const int s = (cd.curvature > 0) ? 1 : -1;
+    const double rc = 1. / cd.curvature, rx = cd.pos0[limb][0], ry = cd.pos0[limb][1] - rc;
+    const double r = sqrt(rx * rx + ry * ry);
+    const double alpha = atan2(ry, rx), beta = -s * dx / cd.max_radius, gamma = alpha - beta / 2;
+    const double sb = 2 * sin(beta / 2);
+    double sg, cg;
+    sincos(gamma, &sg, &cg);
+    dx = r * sg * sb;
+    dy += -r * cg * sb;
+  }
+  p[0] = dx + cd.pos0[limb][0];
+  p[1] = dy + cd.pos0[limb][1];
+  p[2] = dz + cd.pos0[limb][2];
+}
+
+// ------------------------------------------------------------------ closed-form limb IK (a3)
+// lik.cpp:151-223.  pl = foot target in the hip joint frame.  Returns false when out of reach.
+HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, double* ang) {
+  const double l0 = L.ls[0], l1 = L.ls[1], l2 = L.ls[2];
+  const int s0 = L.ysign, s1 = 2 * (L.bend != 0) - 1;
+  const bool yxx = (L.kind == HSL_IK_YXX);
+  const double zoff = yxx ? pl[2] - s0 * l0 : pl[2] + l0;
+  double l = sqrt(pl[0] * pl[0] + pl[1] * pl[1] + zoff * zoff);
+  bool ok = true;
+  if (l1 + l2 - l < 0) {
+    if (ignore_reach) l = l1 + l2; else ok = false;
+  }
+  const double c = zoff / l;
+  double phi = atan2(pl[0], pl[1]);
+  double theta = yxx ? acos(c) + (1 - s0) * M_PI / 2 : acos(c) - s0 * M_PI / 2;
+  wrap_pm_pi(phi);
+  wrap_pm_pi(theta);
+  const double ll = l * l, del = l2 * l2 - l1 * l1;
+  const int sg = yxx ? s1 * s0 : s1;
+  const double beta = sg * acos((ll - del) / (2 * l1 * l));
+  const double gamma = sg * acos((ll + del) / (2 * l2 * l));
+  ang[0] = -phi;
+  ang[1] = -theta + beta;
+  ang[2] = -(beta + gamma);
+  return ok;
+}
+
+// ------------------------------------------------------------------ shared-memory view
+// All exchange arrays are [field][slot] so that consecutive lanes (= consecutive frames) hit
+// consecutive 8-byte words: conflict-free LDS.64 / STS.64.
+template <int NF, int FB>
+struct HslSmem {
+  double* pos;   // [(3*NF + ntrunk)*3][FB]   COM positions
+  double* ust;   // [(3*NF + 1)*3][FB]        u*sin(theta) of body rotations (one entry for all trunk bodies)
+  double* q;     // [3*NF][FB]                hinge angles
+  double* part;  // [NF*HSL_PART][FB]         limb -> trunk partials ; reused for limb -> trunk results after phase D
+  double* mu;    // [7][FB]                   trunk -> limb multiplier (+ validity)
+  HSL_HD static int doubles_per_slot(int ntrunk) { return (3 * NF + ntrunk) * 3 + (3 * NF + 1) * 3 + 3 * NF + NF * 19 + 7; }
+  HSL_HD void carve(double* base, int ntrunk) {
+    pos = base;
+    ust = pos + (3 * NF + ntrunk) * 3 * FB;
+    q = ust + (3 * NF + 1) * 3 * FB;
+    part = q + 3 * NF * FB;
+    mu = part + NF * 19 * FB;
+  }
+};
+#define HSL_PART 19  // Fl[3] Tl[3] W[6] Wg[3] r[3] contact
+
+// Where a thread sits.
+struct HslSlot {
+  int64_t c;     // candidate (FIELDS: 0)
+  int32_t i;     // generated-frame index 0..n_t+3 (FIELDS: frame index)
+  int32_t s;     // slot inside the block
+  int64_t fo;    // index of the solved frame in the per-frame outputs (c*n_t + i-2), valid when interior
+  bool valid;    // slot maps to an existing (candidate, frame)
+  bool interior; // frame is solved by this block (has its +-2 neighbours in the block)
+};
+
+// Limb thread state carried across phases (lives in registers on the device).
+template <bool DUMP>
+struct HslLegState {
+  double jpos[3][3], axis[3][3], pos[3][3], fpos[3];  // A -> B
+  double taup[3], w[3][3], W[6], Wg[3], r[3], qd[3];  // B -> D
+  double T[3][3], F[3][3];                            // B -> D, only read when DUMP
+  int contact, bad;
+};
+struct HslTrunkState {
+  double R0[9], t0[3];  // A -> B
+  double F0[3], T0[3];  // B -> C : trunk bodies' own share of the root wrench
+  double lam[HSL_MAX_LIMBS][3];  // C (DUMP only)
+};
+
+// ------------------------------------------------------------------ phase A
+// FK of one hinge body given its parent's frame (model.cpp:183-195): joint frame, body frame, COM, ust.
+HSL_HD void hinge_fk(const HslHinge& H, double qv, const double* Rp, const double* tp, double* Rb, double* tb,
+                     double* jpos, double* axis, double* com, double* ust) {
+  double Rj[9];
+  m3_mul(Rp, H.Rjp, Rj);
+  m3_affine(Rp, H.tjp, tp, jpos);
+  axis[0] = Rj[6]; axis[1] = Rj[7]; axis[2] = Rj[8];  // dynpart::get_joint_zaxis, dynrec.cpp:84-93
+  double sn, cs;
+  sincos(qv, &sn, &cs);
+  double Rz[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {  // Rj * Rz(q), model.cpp:49-57
+    Rz[i] = Rj[i] * cs + Rj[3 + i] * sn;
+    Rz[3 + i] = Rj[3 + i] * cs - Rj[i] * sn;
+    Rz[6 + i] = Rj[6 + i];
+  }
+  m3_mul(Rz, H.Rpb, Rb);
+  m3_affine(Rz, H.tpb, jpos, tb);
+  m3_affine(Rb, H.com, tb, com);
+  ust[0] = (Rb[5] - Rb[7]) / 2;  // dynrec.cpp:142-145: (A(2,1)-A(1,2))/2 ...
+  ust[1] = (Rb[6] - Rb[2]) / 2;
+  ust[2] = (Rb[1] - Rb[3]) / 2;
+}
+
+template <int NF, int FB, int MODE, bool DUMP>
+HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, int limb,
+                        HslLegState<DUMP>& st) {
+  const HslLimb& L = M.limb[limb];
+  st.bad = 0;
+  st.contact = 0;
+  if (MODE == HSL_MODE_FIELDS) {
+    const int64_t fb = sl.i;
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      const int b = L.h[h].body;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        st.pos[h][k] = A.f_pos[(fb * M.n + b) * 3 + k];
+        st.jpos[h][k] = A.f_jpos[(fb * M.n + b) * 3 + k];
+        st.axis[h][k] = A.f_jz[(fb * M.n + b) * 3 + k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) st.fpos[k] = A.f_fpos[(fb * M.nf + limb) * 3 + k];
+    st.contact = A.f_contacts[fb * M.nf + limb] != 0;
+    return;
+  }
+  double R0[9], t0[3], qt[3], eul[3], qa[3];
+  if (MODE == HSL_MODE_GAIT) {
+    const HslCand& cd = A.cand[sl.c];
+    const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
+    if (torso_values(cd, t, qt, eul)) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) R0[k] = cd.R0[k];
+    } else {
+      euler_to_R(eul[0], eul[1], eul[2], R0);
+    }
+    torso_frame(M, qt, R0, t0);
+    // foot target into the hip joint frame (lik.cpp:341-347), then the closed-form solver
+    double p[3], Rh[9], th[3], oj[3], d[3], pl[3];
+    foot_target(cd, limb, t, p);
+#pragma unroll
+    for (int k = 0; k < 3; k++) oj[k] = L.oatt[k];
+    double ta[3];
+    m3_affine(R0, oj, t0, ta);           // frame of the trunk body the limb hangs from
+    m3_mul(R0, L.h[0].Rjp, Rh);
+    m3_affine(R0, L.h[0].tjp, ta, th);
+#pragma unroll
+    for (int k = 0; k < 3; k++) d[k] = p[k] - th[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) pl[k] = Rh[3 * k] * d[0] + Rh[3 * k + 1] * d[1] + Rh[3 * k + 2] * d[2];
+    if (!limb_ik(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, qa)) st.bad |= HSL_ST_UNREACHABLE;
+  } else {  // HSL_MODE_TRAJ
+    const double* qrow = A.traj + (sl.c * (A.n_t + 5) + sl.i) * M.config_dim;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { qt[k] = qrow[k]; eul[k] = qrow[3 + k]; qa[k] = qrow[6 + 3 * limb + k]; }
+    euler_to_R(eul[0], eul[1], eul[2], R0);
+    torso_frame(M, qt, R0, t0);
+  }
+  // FK down the limb
+  double Rp[9], tp[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) Rp[k] = R0[k];
+  m3_affine(R0, L.oatt, t0, tp);
+  double Rb[9], tb[3];
+#pragma unroll
+  for (int h = 0; h < 3; h++) {
+    double ust[3];
+    hinge_fk(L.h[h], qa[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      sm.pos[((3 * limb + h) * 3 + k) * FB + sl.s] = st.pos[h][k];
+      sm.ust[((3 * limb + h) * 3 + k) * FB + sl.s] = ust[k];
+    }
+    sm.q[(3 * limb + h) * FB + sl.s] = qa[h];
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rp[k] = Rb[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) tp[k] = tb[k];
+  }
+  m3_affine(Rb, L.foot, tb, st.fpos);                 // odepart::get_foot_pos, visualization.cpp:565
+  st.contact = (st.fpos[2] < M.rcap + 1e-4);          // dynrec.cpp:149
+  if (DUMP && MODE == HSL_MODE_GAIT && A.q_out && sl.valid) {
+    const int64_t tot = A.n_cand * (A.n_t + 4), g = sl.c * (A.n_t + 4) + sl.i;
+#pragma unroll
+    for (int h = 0; h < 3; h++) A.q_out[(6 + 3 * limb + h) * tot + g] = qa[h];
+    if (limb == 0) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) { A.q_out[k * tot + g] = qt[k]; A.q_out[(3 + k) * tot + g] = eul[k]; }
+    }
+  }
+}
+
+template <int NF, int FB, int MODE>
+HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl,
+                          HslTrunkState& st) {
+  if (MODE == HSL_MODE_FIELDS) return;
+  double qt[3], eul[3];
+  if (MODE == HSL_MODE_GAIT) {
+    const HslCand& cd = A.cand[sl.c];
+    const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
+    if (torso_values(cd, t, qt, eul)) {
+#pragma unroll
+      for (int k = 0; k < 9; k++) st.R0[k] = cd.R0[k];
+    } else {
+      euler_to_R(eul[0], eul[1], eul[2], st.R0);
+    }
+  } else {
+    const double* qrow = A.traj + (sl.c * (A.n_t + 5) + sl.i) * M.config_dim;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { qt[k] = qrow[k]; eul[k] = qrow[3 + k]; }
+    euler_to_R(eul[0], eul[1], eul[2], st.R0);
+  }
+  torso_frame(M, qt, st.R0, st.t0);
+  for (int tb = 0; tb < M.ntrunk; tb++) {
+    double ob[3], pb[3];
+    m3_affine(st.R0, M.trunk[tb].off, st.t0, ob);
+    m3_affine(st.R0, M.trunk[tb].com, ob, pb);
+#pragma unroll
+    for (int k = 0; k < 3; k++) sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s] = pb[k];
+  }
+  sm.ust[((3 * NF) * 3 + 0) * FB + sl.s] = (st.R0[5] - st.R0[7]) / 2;
+  sm.ust[((3 * NF) * 3 + 1) * FB + sl.s] = (st.R0[6] - st.R0[2]) / 2;
+  sm.ust[((3 * NF) * 3 + 2) * FB + sl.s] = (st.R0[1] - st.R0[3]) / 2;
+}
+
+// ------------------------------------------------------------------ phase B
+// Reference point of the torso (root) wrench.  The root's torque row of B has no (jpos - pos) x F term
+// (the cross elements are only inserted when the body has a parent, dynrec.cpp:282-287), so its joint
+// torque is taken about the torso COM, which moves with the frame.
+template <int NF, int FB, int MODE>
+HSL_HD void root_ref(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, double* ref) {
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+    ref[k] = (MODE == HSL_MODE_FIELDS) ? A.f_pos[((int64_t)sl.i * M.n + M.trunk[0].body) * 3 + k]
+                                       : sm.pos[((3 * NF + 0) * 3 + k) * FB + sl.s];
+}
+// Second central difference exactly as the reference stages it (dynrec.cpp:175-224):
+//   first  = (f(s+1)-f(s-1)) * hh  at frames s+-1, scaled by the mass / inertia,
+//   second = (first(s+1)-first(s-1)) * hh.
+HSL_HD double fd2(const double* a, int s, int FB_, double hh, double scale) {
+  const double m2 = a[s - 2], c0 = a[s], p2 = a[s + 2];
+  (void)FB_;
+  const double hi = (p2 - c0) * hh * scale, lo = (c0 - m2) * hh * scale;
+  return (hi - lo) * hh;
+}
+// In-place inverse of a symmetric positive definite 3x3 stored as (00,01,02,11,12,22), via LDL^T.
+HSL_HD bool spd3_inverse(const double* H, double* W) {
+  const double d0 = H[0];
+  const double i0 = 1.0 / d0;
+  const double l10 = H[1] * i0, l20 = H[2] * i0;
+  const double d1 = H[3] - l10 * H[1];
+  const double i1 = 1.0 / d1;
+  const double l21 = (H[4] - l20 * H[1]) * i1;
+  const double d2 = H[5] - l20 * H[2] - l21 * l21 * d1;
+  const double i2 = 1.0 / d2;
+  // inverse of L (unit lower): m10 = -l10, m21 = -l21, m20 = l10*l21 - l20
+  const double m10 = -l10, m21 = -l21, m20 = l10 * l21 - l20;
+  W[5] = i2;
+  W[4] = m21 * i2;
+  W[2] = m20 * i2;
+  W[3] = i1 + m21 * m21 * i2;
+  W[1] = m10 * i1 + m21 * m20 * i2;
+  W[0] = i0 + m10 * m10 * i1 + m20 * m20 * i2;
+  const double tol = 1e-13 * (H[0] + H[3] + H[5]);
+  return (d0 > tol) && (d1 > tol) && (d2 > tol);
+}
+HSL_HD void sym3_mul(const double* W, const double* x, double* y) {
+  y[0] = W[0] * x[0] + W[1] * x[1] + W[2] * x[2];
+  y[1] = W[1] * x[0] + W[3] * x[1] + W[4] * x[2];
+  y[2] = W[2] * x[0] + W[4] * x[1] + W[5] * x[2];
+}
+
+template <int NF, int FB, int MODE, bool DUMP>
+HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, int limb,
+                        HslLegState<DUMP>& st) {
+  const HslLimb& L = M.limb[limb];
+  double f[3][3], nn[3][3];
+  if (MODE == HSL_MODE_FIELDS) {
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+      const int b = L.h[h].body;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        f[h][k] = A.f_momrate[((int64_t)sl.i * M.n + b) * 3 + k];
+        nn[h][k] = A.f_angrate[((int64_t)sl.i * M.n + b) * 3 + k];
+      }
+      f[h][2] += L.h[h].mass * M.g;
+      st.qd[h] = 0;
+    }
+  } else {
+    double hh, dt;
+    if (MODE == HSL_MODE_GAIT) { hh = A.cand[sl.c].hh; dt = A.cand[sl.c].dt; }
+    else { dt = A.dt_in[sl.c]; hh = 1. / (2 * dt); }
+#pragma unroll
+    for (int h = 0; h < 3; h++) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        f[h][k] = fd2(sm.pos + ((3 * limb + h) * 3 + k) * FB, sl.s, FB, hh, L.h[h].mass);
+        nn[h][k] = fd2(sm.ust + ((3 * limb + h) * 3 + k) * FB, sl.s, FB, hh, L.h[h].inertia);
+      }
+      f[h][2] += L.h[h].mass * M.g;  // dynrec.cpp:293-297
+      // joint rate, periodic.cpp:261-282
+      double d = sm.q[(3 * limb + h) * FB + sl.s + 1] - sm.q[(3 * limb + h) * FB + sl.s - 1];
+      if (d > M_PI) d -= 2 * M_PI; else if (d < -M_PI) d += 2 * M_PI;
+      st.qd[h] = d / (2 * dt);
+    }
+  }
+  // backward Newton-Euler recursion foot -> hip: F_j = f_j + F_child,
+  // T_j = n_j + (pos_j - jpos_j) x f_j + T_child + (jpos_child - jpos_j) x F_child   (rows of B, dynrec.cpp:227-291)
+  double F[3], T[3], d[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { F[k] = 0; T[k] = 0; }
+#pragma unroll
+  for (int h = 2; h >= 0; h--) {
+    if (h < 2) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) d[k] = st.jpos[h + 1][k] - st.jpos[h][k];
+      v3_cross_add(d, F, T);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) { d[k] = st.pos[h][k] - st.jpos[h][k]; T[k] += nn[h][k]; F[k] += f[h][k]; }
+    v3_cross_add(d, f[h], T);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { st.T[h][k] = T[k]; st.F[h][k] = F[k]; }
+  }
+  // limb wrench referred to the root reference point
+  double ref[3];
+  root_ref<NF, FB, MODE>(M, A, sm, sl, ref);
+#pragma unroll
+  for (int k = 0; k < 3; k++) d[k] = st.jpos[0][k] - ref[k];
+  v3_cross_add(d, F, T);
+  double* P = sm.part + (limb * HSL_PART) * FB + sl.s;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { P[k * FB] = F[k]; P[(3 + k) * FB] = T[k]; }
+  P[18 * FB] = st.contact ? 1.0 : 0.0;
+  // motor torque of the particular solution and its sensitivity to the contact force:
+  // tau_h = a_h . T_h - (a_h x rho_h) . lambda ,  rho_h = fpos - jpos_h     (periodic.cpp:328-343)
+  double Hs[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
+#pragma unroll
+  for (int h = 0; h < 3; h++) {
+    double rho[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) rho[k] = st.fpos[k] - st.jpos[h][k];
+    st.taup[h] = v3_dot(st.axis[h], st.T[h]);
+    v3_cross(st.axis[h], rho, st.w[h]);
+    // level-1 cost sum_k (a_k (T_k - (rho x lambda)_k))^2, component-wise weights (ftsolver.cpp:239-246)
+    const double ax = st.axis[h][0], ay = st.axis[h][1], az = st.axis[h][2];
+    const double ux[3] = {0, -ax * rho[2], ax * rho[1]};
+    const double uy[3] = {ay * rho[2], 0, -ay * rho[0]};
+    const double uz[3] = {-az * rho[1], az * rho[0], 0};
+    const double cx = ax * st.T[h][0], cy = ay * st.T[h][1], cz = az * st.T[h][2];
+    Hs[0] += uy[0] * uy[0] + uz[0] * uz[0];
+    Hs[1] += uz[0] * uz[1];
+    Hs[2] += uy[0] * uy[2];
+    Hs[3] += ux[1] * ux[1] + uz[1] * uz[1];
+    Hs[4] += ux[1] * ux[2];
+    Hs[5] += ux[2] * ux[2] + uy[2] * uy[2];
+    g[0] -= cy * uy[0] + cz * uz[0];
+    g[1] -= cx * ux[1] + cz * uz[1];
+    g[2] -= cx * ux[2] + cy * uy[2];
+  }
+  if (st.contact) {
+    if (!spd3_inverse(Hs, st.W)) st.bad |= HSL_ST_SOLVER;
+    sym3_mul(st.W, g, st.Wg);
+#pragma unroll
+    for (int k = 0; k < 3; k++) st.r[k] = st.fpos[k] - ref[k];
+#pragma unroll
+    for (int k = 0; k < 6; k++) P[(6 + k) * FB] = st.W[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { P[(12 + k) * FB] = st.Wg[k]; P[(15 + k) * FB] = st.r[k]; }
+  }
+}
+
+template <int NF, int FB, int MODE>
+HSL_HD void phase_b_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl,
+                          HslTrunkState& st) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) { st.F0[k] = 0; st.T0[k] = 0; }
+  double hh = 0;
+  if (MODE == HSL_MODE_GAIT) hh = A.cand[sl.c].hh;
+  if (MODE == HSL_MODE_TRAJ) hh = 1. / (2 * A.dt_in[sl.c]);
+  double ref[3];
+  root_ref<NF, FB, MODE>(M, A, sm, sl, ref);
+  for (int tb = 0; tb < M.ntrunk; tb++) {
+    double f[3], nn[3], pb[3], d[3];
+    if (MODE == HSL_MODE_FIELDS) {
+      const int b = M.trunk[tb].body;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        f[k] = A.f_momrate[((int64_t)sl.i * M.n + b) * 3 + k];
+        nn[k] = A.f_angrate[((int64_t)sl.i * M.n + b) * 3 + k];
+        pb[k] = A.f_pos[((int64_t)sl.i * M.n + b) * 3 + k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        f[k] = fd2(sm.pos + ((3 * NF + tb) * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].mass);
+        nn[k] = fd2(sm.ust + ((3 * NF) * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].inertia);
+        pb[k] = sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s];
+      }
+    }
+    f[2] += M.trunk[tb].mass * M.g;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { d[k] = pb[k] - ref[k]; st.F0[k] += f[k]; st.T0[k] += nn[k]; }
+    v3_cross_add(d, f, st.T0);
+  }
+}
+
+// ------------------------------------------------------------------ phase C (trunk)
+// LDL^T solve of a symmetric positive definite 6x6 (lower triangle in S[i][j], i>=j). Returns false on breakdown.
+HSL_HD bool spd6_solve(double S[6][6], double* b) {
+  double dinv[6], dd[6];
+  double tr = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) tr += S[i][i];
+  const double tol = 1e-13 * tr;
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    // column j: u_i = S_ij - sum_k L_ik (L_jk d_k) for i >= j ; d_j = u_j ; L_ij = u_i / d_j
+    double ld[6];
+#pragma unroll
+    for (int k = 0; k < j; k++) ld[k] = S[j][k] * dd[k];
+    double d = S[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= S[j][k] * ld[k];
+    ok = ok && (d > tol);
+    dd[j] = d;
+    dinv[j] = 1.0 / d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      double v = S[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= S[i][k] * ld[k];
+      S[i][j] = v * dinv[j];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int k = 0; k < i; k++) b[i] -= S[i][k] * b[k];
+#pragma unroll
+  for (int i = 0; i < 6; i++) b[i] *= dinv[i];
+#pragma unroll
+  for (int i = 5; i >= 0; i--)
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) b[i] -= S[k][i] * b[k];
+  return ok;
+}
+
+template <int NF, int FB, int MODE, bool DUMP>
+HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl,
+                         HslTrunkState& st) {
+  int bad = 0;
+  double b[6] = {st.F0[0], st.F0[1], st.F0[2], st.T0[0], st.T0[1], st.T0[2]};
+  double S[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) S[i][j] = 0;
+  double v[6] = {0, 0, 0, 0, 0, 0};
+  int nc = 0;
+  double rA[3] = {0, 0, 0}, rB[3] = {0, 0, 0};
+#pragma unroll
+  for (int l = 0; l < NF; l++) {
+    const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+#pragma unroll
+    for (int k = 0; k < 6; k++) b[k] += P[k * FB];
+    if (P[18 * FB] != 0.0) {
+      double W[6], Wg[3], r[3];
+#pragma unroll
+      for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
+      if (nc == 0) { rA[0] = r[0]; rA[1] = r[1]; rA[2] = r[2]; }
+      if (nc == 1) { rB[0] = r[0]; rB[1] = r[1]; rB[2] = r[2]; }
+      nc++;
+      // S += A W A^T with A = [I ; [r]x]:  K = [r]x W ; blocks [[W, K^T],[K, [r]x K^T]]
+      const double Wc[3][3] = {{W[0], W[1], W[2]}, {W[1], W[3], W[4]}, {W[2], W[4], W[5]}};
+      double K[3][3];  // K[i][j] = (r x W_col_j)_i
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        K[0][j] = r[1] * Wc[2][j] - r[2] * Wc[1][j];
+        K[1][j] = r[2] * Wc[0][j] - r[0] * Wc[2][j];
+        K[2][j] = r[0] * Wc[1][j] - r[1] * Wc[0][j];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) S[i][j] += Wc[i][j];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) S[3 + i][j] += K[i][j];
+      // bottom-right: column j of [r]x K^T = r x (row j of K); symmetric, fill lower part
+      {
+        const double c0[3] = {r[1] * K[0][2] - r[2] * K[0][1], r[2] * K[0][0] - r[0] * K[0][2], r[0] * K[0][1] - r[1] * K[0][0]};
+        const double c1[3] = {r[1] * K[1][2] - r[2] * K[1][1], r[2] * K[1][0] - r[0] * K[1][2], r[0] * K[1][1] - r[1] * K[1][0]};
+        const double c2[3] = {r[1] * K[2][2] - r[2] * K[2][1], r[2] * K[2][0] - r[0] * K[2][2], r[0] * K[2][1] - r[1] * K[2][0]};
+        S[3][3] += c0[0]; S[4][3] += c0[1]; S[5][3] += c0[2];
+        S[4][4] += c1[1]; S[5][4] += c1[2];
+        S[5][5] += c2[2];
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) v[k] += Wg[k];
+      v3_cross_add(r, Wg, v + 3);
+    }
+  }
+  double mu[6] = {0, 0, 0, 0, 0, 0};
+  if (nc >= 2) {
+    if (nc == 2) {
+      // two contacts: level 0 has rank 5; the unreachable wrench direction is n = (rA x d, d), d = rA - rB
+      // (torque about the line through both contact points).  Project it out of b and regularise S with it.
+      double d[3] = {rA[0] - rB[0], rA[1] - rB[1], rA[2] - rB[2]}, nf_[3];
+      v3_cross(rA, d, nf_);
+      const double nn = 1.0 / sqrt(v3_dot(nf_, nf_) + v3_dot(d, d));
+      const double nv[6] = {nf_[0] * nn, nf_[1] * nn, nf_[2] * nn, d[0] * nn, d[1] * nn, d[2] * nn};
+      double pb = 0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) pb += nv[k] * b[k];
+#pragma unroll
+      for (int k = 0; k < 6; k++) mu[k] = -(b[k] - pb * nv[k] + v[k]);
+#pragma unroll
+      for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) S[i][j] += nv[i] * nv[j];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 6; k++) mu[k] = -(b[k] + v[k]);
+    }
+    if (!spd6_solve(S, mu)) bad |= HSL_ST_SOLVER;
+  } else {
+    bad |= HSL_ST_FEW_CONTACTS;
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) sm.mu[k * FB + sl.s] = mu[k];
+  sm.mu[6 * FB + sl.s] = (nc >= 2) ? 1.0 : 0.0;
+
+  if (DUMP && A.x) {
+    // joint forces / torques of the trunk bodies (rows of x for bodies without a limb):
+    // F_b = sum over the subtree of f - sum of contact forces in the subtree, same for torques about jpos_b.
+    double lam[NF][3];
+    bool con[NF];
+#pragma unroll
+    for (int l = 0; l < NF; l++) {
+      const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+      con[l] = (P[18 * FB] != 0.0) && (nc >= 2);
+      lam[l][0] = lam[l][1] = lam[l][2] = 0;
+      if (con[l]) {
+        double W[6], y[3], r[3], Wy[3];
+#pragma unroll
+        for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
+#pragma unroll
+        for (int k = 0; k < 3; k++) r[k] = P[(15 + k) * FB];
+        v3_cross(mu + 3, r, y);
+#pragma unroll
+        for (int k = 0; k < 3; k++) y[k] += mu[k];
+        sym3_mul(W, y, Wy);
+#pragma unroll
+        for (int k = 0; k < 3; k++) lam[l][k] = -(P[(12 + k) * FB] + Wy[k]);
+      }
+    }
+    double hh = 0;
+    if (MODE == HSL_MODE_GAIT) hh = A.cand[sl.c].hh;
+    if (MODE == HSL_MODE_TRAJ) hh = 1. / (2 * A.dt_in[sl.c]);
+    double ref[3];
+    root_ref<NF, FB, MODE>(M, A, sm, sl, ref);
+    for (int tb = 0; tb < M.ntrunk; tb++) {
+      // reference point: torso -> its COM (see root_ref) ; jointless body -> its frame origin (= jpos)
+      double jp[3];
+      if (tb == 0) { jp[0] = ref[0]; jp[1] = ref[1]; jp[2] = ref[2]; }
+      else if (MODE == HSL_MODE_FIELDS) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) jp[k] = A.f_jpos[((int64_t)sl.i * M.n + M.trunk[tb].body) * 3 + k];
+      } else m3_affine(st.R0, M.trunk[tb].off, st.t0, jp);
+      double Fb[3] = {0, 0, 0}, Tb[3] = {0, 0, 0};
+      for (int t2 = 0; t2 < M.ntrunk; t2++) {  // trunk bodies in the subtree of tb
+        int a = t2;
+        while (a > tb) a = M.trunk[a].parent_trunk;
+        if (a != tb) continue;
+        double f[3], nn[3], pb[3], d[3];
+        if (MODE == HSL_MODE_FIELDS) {
+          const int bb = M.trunk[t2].body;
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            f[k] = A.f_momrate[((int64_t)sl.i * M.n + bb) * 3 + k];
+            nn[k] = A.f_angrate[((int64_t)sl.i * M.n + bb) * 3 + k];
+            pb[k] = A.f_pos[((int64_t)sl.i * M.n + bb) * 3 + k];
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; k++) {
+            f[k] = fd2(sm.pos + ((3 * NF + t2) * 3 + k) * FB, sl.s, FB, hh, M.trunk[t2].mass);
+            nn[k] = fd2(sm.ust + ((3 * NF) * 3 + k) * FB, sl.s, FB, hh, M.trunk[t2].inertia);
+            pb[k] = sm.pos[((3 * NF + t2) * 3 + k) * FB + sl.s];
+          }
+        }
+        f[2] += M.trunk[t2].mass * M.g;
+#pragma unroll
+        for (int k = 0; k < 3; k++) { d[k] = pb[k] - jp[k]; Fb[k] += f[k]; Tb[k] += nn[k]; }
+        v3_cross_add(d, f, Tb);
+      }
+#pragma unroll
+      for (int l = 0; l < NF; l++) {  // limbs hanging in the subtree of tb
+        int a = M.limb[l].attach;
+        while (a > tb) a = M.trunk[a].parent_trunk;
+        if (a != tb) continue;
+        const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+        double Fl[3], d[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { Fl[k] = P[k * FB]; Fb[k] += Fl[k]; Tb[k] += P[(3 + k) * FB]; d[k] = ref[k] - jp[k]; }
+        v3_cross_add(d, Fl, Tb);  // move the limb wrench from the root reference point to jp
+        if (con[l]) {
+          double rr[3];
+#pragma unroll
+          for (int k = 0; k < 3; k++) { rr[k] = P[(15 + k) * FB] + ref[k] - jp[k]; Fb[k] -= lam[l][k]; }
+          double cr[3];
+          v3_cross(rr, lam[l], cr);
+#pragma unroll
+          for (int k = 0; k < 3; k++) Tb[k] -= cr[k];
+        }
+      }
+      const int bb = M.trunk[tb].body;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        A.x[(int64_t)(3 * bb + k) * A.n_frames + sl.fo] = Fb[k];
+        A.x[(int64_t)(3 * (M.n + bb) + k) * A.n_frames + sl.fo] = Tb[k];
+      }
+    }
+  }
+  return bad;
+}
+
+// ------------------------------------------------------------------ phase D (limb)
+template <int NF, int FB, int MODE, bool DUMP>
+HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, int limb,
+                        HslLegState<DUMP>& st) {
+  const HslLimb& L = M.limb[limb];
+  double lam[3] = {0, 0, 0};
+  const bool con = st.contact && (sm.mu[6 * FB + sl.s] != 0.0);
+  if (con) {
+    double mu[6], y[3], Wy[3];
+#pragma unroll
+    for (int k = 0; k < 6; k++) mu[k] = sm.mu[k * FB + sl.s];
+    v3_cross(mu + 3, st.r, y);  // A_c^T mu = mu_f + mu_t x r
+#pragma unroll
+    for (int k = 0; k < 3; k++) y[k] += mu[k];
+    sym3_mul(st.W, y, Wy);
+#pragma unroll
+    for (int k = 0; k < 3; k++) lam[k] = -(st.Wg[k] + Wy[k]);
+  }
+  double work = 0, tau[3];
+#pragma unroll
+  for (int h = 0; h < 3; h++) {
+    tau[h] = st.taup[h] - v3_dot(st.w[h], lam);
+    const double dw = tau[h] * st.qd[h];
+    work += (dw > 0) ? dw : 0;  // periodic.cpp:291-304
+  }
+  double cfz = 1e300, mu_f = -1e300;
+  if (con) {  // periodic.cpp:347-357, over the feet that are on the ground
+    cfz = lam[2];
+    mu_f = sqrt(lam[0] * lam[0] + lam[1] * lam[1]) / lam[2];
+  }
+  double* P = sm.part + (limb * HSL_PART) * FB + sl.s;
+  P[0] = work;
+  P[FB] = cfz;
+  P[2 * FB] = mu_f;
+  if (DUMP) {
+    const int64_t nfr = A.n_frames, fo = sl.fo;
+    if (A.tau) {
+#pragma unroll
+      for (int h = 0; h < 3; h++) A.tau[(int64_t)(3 * limb + h) * nfr + fo] = tau[h];
+    }
+    if (A.z) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) A.z[(int64_t)(3 * limb + k) * nfr + fo] = lam[k];
+    }
+    if (A.contacts) A.contacts[(int64_t)limb * nfr + fo] = (uint8_t)st.contact;
+    if (A.x) {
+#pragma unroll
+      for (int h = 0; h < 3; h++) {
+        const int b = L.h[h].body;
+        double rho[3], cr[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) rho[k] = st.fpos[k] - st.jpos[h][k];
+        v3_cross(rho, lam, cr);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          A.x[(int64_t)(3 * b + k) * nfr + fo] = st.F[h][k] - lam[k];
+          A.x[(int64_t)(3 * (M.n + b) + k) * nfr + fo] = st.T[h][k] - cr[k];
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase E (trunk)
+template <int NF, int FB>
+HSL_HD void phase_e_trunk(const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl) {
+  double work = 0, cfz = 1e300, mu = -1e300;
+#pragma unroll
+  for (int l = 0; l < NF; l++) {
+    const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+    work += P[0];
+    cfz = fmin(cfz, P[FB]);
+    mu = fmax(mu, P[2 * FB]);
+  }
+  if (A.wframe) A.wframe[sl.fo] = work;
+  if (A.fmin_cfz) A.fmin_cfz[sl.fo] = cfz;
+  if (A.fmax_mu) A.fmax_mu[sl.fo] = mu;
+}
+
+// ------------------------------------------------------------------ candidate setup (a1)
+// pgssweeper::setup_pergen / partial_setup_pergen / setup_foot_shift / shift_pos0 (pergen.cpp:453-507),
+// periodicgenerator::set_step_duration / compute_max_radius (pergen.cpp:30-51,144-154),
+// periodic::record_trajectory time base (periodic.cpp:84-91).  p = 13 candidate scalars (include/hsl.h).
+HSL_HD void setup_candidate(const HslModelPod& M, const double* p, int n_t, HslCand& cd, double* ttab) {
+  cd.status = 0;
+  cd.pad = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { cd.tp0[k] = p[k]; cd.eul[k] = p[3 + k]; }
+  euler_to_R(p[3], p[4], p[5], cd.R0);
+  const double f = p[6];
+  cd.period = p[7]; cd.step_length = p[8]; cd.step_height = p[9]; cd.curvature = p[10];
+  const int shift_type = (int)p[11];
+  const double shift_value = p[12];
+  const int n = M.nf;
+  if (!(f >= 0 && f <= 1) || !(cd.period > 0) || n_t < 1) cd.status |= HSL_ST_BAD_PARAMS;
+  cd.t_step = f * (1. / 2 - 1. / n) + 1. / n;
+  cd.v = cd.step_length / cd.period;
+  cd.dt = cd.period / n_t;
+  cd.hh = 1. / (2 * cd.dt);
+  double t0[3];
+  torso_frame(M, cd.tp0, cd.R0, t0);
+  double lat[3] = {0, 0, 0};
+  if (shift_type == 0) {  // A_ground(torso) * (0, shift, 0, 1): includes the torso translation (pergen.cpp:485-488)
+    const double sh[3] = {0, shift_value, 0};
+    m3_affine(cd.R0, sh, t0, lat);
+  }
+  const int jmax = n / 2, z = (jmax == 1) ? 1 : jmax - 1;
+  cd.max_radius = 0;
+  for (int i = 0; i < n; i++) {
+    const HslLimb& L = M.limb[i];
+    double ta[3], hp[3];
+    m3_affine(cd.R0, L.oatt, t0, ta);
+    m3_affine(cd.R0, L.h[0].tjp, ta, hp);  // hip position = origin of the top link's frame (lik.cpp:357-360)
+    if (shift_type == 0) {
+      const double sgn = (i % 2) ? -1.0 : 1.0;
+#pragma unroll
+      for (int k = 0; k < 3; k++) hp[k] += sgn * lat[k];
+    } else if (shift_type == 1) {
+      const double ff = shift_value / sqrt(hp[0] * hp[0] + hp[1] * hp[1]);
+      hp[0] += hp[0] * ff;
+      hp[1] += hp[1] * ff;
+    }
+    cd.pos0[i][0] = hp[0]; cd.pos0[i][1] = hp[1]; cd.pos0[i][2] = M.rcap;
+    const int k = L.pg_index, grp = k / jmax, j = k % jmax;
+    cd.ts[i] = j * (1. / 2 - cd.t_step) / z + double(grp) / 2;
+    cd.xs[i] = cd.ts[i] + cd.t_step / 2 - 1. / 2;
+    if (cd.curvature != 0) {
+      const double dy = hp[1] - 1. / cd.curvature;
+      const double rad = sqrt(hp[0] * hp[0] + dy * dy + M.rcap * M.rcap);
+      if (rad > cd.max_radius) cd.max_radius = rad;
+    }
+  }
+  for (int i = n; i < HSL_MAX_LIMBS; i++) { cd.pos0[i][0] = cd.pos0[i][1] = cd.pos0[i][2] = 0; cd.ts[i] = cd.xs[i] = 0; }
+  if (ttab) {
+    double t = 0;
+    for (int i = 0; i < n_t + 4; i++) { ttab[i] = t; t += cd.dt; }
+  }
+}

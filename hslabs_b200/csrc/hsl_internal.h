@@ -1,0 +1,17 @@
+// Internal launcher interface between the C-ABI layer and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "hsl_frame.h"
+#include "hsl_model.h"
+
+cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int minb, cudaStream_t st);
+cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
+                             int32_t* status, cudaStream_t st);
+cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
+                              const double* wframe, const double* fmin, const double* fmax, const int32_t* status, double* cot,
+                              double* work, double* min_cfz, double* max_mu, cudaStream_t st);
+cudaError_t hsl_launch_dfma_probe(double* out, int blocks, int threads, int iters, cudaStream_t st);
+
+// hsl_model_load.cpp
+int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int errlen);

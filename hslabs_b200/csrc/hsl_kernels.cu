@@ -1,0 +1,200 @@
+// sm_100a kernels of the gait-evaluation hot path.
+//
+//   hsl_setup_kernel   one thread per candidate: candidate constants + frame-time table   (a1, a4)
+//   hsl_frames_kernel  one thread per (frame, role): phases A-E of hsl_frame.h             (a2-a14)
+//   hsl_finish_kernel  one warp per candidate: work = sum_f (power_f * dt), COT, statistics (a14)
+//
+// Block layout of hsl_frames_kernel: FB frame slots x (NF+1) roles, thread = role*FB + slot, so a warp
+// is one role over 32 consecutive frames of (normally) one candidate.  Blocks overlap by 4 slots: the
+// outer two slots on each side only run phase A (they are the +-2 finite-difference halo of their
+// neighbours) and are solved as interior slots of the adjacent block.  Model constants arrive as a
+// __grid_constant__ parameter, i.e. in the constant bank, and are indexed by the warp-uniform role.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "hsl_frame.h"
+#include "hsl_internal.h"
+
+template <int NF, int FB, int MODE, bool DUMP, int MINB>
+__global__ void __launch_bounds__((NF + 1) * FB, MINB)
+hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
+  extern __shared__ double hsl_smem_raw[];
+  HslSmem<NF, FB> sm;
+  sm.carve(hsl_smem_raw, M.ntrunk);
+  const int role = threadIdx.x / FB;
+  HslSlot sl;
+  sl.s = threadIdx.x % FB;
+  if (MODE == HSL_MODE_FIELDS) {
+    const int64_t g = (int64_t)blockIdx.x * FB + sl.s;
+    sl.valid = g < A.n_frames;
+    sl.i = (int32_t)(sl.valid ? g : A.n_frames - 1);
+    sl.c = sl.i;  // status is per frame in this mode
+    sl.fo = sl.i;
+    sl.interior = sl.valid;
+  } else {
+    const int per = A.n_t + 4;
+    const int64_t g = (int64_t)blockIdx.x * (FB - 4) + sl.s;
+    sl.c = g / per;
+    sl.i = (int32_t)(g - sl.c * per);
+    sl.valid = sl.c < A.n_cand;
+    if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+    sl.interior = sl.valid && sl.s >= 2 && sl.s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+    sl.fo = sl.c * A.n_t + (sl.i - 2);
+  }
+  HslLegState<DUMP> lst;
+  HslTrunkState tst;
+  int bad = 0;
+  if (role < NF) {
+    phase_a_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+    bad = lst.bad;
+  } else {
+    phase_a_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+  }
+  __syncthreads();
+  if (sl.interior) {
+    if (role < NF) {
+      phase_b_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+      bad |= lst.bad;
+    } else {
+      phase_b_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+    }
+  }
+  __syncthreads();
+  if (sl.interior && role == NF) bad |= phase_c_trunk<NF, FB, MODE, DUMP>(M, A, sm, sl, tst);
+  __syncthreads();
+  if (sl.interior && role < NF) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+  __syncthreads();
+  if (sl.interior && role == NF) phase_e_trunk<NF, FB>(A, sm, sl);
+  if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
+}
+
+__global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
+                                 HslCand* __restrict__ cand, double* __restrict__ ttab, int32_t* __restrict__ status) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cand) return;
+  double p[HSL_NPARAM];
+#pragma unroll
+  for (int k = 0; k < HSL_NPARAM; k++) p[k] = params[c * HSL_NPARAM + k];
+  HslCand cd;
+  setup_candidate(M, p, n_t, cd, ttab + c * (n_t + 4));
+  cand[c] = cd;
+  status[c] = cd.status;
+}
+
+// One warp per candidate.  periodic::work_over_period (periodic.cpp:285-307) and modelplayer::measure_cot
+// (player.cpp:269-285): work = sum_frames (sum_motors max(tau*qdot,0)) * dt ; COT = work / (total mass * step length).
+__global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, const HslCand* __restrict__ cand,
+                                  const double* __restrict__ dt_in, const double* __restrict__ wframe,
+                                  const double* __restrict__ fmin_in, const double* __restrict__ fmax_in,
+                                  const int32_t* __restrict__ status, double* __restrict__ cot, double* __restrict__ work,
+                                  double* __restrict__ min_cfz, double* __restrict__ max_mu) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x & 31;
+  if (c >= n_cand) return;
+  const double dt = cand ? cand[c].dt : dt_in[c];
+  double w = 0, mn = 1e10, mx = -1e10;  // periodic.cpp:380
+  for (int f = lane; f < n_t; f += 32) {
+    w += wframe[c * n_t + f] * dt;
+    mn = fmin(mn, fmin_in[c * n_t + f]);
+    mx = fmax(mx, fmax_in[c * n_t + f]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    w += __shfl_xor_sync(0xffffffffu, w, o);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if (lane == 0) {
+    const int st = status ? status[c] : 0;
+    const bool fatal = (st & (HSL_ST_BAD_PARAMS | HSL_ST_UNREACHABLE)) != 0;  // the reference exit(1)s here
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    if (work) work[c] = fatal ? nanv : w;
+    if (cot) cot[c] = (fatal || !cand) ? nanv : w / (total_mass * cand[c].step_length);
+    if (min_cfz) min_cfz[c] = fatal ? nanv : mn;
+    if (max_mu) max_mu[c] = fatal ? nanv : mx;
+  }
+}
+
+// FP64 FMA throughput probe: register-resident dependent chains, 8 per thread.  Used by bench.py for the
+// roofline denominator of this FP64-bound path (MEASURED_PEAKS.json has no FP64 figure).
+__global__ void hsl_dfma_probe_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// ------------------------------------------------------------------ launchers
+namespace {
+template <int NF, int FB, int MODE, bool DUMP, int MINB = 1>
+cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
+  const size_t smem = (size_t)HslSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
+  auto kern = hsl_frames_kernel<NF, FB, MODE, DUMP, MINB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int64_t blocks;
+  if (MODE == HSL_MODE_FIELDS) blocks = (A.n_frames + FB - 1) / FB;
+  else {
+    const int64_t slots = A.n_cand * (A.n_t + 4);
+    blocks = (slots - 4 + (FB - 4) - 1) / (FB - 4);  // interior ranges [b(FB-4)+2, b(FB-4)+FB-2) must cover [2, slots-2)
+    if (blocks < 1) blocks = 1;
+  }
+  if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)blocks, (NF + 1) * FB, smem, st>>>(M, A);
+  return cudaGetLastError();
+}
+template <int NF, int FB>
+cudaError_t launch_frames_nf(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, cudaStream_t st) {
+  (void)dump;
+  if (mode == HSL_MODE_GAIT) return launch_frames_t<NF, FB, HSL_MODE_GAIT, true>(M, A, st);
+  if (mode == HSL_MODE_TRAJ) return launch_frames_t<NF, FB, HSL_MODE_TRAJ, true>(M, A, st);
+  return launch_frames_t<NF, FB, HSL_MODE_FIELDS, true>(M, A, st);
+}
+}  // namespace
+
+// Cost-only evaluation (the headline path) comes in a few occupancy variants: fb = frame slots per block,
+// minb = resident blocks per SM the register allocation is bounded for.
+template <int NF>
+cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int minb, cudaStream_t st) {
+  if (fb == 64) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 1>(M, A, st);
+  if (minb >= 3) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 3>(M, A, st);
+  if (minb == 2) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 2>(M, A, st);
+  return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 1>(M, A, st);
+}
+
+cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int minb, cudaStream_t st) {
+  if (M.nf == 6) {
+    if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<6>(M, A, fb, minb, st);
+    return launch_frames_nf<6, 32>(M, A, mode, dump, st);
+  }
+  if (M.nf == 4) {
+    if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<4>(M, A, fb, minb, st);
+    return launch_frames_nf<4, 32>(M, A, mode, dump, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
+                             int32_t* status, cudaStream_t st) {
+  const int tpb = 128;
+  hsl_setup_kernel<<<(unsigned)((n_cand + tpb - 1) / tpb), tpb, 0, st>>>(M, n_cand, n_t, params, cand, ttab, status);
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
+                              const double* wframe, const double* fmin_in, const double* fmax_in, const int32_t* status, double* cot,
+                              double* work, double* min_cfz, double* max_mu, cudaStream_t st) {
+  const int tpb = 256;
+  const int64_t threads = n_cand * 32;
+  hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
+                                                                         fmax_in, status, cot, work, min_cfz, max_mu);
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_dfma_probe(double* out, int blocks, int threads, int iters, cudaStream_t st) {
+  hsl_dfma_probe_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+  return cudaGetLastError();
+}

@@ -1,0 +1,91 @@
+/* hsl.h -- C ABI of the B200 gait-evaluation library (libhsl_b200.so).
+ *
+ * The reference (underactuated/HSLabs) has no plugin / FFI boundary: its evaluation path is a set of
+ * C++ member functions linked into one binary.  These entry points are what a cgo/ctypes/
+ * C++ binding of that path would bind; each one names the reference interface it replaces.  All
+ * pointers are plain; "_host" entries take host buffers and do the host<->device copies themselves,
+ * the others take device pointers and a cudaStream_t (passed as void*).  Every function returns 0 on
+ * success or a negative HSL_ERR_* code; hsl_last_error() gives the message.  Per-candidate failures the
+ * reference turns into exit(1) are reported in a status array (HSL_ST_* bits) and NaN results.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry fails with HSL_ERR_CUDA.
+ */
+#ifndef HSL_H
+#define HSL_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSL_NPARAM 13
+/* candidate row (doubles), the scalars of pgsconfigparams (pergen.h:137-146):
+ *  [0..2] torso_pos  [3..5] torso_angles  [6] step_duration  [7] period  [8] step_length
+ *  [9] step_height  [10] curvature  [11] foot shift type (-1 none, 0 lateral, 1 radial)  [12] shift value */
+
+#define HSL_OK 0
+#define HSL_ERR_ARG -1
+#define HSL_ERR_XML -2          /* unreadable / not a <mujoco> file (model.cpp:230-231) */
+#define HSL_ERR_UNSUPPORTED -3  /* topology / model outside what the path handles (lik.cpp:12-16) */
+#define HSL_ERR_CUDA -4
+#define HSL_ERR_NOMEM -5
+
+#define HSL_ST_BAD_PARAMS 1   /* step_duration outside [0,1] (pergen.cpp:31) */
+#define HSL_ST_UNREACHABLE 2  /* IK target out of reach (lik.cpp:161-164) */
+#define HSL_ST_SOLVER 4       /* contact system not positive definite (ftsolver.cpp:208-232) */
+#define HSL_ST_FEW_CONTACTS 8 /* fewer than two feet on the ground */
+
+#define HSL_FLAG_IGNORE_REACH 1 /* liksolver::set_ignore_reach_flag(true) (lik.cpp:142-146) */
+
+typedef struct HslModel HslModel;
+
+/* kinematicmodel::load_fromxml + liksolver + periodic::set_dynparts (model.cpp:224-242, lik.cpp:7-78,
+ * periodic.cpp:34-58): parse the MuJoCo-style XML, flatten it and keep it resident for the kernels. */
+int hsl_model_load_xml(const char* xml_path, HslModel** out);
+void hsl_model_free(HslModel* m);
+/* dims[6] = n bodies, nf feet, nmj motor joints, config_dim, trunk bodies, lik index (0 myant,1 hexapod,2 spider) */
+int hsl_model_dims(const HslModel* m, int32_t dims[6]);
+double hsl_model_rcap(const HslModel* m); /* liksolver::get_rcap (lik.h:51) */
+/* packed model block (HslModelPod of hslabs_b200/csrc/hsl_model.h); returns its size, copies min(size,cap) bytes */
+size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap);
+const char* hsl_last_error(void);
+int hsl_device_count(void);
+
+/* modelplayer::measure_cot over a batch (player.cpp:269-285 inside the sweep of player.cpp:311-321):
+ * candidates -> cost of transport, work per period, min contact z-force, max friction ratio.
+ * d_params [n_cand][13], outputs [n_cand] (any output may be NULL); all DEVICE pointers. */
+int hsl_eval_gaits(HslModel* m, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                   double* d_min_cfz, double* d_max_mu, int32_t* d_status, void* stream);
+/* same, HOST pointers (pinned staging inside). */
+int hsl_eval_gaits_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, double* cot, double* work,
+                        double* min_cfz, double* max_mu, int32_t* status);
+/* periodic::record_trajectory + compute_torques_over_period with everything kept (periodic.cpp:77-96,
+ * 377-391; forcetorquesolver::solve_forcetorques x/z, ftsolver.cpp:78-102).  HOST pointers, row-major:
+ * traj [n_cand][n_t+4][config_dim] (frames 0..n_t+3), x [n_cand][n_t][6n], z [n_cand][n_t][3nf],
+ * tau [n_cand][n_t][nmj], contacts [n_cand][n_t][nf] -- solved frames 2..n_t+1 in order.  Any may be NULL. */
+int hsl_eval_gaits_detail_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, double* cot, double* work,
+                               double* min_cfz, double* max_mu, int32_t* status, double* traj, double* x, double* z,
+                               double* tau, uint8_t* contacts);
+/* periodic::compute_dynrecs .. work_over_period on supplied joint trajectories (periodic.cpp:149-160,
+ * 192-202, 285-307): traj [n_cand][n_t+5][config_dim], dt [n_cand]; outputs as above (cot is not defined). */
+int hsl_eval_trajectories_host(HslModel* m, int64_t n_cand, int n_t, const double* traj, const double* dt, double* work,
+                               double* min_cfz, double* max_mu, int32_t* status, double* x, double* z, double* tau);
+/* forcetorquesolver::solve_forcetorques + periodic::get_motor_torques on populated dynrecords
+ * (ftsolver.cpp:78-102, periodic.cpp:328-343, dynrec.h:76-106), both torso penalties on.
+ * Inputs [n_frames][n][3] (pos, jpos, jzaxis, mom_rate, ang_mom_rate), fpos [n_frames][nf][3],
+ * contacts [n_frames][nf]; outputs x [n_frames][6n], z [n_frames][3nf], tau [n_frames][nmj],
+ * status [n_frames].  HOST pointers. */
+int hsl_solve_frames_host(HslModel* m, int64_t n_frames, const double* pos, const double* jpos, const double* jzaxis,
+                          const double* mom_rate, const double* ang_mom_rate, const double* fpos, const uint8_t* contacts,
+                          double* x, double* z, double* tau, int32_t* status);
+
+/* tuning / measurement helpers */
+int hsl_set_tuning(HslModel* m, int fb, int minb);            /* frame slots per block (32|64), resident blocks per SM the cost-only kernel is register-bounded for (1..3) */
+int64_t hsl_launch_count(const HslModel* m);                  /* kernels launched through this handle so far */
+int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms); /* FP64 FMA throughput of the device */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,42 @@
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODELS = os.path.join(ROOT, "hslabs_b200", "models")
+PRESETS = os.path.join(MODELS, "pgs_presets.txt")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """The CPU oracle (test infrastructure)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    from oracle import orc as o
+    return o
+
+
+@pytest.fixture(scope="session")
+def hsl():
+    import hslabs_b200
+    return hslabs_b200
+
+
+def model_xml(name):
+    return os.path.join(MODELS, name if name.endswith(".xml") else name + ".xml")
+
+
+def rel_err(a, b):
+    import numpy as np
+    a = np.asarray(a, float)
+    b = np.asarray(b, float)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))

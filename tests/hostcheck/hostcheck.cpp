@@ -1,0 +1,202 @@
+// TEST INFRASTRUCTURE ONLY.  Serial CPU emulation of hsl_frames_kernel: the per-thread phase functions
+// of hslabs_b200/csrc/hsl_frame.h are compiled for the host and run slot by slot, role by role, with a
+// plain array standing in for shared memory and a loop boundary standing in for each block barrier.
+// This lets the CPU-only test tier check the exact arithmetic the CUDA kernels run (same source) against
+// the oracle.  It is never used by the product: hslabs_b200/ has no CPU path.
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../hslabs_b200/csrc/hsl_frame.h"
+#include "../../hslabs_b200/csrc/hsl_model.h"
+
+int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int errlen);
+
+namespace {
+template <int NF, int FB, int MODE, bool DUMP>
+void emulate(const HslModelPod& M, const HslFrameArgs& A) {
+  const int roles = NF + 1;
+  int64_t blocks;
+  if (MODE == HSL_MODE_FIELDS) blocks = (A.n_frames + FB - 1) / FB;
+  else {
+    const int64_t slots = A.n_cand * (A.n_t + 4);
+    blocks = (slots - 4 + (FB - 4) - 1) / (FB - 4);
+    if (blocks < 1) blocks = 1;
+  }
+  std::vector<double> smem((size_t)HslSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB);
+  std::vector<HslLegState<DUMP> > lst((size_t)NF * FB);
+  std::vector<HslTrunkState> tst(FB);
+  std::vector<HslSlot> sls(FB);
+  std::vector<int> bad((size_t)roles * FB);
+  for (int64_t b = 0; b < blocks; b++) {
+    HslSmem<NF, FB> sm;
+    sm.carve(smem.data(), M.ntrunk);
+    std::fill(smem.begin(), smem.end(), NAN);
+    std::fill(bad.begin(), bad.end(), 0);
+    for (int s = 0; s < FB; s++) {
+      HslSlot& sl = sls[s];
+      sl.s = s;
+      if (MODE == HSL_MODE_FIELDS) {
+        const int64_t g = b * FB + s;
+        sl.valid = g < A.n_frames;
+        sl.i = (int32_t)(sl.valid ? g : A.n_frames - 1);
+        sl.c = sl.i; sl.fo = sl.i; sl.interior = sl.valid;
+      } else {
+        const int per = A.n_t + 4;
+        const int64_t g = b * (FB - 4) + s;
+        sl.c = g / per;
+        sl.i = (int32_t)(g - sl.c * per);
+        sl.valid = sl.c < A.n_cand;
+        if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+        sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+        sl.fo = sl.c * A.n_t + (sl.i - 2);
+      }
+    }
+    for (int r = 0; r < roles; r++)
+      for (int s = 0; s < FB; s++) {
+        if (r < NF) { phase_a_leg<NF, FB, MODE, DUMP>(M, A, sm, sls[s], r, lst[r * FB + s]); bad[r * FB + s] = lst[r * FB + s].bad; }
+        else phase_a_trunk<NF, FB, MODE>(M, A, sm, sls[s], tst[s]);
+      }
+    for (int r = 0; r < roles; r++)
+      for (int s = 0; s < FB; s++) {
+        if (!sls[s].interior) continue;
+        if (r < NF) { phase_b_leg<NF, FB, MODE, DUMP>(M, A, sm, sls[s], r, lst[r * FB + s]); bad[r * FB + s] |= lst[r * FB + s].bad; }
+        else phase_b_trunk<NF, FB, MODE>(M, A, sm, sls[s], tst[s]);
+      }
+    for (int s = 0; s < FB; s++)
+      if (sls[s].interior) bad[NF * FB + s] |= phase_c_trunk<NF, FB, MODE, DUMP>(M, A, sm, sls[s], tst[s]);
+    for (int r = 0; r < NF; r++)
+      for (int s = 0; s < FB; s++)
+        if (sls[s].interior) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sls[s], r, lst[r * FB + s]);
+    for (int s = 0; s < FB; s++)
+      if (sls[s].interior) phase_e_trunk<NF, FB>(A, sm, sls[s]);
+    for (int r = 0; r < roles; r++)
+      for (int s = 0; s < FB; s++)
+        if (bad[r * FB + s] && sls[s].valid && A.status) A.status[sls[s].c] |= bad[r * FB + s];
+  }
+}
+template <int NF>
+void run(const HslModelPod& M, const HslFrameArgs& A, int mode) {
+  if (mode == HSL_MODE_GAIT) emulate<NF, 32, HSL_MODE_GAIT, true>(M, A);
+  else if (mode == HSL_MODE_TRAJ) emulate<NF, 32, HSL_MODE_TRAJ, true>(M, A);
+  else emulate<NF, 32, HSL_MODE_FIELDS, true>(M, A);
+}
+void run_any(const HslModelPod& M, const HslFrameArgs& A, int mode) {
+  if (M.nf == 6) run<6>(M, A, mode); else run<4>(M, A, mode);
+}
+void transpose_out(const std::vector<double>& src, int comps, int64_t nfr, double* dst) {
+  if (!dst) return;
+  for (int c = 0; c < comps; c++)
+    for (int64_t f = 0; f < nfr; f++) dst[f * comps + c] = src[(size_t)c * nfr + f];
+}
+void finish(int64_t C, int n_t, double total_mass, const HslCand* cand, const double* dt_in, const std::vector<double>& wf,
+            const std::vector<double>& fmn, const std::vector<double>& fmx, const int32_t* status, double* cot, double* work,
+            double* min_cfz, double* max_mu) {
+  for (int64_t c = 0; c < C; c++) {
+    const double dt = cand ? cand[c].dt : dt_in[c];
+    double w = 0, mn = 1e10, mx = -1e10;
+    for (int f = 0; f < n_t; f++) { w += wf[c * n_t + f] * dt; mn = std::fmin(mn, fmn[c * n_t + f]); mx = std::fmax(mx, fmx[c * n_t + f]); }
+    const bool fatal = status && (status[c] & (HSL_ST_BAD_PARAMS | HSL_ST_UNREACHABLE));
+    if (work) work[c] = fatal ? NAN : w;
+    if (cot) cot[c] = (fatal || !cand) ? NAN : w / (total_mass * cand[c].step_length);
+    if (min_cfz) min_cfz[c] = fatal ? NAN : mn;
+    if (max_mu) max_mu[c] = fatal ? NAN : mx;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int hc_model_pod(const char* xml, HslModelPod* pod) {
+  char err[256];
+  return hsl_build_model_pod(xml, pod, err, sizeof err);
+}
+
+int hc_setup_candidate(const char* xml, const double* params, int n_t, HslCand* cd, double* ttab) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  setup_candidate(M, params, n_t, *cd, ttab);
+  return 0;
+}
+
+int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int flags, double* cot, double* work, double* min_cfz,
+                  double* max_mu, int32_t* status, double* traj, double* x, double* z, double* tau, uint8_t* contacts) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  const int64_t nfr = C * n_t;
+  std::vector<HslCand> cand(C);
+  std::vector<double> ttab((size_t)C * (n_t + 4)), wf(nfr), fmn(nfr), fmx(nfr);
+  std::vector<double> dx((size_t)6 * M.n * nfr), dz((size_t)3 * M.nf * nfr), dtau((size_t)M.nmj * nfr), dq((size_t)M.config_dim * C * (n_t + 4));
+  std::vector<uint8_t> dc((size_t)M.nf * nfr);
+  std::vector<int32_t> st(C, 0);
+  for (int64_t c = 0; c < C; c++) { setup_candidate(M, params + HSL_NPARAM * c, n_t, cand[c], &ttab[c * (n_t + 4)]); st[c] = cand[c].status; }
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.flags = flags; A.n_frames = nfr;
+  A.cand = cand.data(); A.ttab = ttab.data();
+  A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
+  A.x = dx.data(); A.z = dz.data(); A.tau = dtau.data(); A.q_out = dq.data(); A.contacts = dc.data();
+  run_any(M, A, HSL_MODE_GAIT);
+  double tm = 0;
+  for (int i = 0; i < M.n; i++) tm += 1.0;
+  finish(C, n_t, tm, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
+  if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
+  transpose_out(dx, 6 * M.n, nfr, x);
+  transpose_out(dz, 3 * M.nf, nfr, z);
+  transpose_out(dtau, M.nmj, nfr, tau);
+  transpose_out(dq, M.config_dim, C * (n_t + 4), traj);
+  if (contacts)
+    for (int l = 0; l < M.nf; l++)
+      for (int64_t f = 0; f < nfr; f++) contacts[f * M.nf + l] = dc[(size_t)l * nfr + f];
+  return 0;
+}
+
+int hc_eval_trajectories(const char* xml, int64_t C, int n_t, const double* traj, const double* dt, double* work, double* min_cfz,
+                         double* max_mu, int32_t* status, double* x, double* z, double* tau) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  const int64_t nfr = C * n_t;
+  std::vector<double> wf(nfr), fmn(nfr), fmx(nfr), dx((size_t)6 * M.n * nfr), dz((size_t)3 * M.nf * nfr), dtau((size_t)M.nmj * nfr);
+  std::vector<int32_t> st(C, 0);
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.n_frames = nfr; A.traj = traj; A.dt_in = dt;
+  A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
+  A.x = dx.data(); A.z = dz.data(); A.tau = dtau.data();
+  run_any(M, A, HSL_MODE_TRAJ);
+  finish(C, n_t, (double)M.n, nullptr, dt, wf, fmn, fmx, st.data(), nullptr, work, min_cfz, max_mu);
+  if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
+  transpose_out(dx, 6 * M.n, nfr, x);
+  transpose_out(dz, 3 * M.nf, nfr, z);
+  transpose_out(dtau, M.nmj, nfr, tau);
+  return 0;
+}
+
+int hc_solve_frames(const char* xml, int64_t F, const double* pos, const double* jpos, const double* jz, const double* mom_rate,
+                    const double* ang_rate, const double* fpos, const uint8_t* contacts, double* x, double* z, double* tau,
+                    int32_t* status) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  std::vector<double> dx((size_t)6 * M.n * F), dz((size_t)3 * M.nf * F), dtau((size_t)M.nmj * F);
+  std::vector<int32_t> st(F, 0);
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = F; A.n_t = 1; A.n_frames = F;
+  A.f_pos = pos; A.f_jpos = jpos; A.f_jz = jz; A.f_momrate = mom_rate; A.f_angrate = ang_rate; A.f_fpos = fpos; A.f_contacts = contacts;
+  A.status = st.data(); A.x = dx.data(); A.z = dz.data(); A.tau = dtau.data();
+  run_any(M, A, HSL_MODE_FIELDS);
+  if (status) memcpy(status, st.data(), sizeof(int32_t) * F);
+  transpose_out(dx, 6 * M.n, F, x);
+  transpose_out(dz, 3 * M.nf, F, z);
+  transpose_out(dtau, M.nmj, F, tau);
+  return 0;
+}
+}
