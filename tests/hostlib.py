@@ -1,0 +1,68 @@
+"""ctypes access to tests/hostcheck (the CPU emulation of the kernel math; test infrastructure)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "hostcheck", "_build", "libhslhost.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        subprocess.check_call(["make", "-C", os.path.join(HERE, "hostcheck"), "-s"])
+        _lib = C.CDLL(LIB)
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def model_dims(xml):
+    pod = np.zeros(16384, np.uint8)
+    rc = lib().hc_model_pod(xml.encode(), _p(pod))
+    assert rc == 0, rc
+    d = pod[:24].view(np.int32)
+    return dict(n=int(d[0]), nf=int(d[1]), nmj=int(d[2]), ntrunk=int(d[3]), config_dim=int(d[4]), lik_index=int(d[5]))
+
+
+def eval_gaits(xml, params, n_t, flags=0):
+    params = np.ascontiguousarray(params, np.float64).reshape(-1, 13)
+    c = params.shape[0]
+    d = model_dims(xml)
+    out = dict(cot=np.zeros(c), work=np.zeros(c), min_cfz=np.zeros(c), max_mu=np.zeros(c), status=np.zeros(c, np.int32),
+               traj=np.zeros((c, n_t + 4, d["config_dim"])), x=np.zeros((c, n_t, 6 * d["n"])), z=np.zeros((c, n_t, 3 * d["nf"])),
+               tau=np.zeros((c, n_t, d["nmj"])), contacts=np.zeros((c, n_t, d["nf"]), np.uint8))
+    rc = lib().hc_eval_gaits(xml.encode(), C.c_int64(c), C.c_int(n_t), _p(params), C.c_int(flags),
+                             *[_p(out[k]) for k in ("cot", "work", "min_cfz", "max_mu", "status", "traj", "x", "z", "tau", "contacts")])
+    assert rc == 0, rc
+    return out
+
+
+def eval_trajectories(xml, traj, dt, n_t):
+    d = model_dims(xml)
+    traj = np.ascontiguousarray(traj, np.float64).reshape(-1, n_t + 5, d["config_dim"])
+    c = traj.shape[0]
+    dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, np.float64), (c,)))
+    out = dict(work=np.zeros(c), min_cfz=np.zeros(c), max_mu=np.zeros(c), status=np.zeros(c, np.int32),
+               x=np.zeros((c, n_t, 6 * d["n"])), z=np.zeros((c, n_t, 3 * d["nf"])), tau=np.zeros((c, n_t, d["nmj"])))
+    rc = lib().hc_eval_trajectories(xml.encode(), C.c_int64(c), C.c_int(n_t), _p(traj), _p(dt), _p(out["work"]), _p(out["min_cfz"]),
+                                    _p(out["max_mu"]), _p(out["status"]), _p(out["x"]), _p(out["z"]), _p(out["tau"]))
+    assert rc == 0, rc
+    return out
+
+
+def solve_frames(xml, f):
+    d = model_dims(xml)
+    nfr = f["pos"].shape[0]
+    out = dict(x=np.zeros((nfr, 6 * d["n"])), z=np.zeros((nfr, 3 * d["nf"])), tau=np.zeros((nfr, d["nmj"])), status=np.zeros(nfr, np.int32))
+    arrs = [np.ascontiguousarray(f[k], np.float64) for k in ("pos", "jpos", "jzaxis", "mom_rate", "ang_mom_rate", "fpos")]
+    con = np.ascontiguousarray(f["contacts"], np.uint8)
+    rc = lib().hc_solve_frames(xml.encode(), C.c_int64(nfr), *[_p(a) for a in arrs], _p(con), _p(out["x"]), _p(out["z"]), _p(out["tau"]),
+                               _p(out["status"]))
+    assert rc == 0, rc
+    return out

@@ -1,0 +1,104 @@
+"""CPU tier: the C-ABI library builds, loads, exports every symbol include/hsl.h declares, flattens the models
+exactly as the oracle's tree says, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import hostlib
+from conftest import ROOT, model_xml
+
+
+def test_library_exports_header_symbols(hsl):
+    from hslabs_b200 import api, build
+    build.build()
+    lib = C.CDLL(api.lib_path())
+    header = open(os.path.join(ROOT, "include", "hsl.h")).read()
+    declared = set(re.findall(r"\b(hsl_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(api.exported_symbols())
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+
+
+@pytest.mark.parametrize("name,dims", [("hexapod", (22, 6, 18, 24, 4)), ("myant", (17, 4, 12, 18, 5)), ("spider", (19, 6, 18, 24, 1))])
+def test_model_dims(hsl, name, dims):
+    m = hsl.Model(hsl.model_path(name))
+    assert (m.n, m.nf, m.nmj, m.config_dim, m.ntrunk) == dims
+    assert m.rcap == 0.08
+
+
+@pytest.mark.parametrize("name", ["hexapod", "myant", "spider"])
+def test_packed_model_matches_oracle_tree(hsl, orc, name):
+    """The flat constant block (hsl_model.h) against the oracle's restatement of the reference's pointer tree."""
+    cons = orc.Model(model_xml(name)).constants()
+    pod = hsl.Model(hsl.model_path(name)).pod_bytes()
+    host = np.zeros(16384, np.uint8)
+    hostlib.lib().hc_model_pod(model_xml(name).encode(), host.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(pod, host[:pod.size])  # same loader in the library and in the host emulation
+    ints = pod[:24].view(np.int32)
+    n, nf = int(ints[0]), int(ints[1])
+    dbl = pod[24:].view(np.float64)
+    assert dbl[0] == 0.08 and dbl[1] == 1.0
+    # limbs: HslLimb = 3 x HslHinge (30 doubles each) + 9 doubles + 6 int32 ; trunk: 8 doubles + 2 int32 = 9 doubles
+    trunk0 = 2 + 6
+    limb0 = trunk0 + 8 * 9
+    for l in range(nf):
+        base = limb0 + l * (3 * 30 + 9 + 3)
+        body = int(cons["limb_top"][l])
+        for h in range(3):
+            hb = base + 30 * h
+            Rjp, tjp = dbl[hb:hb + 9].reshape(3, 3).T, dbl[hb + 9:hb + 12]
+            Rpb, tpb = dbl[hb + 12:hb + 21].reshape(3, 3).T, dbl[hb + 21:hb + 24]
+            com = dbl[hb + 24:hb + 27]
+            A = cons["J_A_parent"][body].reshape(4, 4).T
+            B = cons["A_pj_body"][body].reshape(4, 4).T
+            assert np.array_equal(Rjp, A[:3, :3]) and np.array_equal(tjp, A[:3, 3])
+            assert np.array_equal(Rpb, B[:3, :3]) and np.array_equal(tpb, B[:3, 3])
+            assert np.array_equal(com, cons["A_body_geom"][body].reshape(4, 4).T[:3, 3])
+            if h < 2:
+                body = int(np.where(cons["parent"] == body)[0][0])
+        assert body == cons["limb_foot"][l]
+        assert np.array_equal(dbl[base + 90:base + 93], cons["capsule_to_pos"][body])
+
+
+def test_bad_inputs_report_errors(hsl, tmp_path):
+    with pytest.raises(hsl.HslError):
+        hsl.Model(str(tmp_path / "missing.xml"))
+    bad = tmp_path / "hexapod.xml"
+    bad.write_text("<notmujoco/>")
+    with pytest.raises(hsl.HslError):
+        hsl.Model(str(bad))
+    other = tmp_path / "walker.xml"
+    other.write_text(open(hsl.model_path("hexapod")).read())
+    with pytest.raises(hsl.HslError):  # no LIK solver for unknown model names (lik.cpp:12-16)
+        hsl.Model(str(other))
+
+
+def test_no_cpu_fallback(hsl):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA device present")
+    m = hsl.Model(hsl.model_path("hexapod"))
+    with pytest.raises(hsl.HslError, match="CUDA"):
+        m.eval_gaits(hsl.make_params(torso_pos=(0, 0, -.1)), 20)
+
+
+def test_preset_parser_matches_oracle(hsl, orc):
+    from conftest import PRESETS
+    for pid in range(28):
+        a, xa = hsl.load_preset(PRESETS, pid)
+        b, xb = orc.load_preset(PRESETS, pid)
+        assert xa == xb and np.array_equal(a, b)
+
+
+def test_product_never_touches_the_oracle():
+    """No file of the product package may reference oracle/ or the host emulation."""
+    pkg = os.path.join(ROOT, "hslabs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".h", ".cu", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle's", "").replace("oracle A", "").lower() or f == "gen_models.py", f
+                assert "hostcheck" not in txt or f in ("hsl_frame.h",), f

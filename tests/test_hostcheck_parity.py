@@ -1,0 +1,104 @@
+"""CPU tier: the kernel's per-thread phase functions (hslabs_b200/csrc/hsl_frame.h), compiled for the host and run
+as a serial emulation of the CUDA block (tests/hostcheck), against the CPU oracle.  This proves the restructured
+algorithm (Newton-Euler recursion + per-contact 3x3 blocks + 6x6 Schur solve) equals the reference-shaped one
+(6n x 6n force-torque matrix, QR, null space, two-level perturbation solve) before any GPU time is spent; the
+`-m gpu` tier then checks the same code running on the device through the C ABI.
+"""
+import numpy as np
+import pytest
+
+import hostlib
+from conftest import PRESETS, model_xml, rel_err
+
+TOL = 1e-9
+
+
+def angle_err(a, b):
+    d = np.abs(a - b)
+    return float(np.minimum(d, np.abs(d - 2 * np.pi)).max())
+
+
+@pytest.mark.parametrize("pid", [0, 1, 2, 3, 7, 8, 9, 10, 15, 17, 20, 23, 24, 25, 26, 27])
+def test_presets(orc, pid):
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    ref = orc.Model(xml).measure_cot(params, n_t, detail=True)
+    got = hostlib.eval_gaits(xml, params, n_t)
+    assert ref["status"] == 0 and got["status"][0] == 0
+    assert angle_err(got["traj"][0], ref["traj"][:n_t + 4]) < 1e-12
+    for key in ("x", "z", "tau"):
+        assert rel_err(got[key][0], ref[key]) < TOL, key
+    assert abs(got["cot"][0] - ref["cot"]) <= TOL * abs(ref["cot"])
+    assert abs(got["work"][0] - ref["work"]) <= TOL * abs(ref["work"])
+
+
+def test_random_batch_hexapod(orc):
+    """Config-2 style random candidates (small batch): costs, ranking and status agree."""
+    rng = np.random.default_rng(20261018)
+    n = 24
+    p = np.zeros((n, 13))
+    p[:, 2] = rng.uniform(-0.15, -0.05, n); p[:, 6] = rng.uniform(0, 1, n); p[:, 7] = rng.uniform(1, 6, n)
+    p[:, 8] = rng.uniform(0.1, 0.5, n); p[:, 9] = rng.uniform(0.02, 0.12, n); p[:, 11] = -1
+    xml = model_xml("hexapod")
+    n_t = 32
+    ref = orc.Model(xml).eval_batch(p, n_t, nthreads=4)
+    got = hostlib.eval_gaits(xml, p, n_t)
+    ok = ref["status"] == 0
+    assert np.array_equal(got["status"] == 0, ok)
+    assert ok.sum() >= n // 2
+    assert rel_err(got["cot"][ok], ref["cot"][ok]) < TOL
+    assert np.array_equal(np.argsort(got["cot"][ok]), np.argsort(ref["cot"][ok]))
+
+
+def test_unreachable_and_ignore_reach(orc):
+    xml = model_xml("hexapod")
+    p, _ = orc.load_preset(PRESETS, 8)
+    p = p.copy()
+    p[2] = 0.3  # torso too high: feet cannot reach the ground
+    m = orc.Model(xml)
+    assert m.measure_cot(p, 20)["status"] == 1
+    got = hostlib.eval_gaits(xml, p, 20)
+    assert got["status"][0] & 2 and np.isnan(got["cot"][0])
+    m.set_ignore_reach(True)
+    ref = m.measure_cot(p, 20, detail=True)
+    got = hostlib.eval_gaits(xml, p, 20, flags=1)
+    assert ref["status"] == 0 and not (got["status"][0] & 2)
+    assert angle_err(got["traj"][0], ref["traj"][:24]) < 1e-12
+
+
+def test_bad_step_duration():
+    got = hostlib.eval_gaits(model_xml("hexapod"), np.array([0, 0, -.1, 0, 0, 0, 1.5, 3, .5, .1, 0, -1, 0.]), 20)
+    assert got["status"][0] & 1 and np.isnan(got["cot"][0])
+
+
+@pytest.mark.parametrize("pid", [8, 9, 26])
+def test_trajectory_entry(orc, pid):
+    """L2 entry: supplied joint trajectories -> x, z, motor torques, work (periodic.cpp:149-160, 192-202, 285-307)."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    m = orc.Model(xml)
+    ref = m.measure_cot(params, n_t, detail=True)
+    dt = params[7] / n_t
+    ref2 = m.eval_trajectory(ref["traj"], n_t, dt)
+    got = hostlib.eval_trajectories(xml, ref["traj"][None], dt, n_t)
+    for key in ("x", "z", "tau"):
+        assert rel_err(got[key][0], ref2[key]) < TOL, key
+    assert abs(got["work"][0] - ref2["work"]) <= TOL * abs(ref2["work"])
+    assert abs(ref2["work"] - ref["work"]) <= 1e-12 * abs(ref["work"])
+
+
+@pytest.mark.parametrize("pid", [8, 9, 24])
+def test_frame_solve_entry(orc, pid):
+    """L1 entry: populated dynrecords -> x, z, motor torques (forcetorquesolver::solve_forcetorques, ftsolver.cpp:78-102)."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    m = orc.Model(xml)
+    ref = m.measure_cot(params, n_t, detail=True)
+    fields = m.frame_fields(params, n_t)
+    got = hostlib.solve_frames(xml, fields)
+    assert (got["status"] == 0).all()
+    for key in ("x", "z", "tau"):
+        assert rel_err(got[key], ref[key]) < TOL, key
