@@ -124,8 +124,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--candidates", type=int, default=N_CAND)
     ap.add_argument("--frames", type=int, default=N_T)
-    ap.add_argument("--fb", type=int, default=0, help="frame slots per block (32/64), 0 = library default")
-    ap.add_argument("--minb", type=int, default=2, help="resident blocks per SM the kernel is register-bounded for (1..3)")
+    ap.add_argument("--fb", type=int, default=0, help="frame slots per block (32/64/96), 0 = library default")
+    ap.add_argument("--maxreg", type=int, default=144, help="register cap per thread of the cost-only kernel variant")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -149,7 +149,7 @@ def main():
     n_cand, n_t = args.candidates, args.frames
     model = hsl.Model(hsl.model_path(MODEL))
     if args.fb:
-        model.set_tuning(args.fb, args.minb)
+        model.set_tuning(args.fb, args.maxreg)
 
     # synthetic candidates for this rank's shard; unreachable draws are redrawn
     rng = np.random.default_rng(SEED + rank)

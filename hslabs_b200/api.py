@@ -25,7 +25,8 @@ class HslError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(HERE, "lib", "libhsl_b200.so")
+    # HSL_B200_LIB selects another build of the same library (e.g. the -DHSL_PHASE_CLOCKS profiling build)
+    return os.environ.get("HSL_B200_LIB") or os.path.join(HERE, "lib", "libhsl_b200.so")
 
 
 def model_path(name):
@@ -138,8 +139,8 @@ class Model:
             pass
 
     # ---- measurement helpers
-    def set_tuning(self, fb=32, minb=2):
-        _check(_load().hsl_set_tuning(self._h, fb, minb))
+    def set_tuning(self, fb=64, maxreg=144):
+        _check(_load().hsl_set_tuning(self._h, fb, maxreg))
 
     def launch_count(self):
         return int(_load().hsl_launch_count(self._h))

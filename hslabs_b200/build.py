@@ -39,9 +39,10 @@ def build(force=False, verbose=False):
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     objs = []
     logs = []
+    extra = os.environ.get("HSL_NVCC_EXTRA", "").split()
     for s in SOURCES:
         o = os.path.join(LIBDIR, s + ".o")
-        cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + extra + ["-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         logs.append(r.stdout)
         if r.returncode != 0:

@@ -56,7 +56,7 @@ struct PinBuf {  // grow-only pinned host buffer
 struct HslModel {
   HslModelPod pod;
   double total_mass;
-  int fb = 32, minb = 2;
+  int fb = 64, maxreg = 144;
   int64_t launches = 0;
   // workspace
   DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b;
@@ -110,10 +110,10 @@ size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap) {
   if (m && dst) memcpy(dst, &m->pod, cap < sizeof(HslModelPod) ? cap : sizeof(HslModelPod));
   return sizeof(HslModelPod);
 }
-int hsl_set_tuning(HslModel* m, int fb, int minb) {
-  if (!m || (fb != 32 && fb != 64) || minb < 1 || minb > 3) return set_err(HSL_ERR_ARG, "frames per block must be 32 or 64, blocks per SM 1..3");
+int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
+  if (!m || (fb != 32 && fb != 64 && fb != 96) || maxreg < 64 || maxreg > 255) return set_err(HSL_ERR_ARG, "frame slots per block must be 32, 64 or 96; register cap 64..255");
   m->fb = fb;
-  m->minb = minb;
+  m->maxreg = maxreg;
   return HSL_OK;
 }
 int64_t hsl_launch_count(const HslModel* m) { return m ? m->launches : 0; }
@@ -146,8 +146,35 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
     A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
     A.q_out = (double*)m->dump_q.p; A.contacts = (uint8_t*)m->dump_c.p;
   }
+#ifdef HSL_PHASE_CLOCKS
+  const int fbp = (dump ? 32 : m->fb), warps = (m->pod.nf + 1) * fbp / 32;
+  const int64_t nblk = (C * (n_t + 4) - 4 + (fbp - 4) - 1) / (fbp - 4);
+  static DevBuf clkbuf;
+  HSL_CUDA(clkbuf.need(sizeof(long long) * nblk * warps * 8));
+  A.phase_clk = (long long*)clkbuf.p;
+#endif
   HSL_CUDA(hsl_launch_setup(m->pod, C, n_t, d_params, (HslCand*)m->cand.p, (double*)m->ttab.p, st_buf, st));
-  HSL_CUDA(hsl_launch_frames(m->pod, A, HSL_MODE_GAIT, dump, m->fb, m->minb, st));
+  HSL_CUDA(hsl_launch_frames(m->pod, A, HSL_MODE_GAIT, dump, m->fb, m->maxreg, st));
+#ifdef HSL_PHASE_CLOCKS
+  {
+    HSL_CUDA(cudaStreamSynchronize(st));
+    std::vector<long long> h((size_t)nblk * warps * 8);
+    HSL_CUDA(cudaMemcpy(h.data(), clkbuf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+    // average cycles per segment, per role: A | wait1 | B | wait2 | C | wait3 | D+E
+    const int roles = m->pod.nf + 1, wpr = fbp / 32;
+    fprintf(stderr, "[phase clocks] blocks=%lld warps/block=%d\n", (long long)nblk, warps);
+    for (int r = 0; r < roles; r++) {
+      double seg[7] = {0, 0, 0, 0, 0, 0, 0};
+      for (int64_t b = 0; b < nblk; b++)
+        for (int w = 0; w < wpr; w++) {
+          const long long* c = &h[((size_t)b * warps + r * wpr + w) * 8];
+          for (int k = 0; k < 7; k++) seg[k] += (double)(c[k + 1] - c[k]);
+        }
+      fprintf(stderr, "  role %d: A %.0f | w %.0f | B %.0f | w %.0f | C %.0f | w %.0f | DE %.0f  (cycles)\n", r, seg[0] / (nblk * wpr),
+              seg[1] / (nblk * wpr), seg[2] / (nblk * wpr), seg[3] / (nblk * wpr), seg[4] / (nblk * wpr), seg[5] / (nblk * wpr), seg[6] / (nblk * wpr));
+    }
+  }
+#endif
   HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, (const HslCand*)m->cand.p, nullptr, A.wframe, A.fmin_cfz, A.fmax_mu, st_buf,
                              d_cot, d_work, d_min, d_max, st));
   m->launches += 3;

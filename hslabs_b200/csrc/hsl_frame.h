@@ -72,6 +72,7 @@ struct HslFrameArgs {
   double *x, *z, *tau;
   double* q_out;       // [config_dim][C*(n_t+4)] generated joint values (GAIT)
   uint8_t* contacts;   // [nf][n_frames]
+  long long* phase_clk;  // [blocks][warps][8] cycle stamps, only written by -DHSL_PHASE_CLOCKS builds (profiling aid)
 };
 
 // ------------------------------------------------------------------ small vector helpers

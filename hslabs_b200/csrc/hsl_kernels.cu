@@ -16,8 +16,8 @@
 #include "hsl_frame.h"
 #include "hsl_internal.h"
 
-template <int NF, int FB, int MODE, bool DUMP, int MINB>
-__global__ void __launch_bounds__((NF + 1) * FB, MINB)
+template <int NF, int FB, int MODE, bool DUMP, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
   extern __shared__ double hsl_smem_raw[];
   HslSmem<NF, FB> sm;
@@ -42,16 +42,26 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
     sl.interior = sl.valid && sl.s >= 2 && sl.s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
     sl.fo = sl.c * A.n_t + (sl.i - 2);
   }
+#ifdef HSL_PHASE_CLOCKS
+  long long clk[8];
+  int nclk = 0;
+#define HSL_STAMP() clk[nclk++] = clock64()
+#else
+#define HSL_STAMP()
+#endif
   HslLegState<DUMP> lst;
   HslTrunkState tst;
   int bad = 0;
+  HSL_STAMP();
   if (role < NF) {
     phase_a_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
     bad = lst.bad;
   } else {
     phase_a_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
   }
+  HSL_STAMP();
   __syncthreads();
+  HSL_STAMP();
   if (sl.interior) {
     if (role < NF) {
       phase_b_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
@@ -60,13 +70,24 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
       phase_b_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
     }
   }
+  HSL_STAMP();
   __syncthreads();
+  HSL_STAMP();
   if (sl.interior && role == NF) bad |= phase_c_trunk<NF, FB, MODE, DUMP>(M, A, sm, sl, tst);
+  HSL_STAMP();
   __syncthreads();
+  HSL_STAMP();
   if (sl.interior && role < NF) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
   __syncthreads();
   if (sl.interior && role == NF) phase_e_trunk<NF, FB>(A, sm, sl);
+  HSL_STAMP();
   if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
+#ifdef HSL_PHASE_CLOCKS
+  if (A.phase_clk && (threadIdx.x & 31) == 0) {
+    long long* dst = A.phase_clk + ((size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * 8;
+    for (int k = 0; k < 8; k++) dst[k] = clk[k];
+  }
+#endif
 }
 
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
@@ -129,10 +150,10 @@ __global__ void hsl_dfma_probe_kernel(double* out, int iters, double a, double b
 
 // ------------------------------------------------------------------ launchers
 namespace {
-template <int NF, int FB, int MODE, bool DUMP, int MINB = 1>
+template <int NF, int FB, int MODE, bool DUMP, int MAXREG = 255>
 cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
   const size_t smem = (size_t)HslSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
-  auto kern = hsl_frames_kernel<NF, FB, MODE, DUMP, MINB>;
+  auto kern = hsl_frames_kernel<NF, FB, MODE, DUMP, MAXREG>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int64_t blocks;
@@ -156,22 +177,26 @@ cudaError_t launch_frames_nf(const HslModelPod& M, const HslFrameArgs& A, int mo
 }  // namespace
 
 // Cost-only evaluation (the headline path) comes in a few occupancy variants: fb = frame slots per block,
-// minb = resident blocks per SM the register allocation is bounded for.
+// maxreg = register cap per thread (sets how many blocks fit an SM's 64K registers).
 template <int NF>
-cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int minb, cudaStream_t st) {
-  if (fb == 64) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 1>(M, A, st);
-  if (minb >= 3) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 3>(M, A, st);
-  if (minb == 2) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 2>(M, A, st);
-  return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 1>(M, A, st);
+cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int maxreg, cudaStream_t st) {
+  if (fb == 96) return launch_frames_t<NF, 96, HSL_MODE_GAIT, false, 96>(M, A, st);
+  if (fb == 64) {
+    if (maxreg <= 128) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128>(M, A, st);
+    return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 144>(M, A, st);
+  }
+  if (maxreg <= 96) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 96>(M, A, st);
+  if (maxreg <= 144) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 144>(M, A, st);
+  return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 255>(M, A, st);
 }
 
-cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int minb, cudaStream_t st) {
+cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int maxreg, cudaStream_t st) {
   if (M.nf == 6) {
-    if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<6>(M, A, fb, minb, st);
+    if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<6>(M, A, fb, maxreg, st);
     return launch_frames_nf<6, 32>(M, A, mode, dump, st);
   }
   if (M.nf == 4) {
-    if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<4>(M, A, fb, minb, st);
+    if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<4>(M, A, fb, maxreg, st);
     return launch_frames_nf<4, 32>(M, A, mode, dump, st);
   }
   return cudaErrorInvalidValue;
