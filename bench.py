@@ -125,7 +125,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=N_CAND)
     ap.add_argument("--frames", type=int, default=N_T)
     ap.add_argument("--fb", type=int, default=0, help="frame slots per block (32/64/96), 0 = library default")
-    ap.add_argument("--maxreg", type=int, default=144, help="register cap per thread of the cost-only kernel variant")
+    ap.add_argument("--maxreg", type=int, default=128, help="register cap per thread of the cost-only kernel variant")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

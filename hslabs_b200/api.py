@@ -139,7 +139,7 @@ class Model:
             pass
 
     # ---- measurement helpers
-    def set_tuning(self, fb=64, maxreg=144):
+    def set_tuning(self, fb=64, maxreg=128):
         _check(_load().hsl_set_tuning(self._h, fb, maxreg))
 
     def launch_count(self):

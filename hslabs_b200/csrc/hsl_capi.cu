@@ -56,7 +56,7 @@ struct PinBuf {  // grow-only pinned host buffer
 struct HslModel {
   HslModelPod pod;
   double total_mass;
-  int fb = 64, maxreg = 144;
+  int fb = 64, maxreg = 128;
   int64_t launches = 0;
   // workspace
   DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b;
@@ -111,7 +111,7 @@ size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap) {
   return sizeof(HslModelPod);
 }
 int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
-  if (!m || (fb != 32 && fb != 64 && fb != 96) || maxreg < 64 || maxreg > 255) return set_err(HSL_ERR_ARG, "frame slots per block must be 32, 64 or 96; register cap 64..255");
+  if (!m || (fb != 32 && fb != 64) || maxreg < 64 || maxreg > 255) return set_err(HSL_ERR_ARG, "frame slots per block must be 32 or 64; register cap 64..255");
   m->fb = fb;
   m->maxreg = maxreg;
   return HSL_OK;

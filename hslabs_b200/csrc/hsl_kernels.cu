@@ -177,17 +177,15 @@ cudaError_t launch_frames_nf(const HslModelPod& M, const HslFrameArgs& A, int mo
 }  // namespace
 
 // Cost-only evaluation (the headline path) comes in a few occupancy variants: fb = frame slots per block,
-// maxreg = register cap per thread (sets how many blocks fit an SM's 64K registers).
+// maxreg = register cap per thread.  The register file is 16K registers per SM sub-partition and warps are dealt
+// round-robin to the 4 sub-partitions, so ceil(resident warps / 4) * 32 * maxreg must stay <= 16384:
+// 4 warps per sub-partition -> 128 registers, 3 -> 168, 2 -> 255.
 template <int NF>
 cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int maxreg, cudaStream_t st) {
-  if (fb == 96) return launch_frames_t<NF, 96, HSL_MODE_GAIT, false, 96>(M, A, st);
-  if (fb == 64) {
-    if (maxreg <= 128) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128>(M, A, st);
-    return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 144>(M, A, st);
-  }
-  if (maxreg <= 96) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 96>(M, A, st);
-  if (maxreg <= 144) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 144>(M, A, st);
-  return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 255>(M, A, st);
+  if (fb == 64) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128>(M, A, st);  // 14 warps (nf=6): 4 per sub-partition
+  if (maxreg <= 96) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 80>(M, A, st);   // 3 blocks x 7 warps
+  if (maxreg <= 128) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 128>(M, A, st); // 2 blocks x 7 warps
+  return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 255>(M, A, st);                    // 1 block x 7 warps
 }
 
 cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int maxreg, cudaStream_t st) {

@@ -1,0 +1,44 @@
+"""Multi-GPU host logic: shard candidates over ranks, evaluate locally, all-gather the costs for selection.
+
+Candidates are independent and never span GPUs.  `torch.distributed` is the plumbing: NCCL over
+NVLink on the GPU box (costs stay on the device), gloo in the CPU test tier.  The only collective is one all-gather
+of 8 B per candidate; selection (argmin / ranking) runs on every rank.
+"""
+import numpy as np
+
+
+def shard_bounds(n_cand, world, rank):
+    """Contiguous blocks of ceil(C/G) candidates per rank (the last ranks may get fewer or none)."""
+    per = -(-n_cand // world)
+    lo = min(rank * per, n_cand)
+    return lo, min(lo + per, n_cand), per
+
+
+def evaluate_sharded(eval_fn, params, world, rank, all_gather_fn):
+    """eval_fn(local_params) -> cost array for the local shard (NaN = failed candidate).
+    all_gather_fn(padded_local_costs) -> array [world * per].  Returns (costs[C], best index, ranking)."""
+    params = np.asarray(params, np.float64).reshape(-1, params.shape[-1])
+    n = params.shape[0]
+    lo, hi, per = shard_bounds(n, world, rank)
+    local = np.full(per, np.nan)
+    if hi > lo:
+        local[:hi - lo] = np.asarray(eval_fn(params[lo:hi]), np.float64)
+    gathered = np.asarray(all_gather_fn(local), np.float64).reshape(world, per)
+    costs = np.concatenate([gathered[r][:max(0, min(per, n - r * per))] for r in range(world)])
+    key = np.where(np.isnan(costs), np.inf, costs)
+    order = np.argsort(key, kind="stable")
+    return costs, int(order[0]), order
+
+
+def torch_all_gather(dist, device=None):
+    """all_gather_fn backed by torch.distributed (NCCL when `device` is a CUDA device, gloo on CPU)."""
+    import torch
+
+    def fn(local):
+        t = torch.from_numpy(np.ascontiguousarray(local))
+        if device is not None:
+            t = t.to(device)
+        out = torch.empty(dist.get_world_size() * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy()
+    return fn

@@ -41,3 +41,175 @@ def test_presets_detail(hsl, orc, pid, n_t):
     assert abs(gpu["min_cfz"][0] - lam[:, 2].min()) <= TOL * np.abs(lam).max()
     mu = np.sqrt(lam[:, 0] ** 2 + lam[:, 1] ** 2) / lam[:, 2]
     assert abs(gpu["max_mu"][0] - mu.max()) <= 1e-7 * max(1.0, abs(mu.max()))
+
+
+def test_golden_fixtures(hsl):
+    """Committed golden frames (frozen from the oracle, tests/golden/make_golden.py): no oracle call needed."""
+    import os
+    from conftest import GOLDEN
+    for name in ("hexapod", "myant", "spider"):
+        g = np.load(os.path.join(GOLDEN, "frames_%s.npz" % name))
+        out = hsl.Model(model_xml(name)).eval_gaits_detail(g["params"], 20)
+        assert out["status"][0] == 0
+        assert _angle_err(out["traj"][0], g["traj"][:24]) < 1e-12
+        for key in ("x", "z", "tau"):
+            assert rel_err(out[key][0], g[key]) < TOL, (name, key)
+        assert abs(out["cot"][0] - float(g["cot"])) <= TOL * abs(float(g["cot"]))
+
+
+def test_golden_sweep(hsl):
+    """measure_cot_sweep(pgs, 20, "period", 3, 18, 15) on preset 8 (main.cpp:69) against the frozen sweep."""
+    import json
+    import os
+    from conftest import GOLDEN
+    gold = json.load(open(os.path.join(GOLDEN, "sweep_preset8_period.json")))
+    params, name = hsl.load_preset(PRESETS, 8)
+    vals, cots = hsl.measure_cot_sweep(hsl.Model(model_xml(name)), params, 20, "period", 3, 18, 15)
+    assert np.allclose(vals, gold["vals"], rtol=0, atol=1e-12)
+    assert rel_err(cots, gold["cots"]) < TOL
+    assert np.array_equal(np.argsort(cots), np.argsort(gold["cots"]))
+
+
+def _random_candidates(model, n, seed):
+    rng = np.random.default_rng(seed)
+    p = np.zeros((n, 13))
+    p[:, 6] = rng.uniform(0, 1, n); p[:, 7] = rng.uniform(1, 6, n); p[:, 8] = rng.uniform(0.1, 0.5, n)
+    p[:, 9] = rng.uniform(0.02, 0.12, n); p[:, 11] = -1
+    if model == "hexapod":
+        p[:, 2] = rng.uniform(-0.15, -0.05, n)
+    elif model == "myant":
+        p[:, 2] = rng.uniform(-0.12, -0.04, n)
+    else:  # spider: BASELINE config 3
+        p[:, 2] = rng.uniform(0.0, 0.1, n); p[:, 11] = 0; p[:, 12] = rng.uniform(0.3, 0.5, n)
+    return p
+
+
+@pytest.mark.parametrize("model,n_t", [("hexapod", 64), ("myant", 48), ("spider", 64)])
+def test_random_batch_costs_and_ranking(hsl, orc, model, n_t):
+    """Random candidates in the BASELINE ranges: per-candidate costs within 1e-9, identical status and ranking."""
+    p = _random_candidates(model, 48, 20261018)
+    ref = orc.Model(model_xml(model)).eval_batch(p, n_t, nthreads=8)
+    gpu = hsl.Model(model_xml(model)).eval_gaits(p, n_t)
+    ok = ref["status"] == 0
+    assert np.array_equal((gpu["status"] & 3) == 0, ok)
+    assert ok.sum() >= 24
+    assert (gpu["status"][ok] == 0).all()
+    assert np.abs(gpu["cot"][ok] - ref["cot"][ok]).max() <= TOL * np.abs(ref["cot"][ok]).max()
+    assert np.abs(gpu["work"][ok] - ref["work"][ok]).max() <= TOL * np.abs(ref["work"][ok]).max()
+    assert np.isnan(gpu["cot"][~ok]).all()
+    ro, go = np.argsort(ref["cot"][ok]), np.argsort(gpu["cot"][ok])
+    assert np.array_equal(ro, go)
+
+
+def test_curved_and_shifted_batch(hsl, orc):
+    """BASELINE config 2, second batch: curvature U[-.1,.1], lateral foot shift U[0,.3] (curved-path branch)."""
+    rng = np.random.default_rng(7)
+    p = _random_candidates("hexapod", 24, 11)
+    p[:, 10] = rng.uniform(-0.1, 0.1, 24); p[:, 11] = 0; p[:, 12] = rng.uniform(0, 0.3, 24)
+    ref = orc.Model(model_xml("hexapod")).eval_batch(p, 40, nthreads=8)
+    gpu = hsl.Model(model_xml("hexapod")).eval_gaits(p, 40)
+    ok = ref["status"] == 0
+    assert ok.sum() >= 8 and np.array_equal((gpu["status"] & 3) == 0, ok)
+    assert np.abs(gpu["cot"][ok] - ref["cot"][ok]).max() <= TOL * np.abs(ref["cot"][ok]).max()
+
+
+def test_status_codes_and_ignore_reach(hsl, orc):
+    xml = model_xml("hexapod")
+    p, _ = orc.load_preset(PRESETS, 8)
+    bad = p.copy(); bad[2] = 0.3           # feet cannot reach the ground
+    oob = p.copy(); oob[6] = 1.5           # step_duration out of [0,1]
+    m = hsl.Model(xml)
+    out = m.eval_gaits(np.stack([p, bad, oob]), 20)
+    assert out["status"][0] == 0 and np.isfinite(out["cot"][0])
+    assert out["status"][1] & 2 and np.isnan(out["cot"][1])
+    assert out["status"][2] & 1 and np.isnan(out["cot"][2])
+    om = orc.Model(xml)
+    assert om.measure_cot(bad, 20)["status"] == 1
+    om.set_ignore_reach(True)
+    ref = om.measure_cot(bad, 20, detail=True)
+    got = m.eval_gaits_detail(bad, 20, flags=hsl.HSL_FLAG_IGNORE_REACH)
+    assert not (got["status"][0] & 2)
+    assert _angle_err(got["traj"][0], ref["traj"][:24]) < 1e-12
+
+
+@pytest.mark.parametrize("pid", [8, 9, 26])
+def test_trajectory_entry(hsl, orc, pid):
+    """hsl_eval_trajectories_host: supplied joint trajectories -> x, z, tau, work."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    om = orc.Model(xml)
+    ref = om.measure_cot(params, n_t, detail=True)
+    dt = params[7] / n_t
+    ref2 = om.eval_trajectory(ref["traj"], n_t, dt)
+    got = hsl.Model(xml).eval_trajectories(np.stack([ref["traj"], ref["traj"]]), dt, n_t)
+    for c in range(2):
+        for key in ("x", "z", "tau"):
+            assert rel_err(got[key][c], ref2[key]) < TOL, key
+        assert abs(got["work"][c] - ref2["work"]) <= TOL * abs(ref2["work"])
+
+
+@pytest.mark.parametrize("pid", [8, 9, 24])
+def test_frame_solve_entry(hsl, orc, pid):
+    """hsl_solve_frames_host: populated dynrecords -> x, z, motor torques (the narrowest entry)."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    om = orc.Model(xml)
+    ref = om.measure_cot(params, 20, detail=True)
+    f = om.frame_fields(params, 20)
+    got = hsl.Model(xml).solve_frames(f["pos"], f["jpos"], f["jzaxis"], f["mom_rate"], f["ang_mom_rate"], f["fpos"], f["contacts"])
+    assert (got["status"] == 0).all()
+    for key in ("x", "z", "tau"):
+        assert rel_err(got[key], ref[key]) < TOL, key
+
+
+def test_frame_solve_ragged_sizes(hsl, orc):
+    """Frame counts that do not fill a block (1, 31, 33 frames) give the same per-frame results."""
+    params, name = orc.load_preset(PRESETS, 8)
+    xml = model_xml(name)
+    f = orc.Model(xml).frame_fields(params, 40)
+    m = hsl.Model(xml)
+    full = m.solve_frames(f["pos"], f["jpos"], f["jzaxis"], f["mom_rate"], f["ang_mom_rate"], f["fpos"], f["contacts"])
+    for k in (1, 31, 33):
+        part = m.solve_frames(*(f[a][:k] for a in ("pos", "jpos", "jzaxis", "mom_rate", "ang_mom_rate", "fpos", "contacts")))
+        assert np.array_equal(part["x"], full["x"][:k]) and np.array_equal(part["tau"], full["tau"][:k])
+
+
+def test_kernel_variants_agree(hsl):
+    """All occupancy variants of the cost-only kernel and the detail kernel give identical costs (same arithmetic)."""
+    p = _random_candidates("hexapod", 96, 3)
+    m = hsl.Model(model_xml("hexapod"))
+    ref = m.eval_gaits_detail(p, 37)["cot"]
+    for fb, mr in ((32, 255), (32, 128), (32, 96), (64, 128)):
+        m.set_tuning(fb, mr)
+        got = m.eval_gaits(p, 37)["cot"]
+        assert np.array_equal(got, ref, equal_nan=True), (fb, mr)
+
+
+def test_full_size_properties(hsl, orc):
+    """BASELINE config 2 at full size (4096 x 256): determinism, batch-order invariance, agreement with the oracle on
+    a sampled subset, ranking of the sample identical, static-limit rows carry the weight."""
+    n, n_t = 4096, 256
+    p = _random_candidates("hexapod", n, 20261018)
+    p[:8, 8] = 1e-6; p[:8, 9] = 1e-6        # static-limit rows
+    m = hsl.Model(model_xml("hexapod"))
+    a = m.eval_gaits(p, n_t)
+    b = m.eval_gaits(p, n_t)
+    for k in ("cot", "work", "min_cfz", "max_mu"):
+        assert np.array_equal(a[k], b[k], equal_nan=True)          # bit-reproducible run to run
+    perm = np.random.default_rng(0).permutation(n)
+    c = m.eval_gaits(p[perm], n_t)
+    assert np.array_equal(c["cot"], a["cot"][perm], equal_nan=True)  # a candidate's cost does not depend on its neighbours
+    ok = np.where(a["status"] == 0)[0]
+    assert ok.size > n // 2
+    sample = ok[np.linspace(0, ok.size - 1, 12).astype(int)]
+    ref = orc.Model(model_xml("hexapod")).eval_batch(p[sample], n_t, nthreads=12)
+    assert (ref["status"] == 0).all()
+    assert np.abs(a["cot"][sample] - ref["cot"]).max() <= TOL * np.abs(ref["cot"]).max()
+    assert np.array_equal(np.argsort(a["cot"][sample]), np.argsort(ref["cot"]))
+    # static limit: work vanishes, every contact force is a share of the weight (min_cfz > 0)
+    st = [i for i in range(8) if a["status"][i] == 0]
+    assert len(st) >= 4 and (a["min_cfz"][st] > 0).all() and (a["work"][st] < 1e-4).all()
+    # unreachable candidates report NaN and a status bit, never garbage
+    badrows = a["status"] & 3 != 0
+    assert np.isnan(a["cot"][badrows]).all() and np.isfinite(a["cot"][~badrows]).all()
