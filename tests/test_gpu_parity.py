@@ -176,14 +176,16 @@ def test_frame_solve_ragged_sizes(hsl, orc):
 
 
 def test_kernel_variants_agree(hsl):
-    """All occupancy variants of the cost-only kernel and the detail kernel give identical costs (same arithmetic)."""
+    """All occupancy variants of the cost-only kernel and the detail kernel agree to round-off (they are separate
+    compilations of the same source: instruction scheduling / FMA contraction may differ in the last bits)."""
     p = _random_candidates("hexapod", 96, 3)
     m = hsl.Model(model_xml("hexapod"))
     ref = m.eval_gaits_detail(p, 37)["cot"]
     for fb, mr in ((32, 255), (32, 128), (32, 96), (64, 128)):
         m.set_tuning(fb, mr)
         got = m.eval_gaits(p, 37)["cot"]
-        assert np.array_equal(got, ref, equal_nan=True), (fb, mr)
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (fb, mr)
+        assert np.nanmax(np.abs(got - ref) / np.abs(ref)) < 1e-12, (fb, mr)
 
 
 def test_full_size_properties(hsl, orc):
