@@ -184,28 +184,54 @@ HSL_HD void foot_target(const HslCand& cd, int limb, double t, double* p) {
 
 // ------------------------------------------------------------------ closed-form limb IK (a3)
 // lik.cpp:151-223.  pl = foot target in the hip joint frame.  Returns false when out of reach.
-HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, double* ang) {
+// The reference computes the three joint angles with atan2 / acos and the FK that follows takes their
+// sines and cosines again.  Here the cosines and sines of the joint angles are formed algebraically from
+// the same intermediate quantities (cos(acos(c)) = c, sin(acos(c)) = sqrt((1-c)(1+c)), angle-sum formulas),
+// so the hot path needs no inverse trigonometry at all; the angles themselves (ang != nullptr) are only
+// evaluated when a trajectory dump is requested.
+//   q0 = -phi,  q1 = -theta + beta,  q2 = -(beta + gamma)                       (lik.cpp:181,220)
+HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, double* cq, double* sq, double* ang) {
   const double l0 = L.ls[0], l1 = L.ls[1], l2 = L.ls[2];
   const int s0 = L.ysign, s1 = 2 * (L.bend != 0) - 1;
   const bool yxx = (L.kind == HSL_IK_YXX);
   const double zoff = yxx ? pl[2] - s0 * l0 : pl[2] + l0;
-  double l = sqrt(pl[0] * pl[0] + pl[1] * pl[1] + zoff * zoff);
+  const double rho2 = pl[0] * pl[0] + pl[1] * pl[1];
+  double l = sqrt(rho2 + zoff * zoff);
   bool ok = true;
   if (l1 + l2 - l < 0) {
     if (ignore_reach) l = l1 + l2; else ok = false;
   }
   const double c = zoff / l;
-  double phi = atan2(pl[0], pl[1]);
-  double theta = yxx ? acos(c) + (1 - s0) * M_PI / 2 : acos(c) - s0 * M_PI / 2;
-  wrap_pm_pi(phi);
-  wrap_pm_pi(theta);
   const double ll = l * l, del = l2 * l2 - l1 * l1;
   const int sg = yxx ? s1 * s0 : s1;
-  const double beta = sg * acos((ll - del) / (2 * l1 * l));
-  const double gamma = sg * acos((ll + del) / (2 * l2 * l));
-  ang[0] = -phi;
-  ang[1] = -theta + beta;
-  ang[2] = -(beta + gamma);
+  const double cb = (ll - del) / (2 * l1 * l);
+  const double cg = (ll + del) / (2 * l2 * l);
+  // phi = atan2(x, y): cos(phi) = y / rho, sin(phi) = x / rho  (atan2(0,0) = 0)
+  const double rho = sqrt(rho2);
+  const double cphi = (rho > 0) ? pl[1] / rho : 1.0, sphi = (rho > 0) ? pl[0] / rho : 0.0;
+  const double st0 = sqrt((1 - c) * (1 + c));  // sin(acos(c)) >= 0 ; NaN when |c| > 1, as acos would be
+  double cth, sth;
+  if (yxx) {  // theta = acos(c) + (1 - s0) pi/2 : unchanged for s0 = 1, shifted by pi for s0 = -1
+    cth = (s0 > 0) ? c : -c;
+    sth = (s0 > 0) ? st0 : -st0;
+  } else {    // theta = acos(c) - s0 pi/2
+    cth = s0 * st0;
+    sth = -s0 * c;
+  }
+  const double sb = sg * sqrt((1 - cb) * (1 + cb)), sgm = sg * sqrt((1 - cg) * (1 + cg));
+  cq[0] = cphi;                 sq[0] = -sphi;
+  cq[1] = cth * cb + sth * sb;  sq[1] = cth * sb - sth * cb;
+  cq[2] = cb * cg - sb * sgm;   sq[2] = -(sb * cg + cb * sgm);
+  if (ang) {
+    double phi = atan2(pl[0], pl[1]);
+    double theta = yxx ? acos(c) + (1 - s0) * M_PI / 2 : acos(c) - s0 * M_PI / 2;
+    wrap_pm_pi(phi);
+    wrap_pm_pi(theta);
+    const double beta = sg * acos(cb), gamma = sg * acos(cg);
+    ang[0] = -phi;
+    ang[1] = -theta + beta;
+    ang[2] = -(beta + gamma);
+  }
   return ok;
 }
 
@@ -216,15 +242,15 @@ template <int NF, int FB>
 struct HslSmem {
   double* pos;   // [(3*NF + ntrunk)*3][FB]   COM positions
   double* ust;   // [(3*NF + 1)*3][FB]        u*sin(theta) of body rotations (one entry for all trunk bodies)
-  double* q;     // [3*NF][FB]                hinge angles
+  double* cs;    // [6*NF][FB]                cos, sin of the hinge angles
   double* part;  // [NF*HSL_PART][FB]         limb -> trunk partials ; reused for limb -> trunk results after phase D
   double* mu;    // [7][FB]                   trunk -> limb multiplier (+ validity)
-  HSL_HD static int doubles_per_slot(int ntrunk) { return (3 * NF + ntrunk) * 3 + (3 * NF + 1) * 3 + 3 * NF + NF * 19 + 7; }
+  HSL_HD static int doubles_per_slot(int ntrunk) { return (3 * NF + ntrunk) * 3 + (3 * NF + 1) * 3 + 6 * NF + NF * 19 + 7; }
   HSL_HD void carve(double* base, int ntrunk) {
     pos = base;
     ust = pos + (3 * NF + ntrunk) * 3 * FB;
-    q = ust + (3 * NF + 1) * 3 * FB;
-    part = q + 3 * NF * FB;
+    cs = ust + (3 * NF + 1) * 3 * FB;
+    part = cs + 6 * NF * FB;
     mu = part + NF * 19 * FB;
   }
 };
@@ -256,23 +282,45 @@ struct HslTrunkState {
 
 // ------------------------------------------------------------------ phase A
 // FK of one hinge body given its parent's frame (model.cpp:183-195): joint frame, body frame, COM, ust.
-HSL_HD void hinge_fk(const HslHinge& H, double qv, const double* Rp, const double* tp, double* Rb, double* tb,
-                     double* jpos, double* axis, double* com, double* ust) {
-  double Rj[9];
-  m3_mul(Rp, H.Rjp, Rj);
-  m3_affine(Rp, H.tjp, tp, jpos);
-  axis[0] = Rj[6]; axis[1] = Rj[7]; axis[2] = Rj[8];  // dynpart::get_joint_zaxis, dynrec.cpp:84-93
-  double sn, cs;
-  sincos(qv, &sn, &cs);
-  double Rz[9];
+// cs, sn = cosine and sine of the joint value.
+template <int AX>  // rotation about the parent-frame coordinate axis AX (cyclic AX -> B -> C)
+HSL_HD void rot_about_axis(const double* Rp, double cs, double sn, double* Rb) {
+  constexpr int B = (AX + 1) % 3, C = (AX + 2) % 3;
 #pragma unroll
-  for (int i = 0; i < 3; i++) {  // Rj * Rz(q), model.cpp:49-57
-    Rz[i] = Rj[i] * cs + Rj[3 + i] * sn;
-    Rz[3 + i] = Rj[3 + i] * cs - Rj[i] * sn;
-    Rz[6 + i] = Rj[6 + i];
+  for (int i = 0; i < 3; i++) {
+    Rb[3 * AX + i] = Rp[3 * AX + i];
+    Rb[3 * B + i] = Rp[3 * B + i] * cs + Rp[3 * C + i] * sn;
+    Rb[3 * C + i] = Rp[3 * C + i] * cs - Rp[3 * B + i] * sn;
   }
-  m3_mul(Rz, H.Rpb, Rb);
-  m3_affine(Rz, H.tpb, jpos, tb);
+}
+HSL_HD void hinge_fk(const HslHinge& H, double cs, double sn, const double* Rp, const double* tp, double* Rb, double* tb,
+                     double* jpos, double* axis, double* com, double* ust) {
+  m3_affine(Rp, H.tjp, tp, jpos);
+  if (H.aligned != 0) {
+    // hinge axis is +-(a coordinate axis of the parent frame) and the joint sits at the body origin (all three
+    // reference models): A_parent * Rz(q) * A_pj_body is the rotation by q about that axis -- two column mixes.
+    const int a = (H.aligned > 0 ? H.aligned : -H.aligned) - 1;
+    const double sg = (H.aligned > 0) ? 1.0 : -1.0, s2 = sg * sn;
+    if (a == 0) rot_about_axis<0>(Rp, cs, s2, Rb);
+    else if (a == 1) rot_about_axis<1>(Rp, cs, s2, Rb);
+    else rot_about_axis<2>(Rp, cs, s2, Rb);
+    const double* ca = (a == 0) ? Rp : (a == 1) ? Rp + 3 : Rp + 6;
+    axis[0] = sg * ca[0]; axis[1] = sg * ca[1]; axis[2] = sg * ca[2];
+    tb[0] = jpos[0]; tb[1] = jpos[1]; tb[2] = jpos[2];
+  } else {
+    double Rj[9];
+    m3_mul(Rp, H.Rjp, Rj);
+    axis[0] = Rj[6]; axis[1] = Rj[7]; axis[2] = Rj[8];  // dynpart::get_joint_zaxis, dynrec.cpp:84-93
+    double Rz[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {  // Rj * Rz(q), model.cpp:49-57
+      Rz[i] = Rj[i] * cs + Rj[3 + i] * sn;
+      Rz[3 + i] = Rj[3 + i] * cs - Rj[i] * sn;
+      Rz[6 + i] = Rj[6 + i];
+    }
+    m3_mul(Rz, H.Rpb, Rb);
+    m3_affine(Rz, H.tpb, jpos, tb);
+  }
   m3_affine(Rb, H.com, tb, com);
   ust[0] = (Rb[5] - Rb[7]) / 2;  // dynrec.cpp:142-145: (A(2,1)-A(1,2))/2 ...
   ust[1] = (Rb[6] - Rb[2]) / 2;
@@ -302,7 +350,7 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
     st.contact = A.f_contacts[fb * M.nf + limb] != 0;
     return;
   }
-  double R0[9], t0[3], qt[3], eul[3], qa[3];
+  double R0[9], t0[3], qt[3], eul[3], qa[3], cq[3], sq[3];
   if (MODE == HSL_MODE_GAIT) {
     const HslCand& cd = A.cand[sl.c];
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
@@ -326,11 +374,14 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
     for (int k = 0; k < 3; k++) d[k] = p[k] - th[k];
 #pragma unroll
     for (int k = 0; k < 3; k++) pl[k] = Rh[3 * k] * d[0] + Rh[3 * k + 1] * d[1] + Rh[3 * k + 2] * d[2];
-    if (!limb_ik(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, qa)) st.bad |= HSL_ST_UNREACHABLE;
+    const bool want_angles = DUMP && A.q_out != nullptr;
+    if (!limb_ik(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, cq, sq, want_angles ? qa : nullptr)) st.bad |= HSL_ST_UNREACHABLE;
   } else {  // HSL_MODE_TRAJ
     const double* qrow = A.traj + (sl.c * (A.n_t + 5) + sl.i) * M.config_dim;
 #pragma unroll
     for (int k = 0; k < 3; k++) { qt[k] = qrow[k]; eul[k] = qrow[3 + k]; qa[k] = qrow[6 + 3 * limb + k]; }
+#pragma unroll
+    for (int k = 0; k < 3; k++) sincos(qa[k], &sq[k], &cq[k]);
     euler_to_R(eul[0], eul[1], eul[2], R0);
     torso_frame(M, qt, R0, t0);
   }
@@ -343,13 +394,14 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
 #pragma unroll
   for (int h = 0; h < 3; h++) {
     double ust[3];
-    hinge_fk(L.h[h], qa[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    hinge_fk(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       sm.pos[((3 * limb + h) * 3 + k) * FB + sl.s] = st.pos[h][k];
       sm.ust[((3 * limb + h) * 3 + k) * FB + sl.s] = ust[k];
     }
-    sm.q[(3 * limb + h) * FB + sl.s] = qa[h];
+    sm.cs[(6 * limb + 2 * h) * FB + sl.s] = cq[h];
+    sm.cs[(6 * limb + 2 * h + 1) * FB + sl.s] = sq[h];
 #pragma unroll
     for (int k = 0; k < 9; k++) Rp[k] = Rb[k];
 #pragma unroll
@@ -477,9 +529,11 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
         nn[h][k] = fd2(sm.ust + ((3 * limb + h) * 3 + k) * FB, sl.s, FB, hh, L.h[h].inertia);
       }
       f[h][2] += L.h[h].mass * M.g;  // dynrec.cpp:293-297
-      // joint rate, periodic.cpp:261-282
-      double d = sm.q[(3 * limb + h) * FB + sl.s + 1] - sm.q[(3 * limb + h) * FB + sl.s - 1];
-      if (d > M_PI) d -= 2 * M_PI; else if (d < -M_PI) d += 2 * M_PI;
+      // joint rate, periodic.cpp:261-282: (q(s+1) - q(s-1)) wrapped to (-pi, pi], over 2 dt.  The wrapped
+      // difference is the angle of the unit complex number e^{i q(s+1)} * conj(e^{i q(s-1)}).
+      const double* csr = sm.cs + (6 * limb + 2 * h) * FB + sl.s;
+      const double cp = csr[1], sp = csr[FB + 1], cm = csr[-1], sm_ = csr[FB - 1];
+      const double d = atan2(sp * cm - cp * sm_, cp * cm + sp * sm_);
       st.qd[h] = d / (2 * dt);
     }
   }

@@ -29,7 +29,8 @@ typedef struct HslHinge {
   double Rpb[9], tpb[3];  // modelnode::A_pj_body  (joint frame past the hinge -> body frame), model.cpp:138-141
   double com[3];          // translation of odepart::A_body_geom (COM in body frame), visualization.cpp:541-545
   double mass, inertia;   // ODE dBodyCreate defaults: 1 and identity (dynrec.cpp:62-68)
-  int32_t body, pad;      // DFS body id
+  int32_t body;           // DFS body id
+  int32_t aligned;        // +-(1,2,3): hinge axis is +-x,y,z of the parent frame and the joint sits at the body origin; 0: general
 } HslHinge;
 
 typedef struct HslLimb {

@@ -248,6 +248,13 @@ int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* errbuf, in
         }
         for (int k = 0; k < 3; k++) H.com[k] = b.com[k];
         H.mass = 1.0; H.inertia = 1.0;
+        H.aligned = 0;
+        {  // axis-aligned hinge at the body origin: lets the kernels rotate two columns instead of two 3x3 products
+          double an = std::sqrt(b.axis[0] * b.axis[0] + b.axis[1] * b.axis[1] + b.axis[2] * b.axis[2]);
+          for (int k = 0; k < 3 && an > 0; k++)
+            if (std::fabs(std::fabs(b.axis[k]) / an - 1.0) < 1e-14 && b.jpos[0] == 0 && b.jpos[1] == 0 && b.jpos[2] == 0)
+              H.aligned = (b.axis[k] > 0) ? (k + 1) : -(k + 1);
+        }
         M.motor_of_body[id] = motor++;
         if (h < 2) {
           if (b.kids.size() != 1) return fail(-3, "limb link must have exactly one child");
