@@ -62,6 +62,7 @@ def _load():
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
     lib.hsl_launch_count.argtypes = [vp]
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
+    lib.hsl_math_selftest.argtypes = [i32, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -71,7 +72,7 @@ def exported_symbols():
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_set_tuning", "hsl_launch_count",
-            "hsl_dfma_probe"]
+            "hsl_dfma_probe", "hsl_math_selftest"]
 
 
 def _check(rc):
@@ -205,6 +206,15 @@ def dfma_probe(blocks=148 * 8, threads=256, iters=4096):
     ms = C.c_float()
     _check(_load().hsl_dfma_probe(blocks, threads, iters, C.byref(tf), C.byref(ms)))
     return tf.value, ms.value
+
+
+def math_selftest(a, b):
+    """Device results of the kernels' branch-free primitives next to the library ones: dict of (ours, reference) pairs."""
+    a = np.ascontiguousarray(a, np.float64)
+    b = np.ascontiguousarray(b, np.float64)
+    out = np.empty((10, a.size))
+    _check(_load().hsl_math_selftest(a.size, _p(a), _p(b), _p(out)))
+    return dict(div=(out[0], out[1]), sqrt=(out[2], out[3]), atan2=(out[4], out[5]), sin=(out[6], out[7]), cos=(out[8], out[9]))
 
 
 def measure_cot(model, params, n_t, flags=0):

@@ -350,6 +350,20 @@ int hsl_solve_frames_host(HslModel* m, int64_t F, const double* pos, const doubl
   return HSL_OK;
 }
 
+// out: [10][n] = hsl_div, a/b, hsl_sqrt(|a|), sqrt(|a|), hsl_atan2(a,b), atan2(a,b), then sin, sin_ref, cos, cos_ref of |a| (|a| <= pi)
+int hsl_math_selftest(int n, const double* a, const double* b, double* out) {
+  double *da = nullptr, *db = nullptr, *dout = nullptr;
+  HSL_CUDA(cudaMalloc(&da, sizeof(double) * n));
+  HSL_CUDA(cudaMalloc(&db, sizeof(double) * n));
+  HSL_CUDA(cudaMalloc(&dout, sizeof(double) * 10 * n));
+  HSL_CUDA(cudaMemcpy(da, a, sizeof(double) * n, cudaMemcpyHostToDevice));
+  HSL_CUDA(cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+  HSL_CUDA(hsl_launch_math_selftest(n, da, db, dout, nullptr));
+  HSL_CUDA(cudaMemcpy(out, dout, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost));
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return HSL_OK;
+}
+
 int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms) {
   double* d = nullptr;
   HSL_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));

@@ -37,6 +37,7 @@
 #include <stdint.h>
 
 #include "hsl_model.h"
+#include "hsl_fastmath.h"
 
 #if defined(__CUDACC__)
 #define HSL_HD __host__ __device__ __forceinline__
@@ -153,16 +154,16 @@ HSL_HD void torso_frame(const HslModelPod& M, const double* qt, const double* R0
 }
 // Foot target of one limb at time t: periodicgenerator::limb_positions / turn_position, pergen.cpp:62-94,160-183.
 HSL_HD void foot_target(const HslCand& cd, int limb, double t, double* p) {
-  const double tr = t / cd.period;
+  const double tr = hsl_div(t, cd.period);
   const int t_int = (int)tr;
   const double tf = tr - t_int;
   const double tl = cd.ts[limb];
   double sf;
   if (tf < tl) sf = 0;
-  else if (tf < tl + cd.t_step) sf = (tf - tl) / cd.t_step;
+  else if (tf < tl + cd.t_step) sf = hsl_div(tf - tl, cd.t_step);
   else sf = 1;
   double sn, cs;
-  sincos(M_PI * sf, &sn, &cs);
+  hsl_sincos_0_pi(M_PI * sf, &sn, &cs);
   double dx = (t_int + cd.xs[limb] + (1 - cs) / 2) * cd.step_length;
   double dy = 0;
   const double dz = sn * sn * cd.step_height;
@@ -196,20 +197,20 @@ HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, doubl
   const bool yxx = (L.kind == HSL_IK_YXX);
   const double zoff = yxx ? pl[2] - s0 * l0 : pl[2] + l0;
   const double rho2 = pl[0] * pl[0] + pl[1] * pl[1];
-  double l = sqrt(rho2 + zoff * zoff);
+  double l = hsl_sqrt(rho2 + zoff * zoff);
   bool ok = true;
   if (l1 + l2 - l < 0) {
     if (ignore_reach) l = l1 + l2; else ok = false;
   }
-  const double c = zoff / l;
+  const double c = hsl_div(zoff, l);
   const double ll = l * l, del = l2 * l2 - l1 * l1;
   const int sg = yxx ? s1 * s0 : s1;
-  const double cb = (ll - del) / (2 * l1 * l);
-  const double cg = (ll + del) / (2 * l2 * l);
+  const double cb = hsl_div(ll - del, 2 * l1 * l);
+  const double cg = hsl_div(ll + del, 2 * l2 * l);
   // phi = atan2(x, y): cos(phi) = y / rho, sin(phi) = x / rho  (atan2(0,0) = 0)
-  const double rho = sqrt(rho2);
-  const double cphi = (rho > 0) ? pl[1] / rho : 1.0, sphi = (rho > 0) ? pl[0] / rho : 0.0;
-  const double st0 = sqrt((1 - c) * (1 + c));  // sin(acos(c)) >= 0 ; NaN when |c| > 1, as acos would be
+  const double rrho = hsl_rcp(hsl_sqrt(rho2));
+  const double cphi = (rho2 > 0) ? pl[1] * rrho : 1.0, sphi = (rho2 > 0) ? pl[0] * rrho : 0.0;
+  const double st0 = hsl_sqrt((1 - c) * (1 + c));  // sin(acos(c)) >= 0 ; NaN when |c| > 1, as acos would be
   double cth, sth;
   if (yxx) {  // theta = acos(c) + (1 - s0) pi/2 : unchanged for s0 = 1, shifted by pi for s0 = -1
     cth = (s0 > 0) ? c : -c;
@@ -218,7 +219,7 @@ HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, doubl
     cth = s0 * st0;
     sth = -s0 * c;
   }
-  const double sb = sg * sqrt((1 - cb) * (1 + cb)), sgm = sg * sqrt((1 - cg) * (1 + cg));
+  const double sb = sg * hsl_sqrt((1 - cb) * (1 + cb)), sgm = sg * hsl_sqrt((1 - cg) * (1 + cg));
   cq[0] = cphi;                 sq[0] = -sphi;
   cq[1] = cth * cb + sth * sb;  sq[1] = cth * sb - sth * cb;
   cq[2] = cb * cg - sb * sgm;   sq[2] = -(sb * cg + cb * sgm);
@@ -476,13 +477,13 @@ HSL_HD double fd2(const double* a, int s, int FB_, double hh, double scale) {
 // In-place inverse of a symmetric positive definite 3x3 stored as (00,01,02,11,12,22), via LDL^T.
 HSL_HD bool spd3_inverse(const double* H, double* W) {
   const double d0 = H[0];
-  const double i0 = 1.0 / d0;
+  const double i0 = hsl_rcp(d0);
   const double l10 = H[1] * i0, l20 = H[2] * i0;
   const double d1 = H[3] - l10 * H[1];
-  const double i1 = 1.0 / d1;
+  const double i1 = hsl_rcp(d1);
   const double l21 = (H[4] - l20 * H[1]) * i1;
   const double d2 = H[5] - l20 * H[2] - l21 * l21 * d1;
-  const double i2 = 1.0 / d2;
+  const double i2 = hsl_rcp(d2);
   // inverse of L (unit lower): m10 = -l10, m21 = -l21, m20 = l10*l21 - l20
   const double m10 = -l10, m21 = -l21, m20 = l10 * l21 - l20;
   W[5] = i2;
@@ -521,6 +522,8 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
     double hh, dt;
     if (MODE == HSL_MODE_GAIT) { hh = A.cand[sl.c].hh; dt = A.cand[sl.c].dt; }
     else { dt = A.dt_in[sl.c]; hh = 1. / (2 * dt); }
+    double sdv[3], cdv[3], dang[3];
+    bool slow[3];
 #pragma unroll
     for (int h = 0; h < 3; h++) {
 #pragma unroll
@@ -533,9 +536,17 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
       // difference is the angle of the unit complex number e^{i q(s+1)} * conj(e^{i q(s-1)}).
       const double* csr = sm.cs + (6 * limb + 2 * h) * FB + sl.s;
       const double cp = csr[1], sp = csr[FB + 1], cm = csr[-1], sm_ = csr[FB - 1];
-      const double d = atan2(sp * cm - cp * sm_, cp * cm + sp * sm_);
-      st.qd[h] = d / (2 * dt);
+      sdv[h] = sp * cm - cp * sm_;
+      cdv[h] = cp * cm + sp * sm_;
+      dang[h] = hsl_small_angle(sdv[h], cdv[h], &slow[h]);
     }
+    if (slow[0] || slow[1] || slow[2]) {  // large step between frames (rare): library arctangent
+#pragma unroll
+      for (int h = 0; h < 3; h++)
+        if (slow[h]) dang[h] = atan2(sdv[h], cdv[h]);
+    }
+#pragma unroll
+    for (int h = 0; h < 3; h++) st.qd[h] = dang[h] * hh;
   }
   // backward Newton-Euler recursion foot -> hip: F_j = f_j + F_child,
   // T_j = n_j + (pos_j - jpos_j) x f_j + T_child + (jpos_child - jpos_j) x F_child   (rows of B, dynrec.cpp:227-291)
@@ -658,7 +669,7 @@ HSL_HD bool spd6_solve(double S[6][6], double* b) {
     for (int k = 0; k < j; k++) d -= S[j][k] * ld[k];
     ok = ok && (d > tol);
     dd[j] = d;
-    dinv[j] = 1.0 / d;
+    dinv[j] = hsl_rcp(d);
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double v = S[i][j];
@@ -745,7 +756,7 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslS
       // (torque about the line through both contact points).  Project it out of b and regularise S with it.
       double d[3] = {rA[0] - rB[0], rA[1] - rB[1], rA[2] - rB[2]}, nf_[3];
       v3_cross(rA, d, nf_);
-      const double nn = 1.0 / sqrt(v3_dot(nf_, nf_) + v3_dot(d, d));
+      const double nn = hsl_rcp(hsl_sqrt(v3_dot(nf_, nf_) + v3_dot(d, d)));
       const double nv[6] = {nf_[0] * nn, nf_[1] * nn, nf_[2] * nn, d[0] * nn, d[1] * nn, d[2] * nn};
       double pb = 0;
 #pragma unroll
@@ -891,7 +902,7 @@ HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
   double cfz = 1e300, mu_f = -1e300;
   if (con) {  // periodic.cpp:347-357, over the feet that are on the ground
     cfz = lam[2];
-    mu_f = sqrt(lam[0] * lam[0] + lam[1] * lam[1]) / lam[2];
+    mu_f = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
   }
   double* P = sm.part + (limb * HSL_PART) * FB + sl.s;
   P[0] = work;

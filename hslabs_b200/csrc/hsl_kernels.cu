@@ -148,6 +148,22 @@ __global__ void hsl_dfma_probe_kernel(double* out, int iters, double a, double b
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// Accuracy self-test of the branch-free primitives of hsl_fastmath.h against the IEEE / CUDA library operations.
+__global__ void hsl_math_selftest_kernel(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = hsl_div(a[i], b[i]);
+  out[n + i] = a[i] / b[i];
+  out[2 * n + i] = hsl_sqrt(fabs(a[i]));
+  out[3 * n + i] = sqrt(fabs(a[i]));
+  out[4 * n + i] = hsl_atan2(a[i], b[i]);
+  out[5 * n + i] = atan2(a[i], b[i]);
+  double sn, cs, sr, cr;
+  hsl_sincos_0_pi(fabs(a[i]), &sn, &cs);
+  sincos(fabs(a[i]), &sr, &cr);
+  out[6 * n + i] = sn; out[7 * n + i] = sr; out[8 * n + i] = cs; out[9 * n + i] = cr;
+}
+
 // ------------------------------------------------------------------ launchers
 namespace {
 template <int NF, int FB, int MODE, bool DUMP, int MAXREG = 255>
@@ -214,6 +230,11 @@ cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const 
   const int64_t threads = n_cand * 32;
   hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
                                                                          fmax_in, status, cot, work, min_cfz, max_mu);
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, double* out, cudaStream_t st) {
+  hsl_math_selftest_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, a, b, out);
   return cudaGetLastError();
 }
 

@@ -84,6 +84,7 @@ int hsl_solve_frames_host(HslModel* m, int64_t n_frames, const double* pos, cons
 int hsl_set_tuning(HslModel* m, int fb, int maxreg);          /* cost-only kernel variant: frame slots per block (32|64), register cap per thread */
 int64_t hsl_launch_count(const HslModel* m);                  /* kernels launched through this handle so far */
 int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms); /* FP64 FMA throughput of the device */
+int hsl_math_selftest(int n, const double* a, const double* b, double* out /*[10][n]*/); /* accuracy of the kernels' branch-free div/sqrt/atan2/sincos vs the library ones (HOST pointers) */
 
 #ifdef __cplusplus
 }
