@@ -111,7 +111,7 @@ size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap) {
   return sizeof(HslModelPod);
 }
 int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
-  if (!m || (fb != 32 && fb != 64) || maxreg < 64 || maxreg > 255) return set_err(HSL_ERR_ARG, "frame slots per block must be 32 or 64; register cap 64..255");
+  if (!m || (fb != 32 && fb != 64) || (maxreg != 1 && (maxreg < 64 || maxreg > 255))) return set_err(HSL_ERR_ARG, "frame slots per block must be 32 or 64; register cap 64..255, or 1 for the pipelined kernel");
   m->fb = fb;
   m->maxreg = maxreg;
   return HSL_OK;

@@ -239,23 +239,25 @@ HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, doubl
 // ------------------------------------------------------------------ shared-memory view
 // All exchange arrays are [field][slot] so that consecutive lanes (= consecutive frames) hit
 // consecutive 8-byte words: conflict-free LDS.64 / STS.64.
-template <int NF, int FB>
+template <int NF, int FB, int PARTN = 19>
 struct HslSmem {
+  static constexpr int PART = PARTN;  // doubles per limb in `part`
   double* pos;   // [(3*NF + ntrunk)*3][FB]   COM positions
   double* ust;   // [(3*NF + 1)*3][FB]        u*sin(theta) of body rotations (one entry for all trunk bodies)
   double* cs;    // [6*NF][FB]                cos, sin of the hinge angles
-  double* part;  // [NF*HSL_PART][FB]         limb -> trunk partials ; reused for limb -> trunk results after phase D
+  double* part;  // [NF*PART][FB]             limb -> trunk partials ; reused for limb -> trunk results after phase D
   double* mu;    // [7][FB]                   trunk -> limb multiplier (+ validity)
-  HSL_HD static int doubles_per_slot(int ntrunk) { return (3 * NF + ntrunk) * 3 + (3 * NF + 1) * 3 + 6 * NF + NF * 19 + 7; }
+  HSL_HD static int doubles_per_slot(int ntrunk) { return (3 * NF + ntrunk) * 3 + (3 * NF + 1) * 3 + 6 * NF + NF * PARTN + 7; }
   HSL_HD void carve(double* base, int ntrunk) {
     pos = base;
     ust = pos + (3 * NF + ntrunk) * 3 * FB;
     cs = ust + (3 * NF + 1) * 3 * FB;
     part = cs + 6 * NF * FB;
-    mu = part + NF * 19 * FB;
+    mu = part + NF * PARTN * FB;
   }
 };
-#define HSL_PART 19  // Fl[3] Tl[3] W[6] Wg[3] r[3] contact
+// part layout per limb: [0..2] Fl  [3..5] Tl  [6..11] W  [12..14] Wg  [15..17] r  [18] contact flag
+// (pipelined kernel, PART = 34: + [19..21] tau_p  [22..30] w  [31..33] qdot)
 
 // Where a thread sits.
 struct HslSlot {
@@ -328,8 +330,8 @@ HSL_HD void hinge_fk(const HslHinge& H, double cs, double sn, const double* Rp, 
   ust[2] = (Rb[1] - Rb[3]) / 2;
 }
 
-template <int NF, int FB, int MODE, bool DUMP>
-HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, int limb,
+template <int NF, int FB, int MODE, bool DUMP, class SM>
+HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
                         HslLegState<DUMP>& st) {
   const HslLimb& L = M.limb[limb];
   st.bad = 0;
@@ -421,8 +423,8 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
   }
 }
 
-template <int NF, int FB, int MODE>
-HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl,
+template <int NF, int FB, int MODE, class SM>
+HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl,
                           HslTrunkState& st) {
   if (MODE == HSL_MODE_FIELDS) return;
   double qt[3], eul[3];
@@ -458,8 +460,8 @@ HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const Hsl
 // Reference point of the torso (root) wrench.  The root's torque row of B has no (jpos - pos) x F term
 // (the cross elements are only inserted when the body has a parent, dynrec.cpp:282-287), so its joint
 // torque is taken about the torso COM, which moves with the frame.
-template <int NF, int FB, int MODE>
-HSL_HD void root_ref(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, double* ref) {
+template <int NF, int FB, int MODE, class SM>
+HSL_HD void root_ref(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, double* ref) {
 #pragma unroll
   for (int k = 0; k < 3; k++)
     ref[k] = (MODE == HSL_MODE_FIELDS) ? A.f_pos[((int64_t)sl.i * M.n + M.trunk[0].body) * 3 + k]
@@ -501,8 +503,8 @@ HSL_HD void sym3_mul(const double* W, const double* x, double* y) {
   y[2] = W[2] * x[0] + W[4] * x[1] + W[5] * x[2];
 }
 
-template <int NF, int FB, int MODE, bool DUMP>
-HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, int limb,
+template <int NF, int FB, int MODE, bool DUMP, class SM>
+HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
                         HslLegState<DUMP>& st) {
   const HslLimb& L = M.limb[limb];
   double f[3][3], nn[3][3];
@@ -572,7 +574,7 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
 #pragma unroll
   for (int k = 0; k < 3; k++) d[k] = st.jpos[0][k] - ref[k];
   v3_cross_add(d, F, T);
-  double* P = sm.part + (limb * HSL_PART) * FB + sl.s;
+  double* P = sm.part + (limb * SM::PART) * FB + sl.s;
 #pragma unroll
   for (int k = 0; k < 3; k++) { P[k * FB] = F[k]; P[(3 + k) * FB] = T[k]; }
   P[18 * FB] = st.contact ? 1.0 : 0.0;
@@ -614,8 +616,8 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
   }
 }
 
-template <int NF, int FB, int MODE>
-HSL_HD void phase_b_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl,
+template <int NF, int FB, int MODE, class SM>
+HSL_HD void phase_b_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl,
                           HslTrunkState& st) {
 #pragma unroll
   for (int k = 0; k < 3; k++) { st.F0[k] = 0; st.T0[k] = 0; }
@@ -691,8 +693,8 @@ HSL_HD bool spd6_solve(double S[6][6], double* b) {
   return ok;
 }
 
-template <int NF, int FB, int MODE, bool DUMP>
-HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl,
+template <int NF, int FB, int MODE, bool DUMP, class SM>
+HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl,
                          HslTrunkState& st) {
   int bad = 0;
   double b[6] = {st.F0[0], st.F0[1], st.F0[2], st.T0[0], st.T0[1], st.T0[2]};
@@ -706,7 +708,7 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslS
   double rA[3] = {0, 0, 0}, rB[3] = {0, 0, 0};
 #pragma unroll
   for (int l = 0; l < NF; l++) {
-    const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+    const double* P = sm.part + (l * SM::PART) * FB + sl.s;
 #pragma unroll
     for (int k = 0; k < 6; k++) b[k] += P[k * FB];
     if (P[18 * FB] != 0.0) {
@@ -786,7 +788,7 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslS
     bool con[NF];
 #pragma unroll
     for (int l = 0; l < NF; l++) {
-      const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+      const double* P = sm.part + (l * SM::PART) * FB + sl.s;
       con[l] = (P[18 * FB] != 0.0) && (nc >= 2);
       lam[l][0] = lam[l][1] = lam[l][2] = 0;
       if (con[l]) {
@@ -848,7 +850,7 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslS
         int a = M.limb[l].attach;
         while (a > tb) a = M.trunk[a].parent_trunk;
         if (a != tb) continue;
-        const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+        const double* P = sm.part + (l * SM::PART) * FB + sl.s;
         double Fl[3], d[3];
 #pragma unroll
         for (int k = 0; k < 3; k++) { Fl[k] = P[k * FB]; Fb[k] += Fl[k]; Tb[k] += P[(3 + k) * FB]; d[k] = ref[k] - jp[k]; }
@@ -875,8 +877,8 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const HslS
 }
 
 // ------------------------------------------------------------------ phase D (limb)
-template <int NF, int FB, int MODE, bool DUMP>
-HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl, int limb,
+template <int NF, int FB, int MODE, bool DUMP, class SM>
+HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
                         HslLegState<DUMP>& st) {
   const HslLimb& L = M.limb[limb];
   double lam[3] = {0, 0, 0};
@@ -904,7 +906,7 @@ HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
     cfz = lam[2];
     mu_f = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
   }
-  double* P = sm.part + (limb * HSL_PART) * FB + sl.s;
+  double* P = sm.part + (limb * SM::PART) * FB + sl.s;
   P[0] = work;
   P[FB] = cfz;
   P[2 * FB] = mu_f;
@@ -938,12 +940,12 @@ HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const HslSm
 }
 
 // ------------------------------------------------------------------ phase E (trunk)
-template <int NF, int FB>
-HSL_HD void phase_e_trunk(const HslFrameArgs& A, const HslSmem<NF, FB>& sm, const HslSlot& sl) {
+template <int NF, int FB, class SM>
+HSL_HD void phase_e_trunk(const HslFrameArgs& A, const SM& sm, const HslSlot& sl) {
   double work = 0, cfz = 1e300, mu = -1e300;
 #pragma unroll
   for (int l = 0; l < NF; l++) {
-    const double* P = sm.part + (l * HSL_PART) * FB + sl.s;
+    const double* P = sm.part + (l * SM::PART) * FB + sl.s;
     work += P[0];
     cfz = fmin(cfz, P[FB]);
     mu = fmax(mu, P[2 * FB]);

@@ -15,6 +15,7 @@
 
 #include "hsl_frame.h"
 #include "hsl_internal.h"
+#include "hsl_pipe.h"
 
 template <int NF, int FB, int MODE, bool DUMP, int MAXREG>
 __global__ void __maxnreg__(MAXREG)
@@ -88,6 +89,55 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
     for (int k = 0; k < 8; k++) dst[k] = clk[k];
   }
 #endif
+}
+
+// Persistent, software-pipelined cost-only kernel (see hsl_pipe.h): the trunk warps finish tile t-1 while the limb
+// warps run phase A of tile t.
+template <int NF, int FB>
+__global__ void __maxnreg__(128)
+hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A, const int64_t n_tiles) {
+  extern __shared__ double hsl_smem_raw[];
+  HslPipeSmem<NF, FB> sm;
+  sm.carve(hsl_smem_raw, M.ntrunk);
+  const int role = threadIdx.x / FB;
+  const int s = threadIdx.x % FB;
+  const int per = A.n_t + 4;
+  HslSlot prev;
+  prev.interior = false; prev.valid = false; prev.c = 0; prev.i = 0; prev.s = s; prev.fo = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    HslSlot sl;
+    sl.s = s;
+    const int64_t g = tile * (FB - 4) + s;
+    sl.c = g / per;
+    sl.i = (int32_t)(g - sl.c * per);
+    sl.valid = sl.c < A.n_cand;
+    if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+    sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+    sl.fo = sl.c * A.n_t + (sl.i - 2);
+    HslLegState<false> lst;
+    int bad = 0;
+    if (role < NF) {
+      phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
+      pipe_a_trunk_bodies<NF, FB>(M, A, sm, sl, role);
+      bad = lst.bad;
+    } else if (prev.interior) {
+      const int tb = pipe_trunk_finish<NF, FB>(A, sm, prev);
+      if (tb && A.status) atomicOr(&A.status[prev.c], tb);
+    }
+    __syncthreads();
+    if (role < NF && sl.interior) {
+      phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
+      pipe_b_extras<NF, FB>(M, A, sm, sl, role, lst);
+      bad |= lst.bad;
+    }
+    if (role < NF && bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
+    __syncthreads();
+    prev = sl;
+  }
+  if (role == NF && prev.interior) {
+    const int tb = pipe_trunk_finish<NF, FB>(A, sm, prev);
+    if (tb && A.status) atomicOr(&A.status[prev.c], tb);
+  }
 }
 
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
@@ -192,12 +242,42 @@ cudaError_t launch_frames_nf(const HslModelPod& M, const HslFrameArgs& A, int mo
 }
 }  // namespace
 
+template <int NF, int FB>
+cudaError_t launch_gait_pipe(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
+  const size_t smem = (size_t)HslPipeSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
+  auto kern = hsl_gait_pipe_kernel<NF, FB>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int64_t slots = A.n_cand * (A.n_t + 4);
+  int64_t n_tiles = (slots - 4 + (FB - 4) - 1) / (FB - 4);
+  if (n_tiles < 1) n_tiles = 1;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NF + 1) * FB, smem);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) return cudaErrorInvalidConfiguration;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > n_tiles) grid = n_tiles;
+  kern<<<(unsigned)grid, (NF + 1) * FB, smem, st>>>(M, A, n_tiles);
+  return cudaGetLastError();
+}
+
 // Cost-only evaluation (the headline path) comes in a few occupancy variants: fb = frame slots per block,
 // maxreg = register cap per thread.  The register file is 16K registers per SM sub-partition and warps are dealt
 // round-robin to the 4 sub-partitions, so ceil(resident warps / 4) * 32 * maxreg must stay <= 16384:
 // 4 warps per sub-partition -> 128 registers, 3 -> 168, 2 -> 255.
 template <int NF>
 cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int maxreg, cudaStream_t st) {
+  if (maxreg == 1) {  // software-pipelined persistent kernel
+    if (fb == 64) return launch_gait_pipe<NF, 64>(M, A, st);
+    return launch_gait_pipe<NF, 32>(M, A, st);
+  }
   if (fb == 64) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128>(M, A, st);  // 14 warps (nf=6): 4 per sub-partition
   if (maxreg <= 96) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 80>(M, A, st);   // 3 blocks x 7 warps
   if (maxreg <= 128) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 128>(M, A, st); // 2 blocks x 7 warps

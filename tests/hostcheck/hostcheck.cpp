@@ -9,6 +9,7 @@
 
 #include "../../hslabs_b200/csrc/hsl_frame.h"
 #include "../../hslabs_b200/csrc/hsl_model.h"
+#include "../../hslabs_b200/csrc/hsl_pipe.h"
 
 int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int errlen);
 
@@ -75,6 +76,61 @@ void emulate(const HslModelPod& M, const HslFrameArgs& A) {
         if (bad[r * FB + s] && sls[s].valid && A.status) A.status[sls[s].c] |= bad[r * FB + s];
   }
 }
+// Serial emulation of hsl_gait_pipe_kernel with `grid` persistent blocks (tile order per block as on the device).
+template <int NF, int FB>
+void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
+  const int64_t slots = A.n_cand * (A.n_t + 4);
+  int64_t n_tiles = (slots - 4 + (FB - 4) - 1) / (FB - 4);
+  if (n_tiles < 1) n_tiles = 1;
+  const int per = A.n_t + 4;
+  std::vector<double> smem((size_t)HslPipeSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB);
+  std::vector<HslLegState<false> > lst((size_t)NF * FB);
+  for (int blk = 0; blk < grid; blk++) {
+    HslPipeSmem<NF, FB> sm;
+    sm.carve(smem.data(), M.ntrunk);
+    std::fill(smem.begin(), smem.end(), NAN);
+    std::vector<HslSlot> prev(FB), cur(FB);
+    for (int s = 0; s < FB; s++) { prev[s].interior = false; prev[s].valid = false; }
+    auto finish = [&](std::vector<HslSlot>& sls) {
+      for (int s = 0; s < FB; s++)
+        if (sls[s].interior) {
+          int tb = pipe_trunk_finish<NF, FB>(A, sm, sls[s]);
+          if (tb && A.status) A.status[sls[s].c] |= tb;
+        }
+    };
+    for (int64_t tile = blk; tile < n_tiles; tile += grid) {
+      for (int s = 0; s < FB; s++) {
+        HslSlot& sl = cur[s];
+        sl.s = s;
+        const int64_t g = tile * (FB - 4) + s;
+        sl.c = g / per; sl.i = (int32_t)(g - sl.c * per);
+        sl.valid = sl.c < A.n_cand;
+        if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+        sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+        sl.fo = sl.c * A.n_t + (sl.i - 2);
+      }
+      // trunk finishes the previous tile from `part` BEFORE the limbs overwrite it in phase B (same order as on the device)
+      finish(prev);
+      for (int r = 0; r < NF; r++)
+        for (int s = 0; s < FB; s++) {
+          phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, cur[s], r, lst[r * FB + s]);
+          pipe_a_trunk_bodies<NF, FB>(M, A, sm, cur[s], r);
+        }
+      for (int r = 0; r < NF; r++)
+        for (int s = 0; s < FB; s++) {
+          HslLegState<false>& st = lst[r * FB + s];
+          if (cur[s].interior) {
+            phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, cur[s], r, st);
+            pipe_b_extras<NF, FB>(M, A, sm, cur[s], r, st);
+          }
+          if (st.bad && cur[s].valid && A.status) A.status[cur[s].c] |= st.bad;
+        }
+      prev = cur;
+    }
+    finish(prev);
+  }
+}
+
 template <int NF>
 void run(const HslModelPod& M, const HslFrameArgs& A, int mode) {
   if (mode == HSL_MODE_GAIT) emulate<NF, 32, HSL_MODE_GAIT, true>(M, A);
@@ -152,6 +208,29 @@ int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int
   if (contacts)
     for (int l = 0; l < M.nf; l++)
       for (int64_t f = 0; f < nfr; f++) contacts[f * M.nf + l] = dc[(size_t)l * nfr + f];
+  return 0;
+}
+
+int hc_eval_gaits_pipe(const char* xml, int64_t C, int n_t, const double* params, int flags, int fb, int grid, double* cot, double* work,
+                       double* min_cfz, double* max_mu, int32_t* status) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  const int64_t nfr = C * n_t;
+  std::vector<HslCand> cand(C);
+  std::vector<double> ttab((size_t)C * (n_t + 4)), wf(nfr, NAN), fmn(nfr, NAN), fmx(nfr, NAN);
+  std::vector<int32_t> st(C, 0);
+  for (int64_t c = 0; c < C; c++) { setup_candidate(M, params + HSL_NPARAM * c, n_t, cand[c], &ttab[c * (n_t + 4)]); st[c] = cand[c].status; }
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.flags = flags; A.n_frames = nfr;
+  A.cand = cand.data(); A.ttab = ttab.data();
+  A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
+  if (M.nf == 6) { if (fb == 64) emulate_pipe<6, 64>(M, A, grid); else emulate_pipe<6, 32>(M, A, grid); }
+  else { if (fb == 64) emulate_pipe<4, 64>(M, A, grid); else emulate_pipe<4, 32>(M, A, grid); }
+  finish(C, n_t, (double)M.n, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
+  if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
   return 0;
 }
 

@@ -66,3 +66,14 @@ def solve_frames(xml, f):
                                _p(out["status"]))
     assert rc == 0, rc
     return out
+
+
+def eval_gaits_pipe(xml, params, n_t, flags=0, fb=64, grid=3):
+    """Serial emulation of the persistent pipelined cost-only kernel."""
+    params = np.ascontiguousarray(params, np.float64).reshape(-1, 13)
+    c = params.shape[0]
+    out = dict(cot=np.zeros(c), work=np.zeros(c), min_cfz=np.zeros(c), max_mu=np.zeros(c), status=np.zeros(c, np.int32))
+    rc = lib().hc_eval_gaits_pipe(xml.encode(), C.c_int64(c), C.c_int(n_t), _p(params), C.c_int(flags), C.c_int(fb), C.c_int(grid),
+                                  *[_p(out[k]) for k in ("cot", "work", "min_cfz", "max_mu", "status")])
+    assert rc == 0, rc
+    return out

@@ -64,7 +64,7 @@ def test_unreachable_and_ignore_reach(orc):
     ref = m.measure_cot(p, 20, detail=True)
     got = hostlib.eval_gaits(xml, p, 20, flags=1)
     assert ref["status"] == 0 and not (got["status"][0] & 2)
-    assert angle_err(got["traj"][0], ref["traj"][:24]) < 1e-12
+    assert angle_err(got["traj"][0], ref["traj"][:24]) < 1e-7  # legs at full extension: acos is ill-conditioned there
 
 
 def test_bad_step_duration():
@@ -102,3 +102,28 @@ def test_frame_solve_entry(orc, pid):
     assert (got["status"] == 0).all()
     for key in ("x", "z", "tau"):
         assert rel_err(got[key], ref[key]) < TOL, key
+
+
+@pytest.mark.parametrize("model,fb,grid", [("hexapod", 64, 3), ("hexapod", 32, 2), ("myant", 64, 2), ("spider", 32, 5)])
+def test_pipelined_kernel_emulation(orc, model, fb, grid):
+    """The persistent software-pipelined cost-only kernel (hsl_pipe.h), emulated serially, against the plain kernel
+    emulation and the oracle: costs, work, contact statistics, status."""
+    rng = np.random.default_rng(11)
+    n, n_t = 9, 37
+    p = np.zeros((n, 13))
+    p[:, 6] = rng.uniform(0, 1, n); p[:, 7] = rng.uniform(1, 6, n); p[:, 8] = rng.uniform(0.1, 0.5, n)
+    p[:, 9] = rng.uniform(0.02, 0.12, n); p[:, 11] = -1
+    p[:, 2] = {"hexapod": -0.1, "myant": -0.07, "spider": 0.05}[model]
+    if model == "spider":
+        p[:, 11] = 0; p[:, 12] = 0.4
+    p[4, 2] = 0.5  # one unreachable candidate
+    xml = model_xml(model)
+    plain = hostlib.eval_gaits(xml, p, n_t)
+    pipe = hostlib.eval_gaits_pipe(xml, p, n_t, fb=fb, grid=grid)
+    assert np.array_equal(pipe["status"], plain["status"]) and pipe["status"][4] & 2
+    ok = plain["status"] == 0
+    for k in ("cot", "work", "min_cfz", "max_mu"):
+        assert np.abs(pipe[k][ok] - plain[k][ok]).max() <= 1e-12 * np.abs(plain[k][ok]).max(), k
+        assert np.isnan(pipe[k][~ok]).all()
+    ref = orc.Model(xml).eval_batch(p, n_t, nthreads=4)
+    assert np.abs(pipe["cot"][ok] - ref["cot"][ok]).max() <= TOL * np.abs(ref["cot"][ok]).max()

@@ -17,7 +17,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=4096)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--variants", default="32:255,32:128,32:96,64:128")
+    ap.add_argument("--variants", default="32:128,64:128,64:1,32:1")
     args = ap.parse_args()
     import torch
     import hslabs_b200 as hsl
