@@ -160,18 +160,32 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
     HSL_CUDA(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)nblk * warps * 8);
     HSL_CUDA(cudaMemcpy(h.data(), clkbuf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    // average cycles per segment, per role: A | wait1 | B | wait2 | C | wait3 | D+E
     const int roles = m->pod.nf + 1, wpr = fbp / 32;
-    fprintf(stderr, "[phase clocks] blocks=%lld warps/block=%d\n", (long long)nblk, warps);
-    for (int r = 0; r < roles; r++) {
-      double seg[7] = {0, 0, 0, 0, 0, 0, 0};
-      for (int64_t b = 0; b < nblk; b++)
-        for (int w = 0; w < wpr; w++) {
-          const long long* c = &h[((size_t)b * warps + r * wpr + w) * 8];
-          for (int k = 0; k < 7; k++) seg[k] += (double)(c[k + 1] - c[k]);
-        }
-      fprintf(stderr, "  role %d: A %.0f | w %.0f | B %.0f | w %.0f | C %.0f | w %.0f | DE %.0f  (cycles)\n", r, seg[0] / (nblk * wpr),
-              seg[1] / (nblk * wpr), seg[2] / (nblk * wpr), seg[3] / (nblk * wpr), seg[4] / (nblk * wpr), seg[5] / (nblk * wpr), seg[6] / (nblk * wpr));
+    if (m->maxreg == 1 && !dump) {  // pipelined kernel: per-tile averages of [work before barrier 1 | wait | phase B | wait]
+      const int64_t grid = nblk < 148 * (fbp == 64 ? 1 : 2) ? nblk : 148 * (fbp == 64 ? 1 : 2);
+      fprintf(stderr, "[pipe clocks] tiles=%lld grid=%lld\n", (long long)nblk, (long long)grid);
+      for (int r = 0; r < roles; r++) {
+        double seg[4] = {0, 0, 0, 0}, tiles = 0;
+        for (int64_t b = 0; b < grid; b++)
+          for (int w = 0; w < wpr; w++) {
+            const long long* c = &h[((size_t)b * warps + r * wpr + w) * 8];
+            for (int k = 0; k < 4; k++) seg[k] += (double)c[k];
+            tiles += (double)c[4];
+          }
+        fprintf(stderr, "  role %d per tile: pre-B1 %.0f | wait %.0f | B %.0f | wait %.0f\n", r, seg[0] / tiles, seg[1] / tiles, seg[2] / tiles, seg[3] / tiles);
+      }
+    } else {
+      fprintf(stderr, "[phase clocks] blocks=%lld warps/block=%d\n", (long long)nblk, warps);
+      for (int r = 0; r < roles; r++) {
+        double seg[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int64_t b = 0; b < nblk; b++)
+          for (int w = 0; w < wpr; w++) {
+            const long long* c = &h[((size_t)b * warps + r * wpr + w) * 8];
+            for (int k = 0; k < 7; k++) seg[k] += (double)(c[k + 1] - c[k]);
+          }
+        fprintf(stderr, "  role %d: A %.0f | w %.0f | B %.0f | w %.0f | C %.0f | w %.0f | DE %.0f  (cycles)\n", r, seg[0] / (nblk * wpr),
+                seg[1] / (nblk * wpr), seg[2] / (nblk * wpr), seg[3] / (nblk * wpr), seg[4] / (nblk * wpr), seg[5] / (nblk * wpr), seg[6] / (nblk * wpr));
+      }
     }
   }
 #endif

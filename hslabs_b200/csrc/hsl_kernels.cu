@@ -102,6 +102,15 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
   const int role = threadIdx.x / FB;
   const int s = threadIdx.x % FB;
   const int per = A.n_t + 4;
+#ifdef HSL_PHASE_CLOCKS
+  long long acc[4] = {0, 0, 0, 0};
+  long long t0c, t1c;
+#define HSL_T0() t0c = clock64()
+#define HSL_T1(k) do { t1c = clock64(); acc[k] += t1c - t0c; t0c = t1c; } while (0)
+#else
+#define HSL_T0()
+#define HSL_T1(k)
+#endif
   HslSlot prev;
   prev.interior = false; prev.valid = false; prev.c = 0; prev.i = 0; prev.s = s; prev.fo = 0;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -116,6 +125,7 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
     sl.fo = sl.c * A.n_t + (sl.i - 2);
     HslLegState<false> lst;
     int bad = 0;
+    HSL_T0();
     if (role < NF) {
       phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
       pipe_a_trunk_bodies<NF, FB>(M, A, sm, sl, role);
@@ -124,16 +134,27 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
       const int tb = pipe_trunk_finish<NF, FB>(A, sm, prev);
       if (tb && A.status) atomicOr(&A.status[prev.c], tb);
     }
+    HSL_T1(0);
     __syncthreads();
+    HSL_T1(1);
     if (role < NF && sl.interior) {
       phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
       pipe_b_extras<NF, FB>(M, A, sm, sl, role, lst);
       bad |= lst.bad;
     }
     if (role < NF && bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
+    HSL_T1(2);
     __syncthreads();
+    HSL_T1(3);
     prev = sl;
   }
+#ifdef HSL_PHASE_CLOCKS
+  if (A.phase_clk && (threadIdx.x & 31) == 0) {
+    long long* dst = A.phase_clk + ((size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * 8;
+    for (int k = 0; k < 4; k++) dst[k] = acc[k];
+    dst[4] = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  }
+#endif
   if (role == NF && prev.interior) {
     const int tb = pipe_trunk_finish<NF, FB>(A, sm, prev);
     if (tb && A.status) atomicOr(&A.status[prev.c], tb);
