@@ -36,8 +36,14 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
   } else {
     const int per = A.n_t + 4;
     const int64_t g = (int64_t)blockIdx.x * (FB - 4) + sl.s;
-    sl.c = g / per;
-    sl.i = (int32_t)(g - sl.c * per);
+    if (g < 0x7fffffffLL) {  // 32-bit division: the 64-bit one is a ~100-instruction software routine
+      const uint32_t c32 = (uint32_t)g / (uint32_t)per;
+      sl.c = c32;
+      sl.i = (int32_t)((uint32_t)g - c32 * (uint32_t)per);
+    } else {
+      sl.c = g / per;
+      sl.i = (int32_t)(g - sl.c * per);
+    }
     sl.valid = sl.c < A.n_cand;
     if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
     sl.interior = sl.valid && sl.s >= 2 && sl.s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
@@ -79,8 +85,6 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
   __syncthreads();
   HSL_STAMP();
   if (sl.interior && role < NF) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
-  __syncthreads();
-  if (sl.interior && role == NF) phase_e_trunk<NF, FB>(A, sm, sl);
   HSL_STAMP();
   if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
 #ifdef HSL_PHASE_CLOCKS
@@ -176,7 +180,7 @@ __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t 
 
 // One warp per candidate.  periodic::work_over_period (periodic.cpp:285-307) and modelplayer::measure_cot
 // (player.cpp:269-285): work = sum_frames (sum_motors max(tau*qdot,0)) * dt ; COT = work / (total mass * step length).
-__global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, const HslCand* __restrict__ cand,
+__global__ void hsl_finish_kernel(int64_t n_cand, int n_t, int n_rows, double total_mass, const HslCand* __restrict__ cand,
                                   const double* __restrict__ dt_in, const double* __restrict__ wframe,
                                   const double* __restrict__ fmin_in, const double* __restrict__ fmax_in,
                                   const int32_t* __restrict__ status, double* __restrict__ cot, double* __restrict__ work,
@@ -186,10 +190,15 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
   if (c >= n_cand) return;
   const double dt = cand ? cand[c].dt : dt_in[c];
   double w = 0, mn = 1e10, mx = -1e10;  // periodic.cpp:380
+  const int64_t nfr = n_cand * n_t;
   for (int f = lane; f < n_t; f += 32) {
-    w += wframe[c * n_t + f] * dt;
-    mn = fmin(mn, fmin_in[c * n_t + f]);
-    mx = fmax(mx, fmax_in[c * n_t + f]);
+    double wf = 0;  // power of the frame: sum over the limb rows, in limb order
+    for (int r = 0; r < n_rows; r++) {
+      wf += wframe[r * nfr + c * n_t + f];
+      mn = fmin(mn, fmin_in[r * nfr + c * n_t + f]);
+      mx = fmax(mx, fmax_in[r * nfr + c * n_t + f]);
+    }
+    w += wf * dt;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -324,12 +333,12 @@ cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, cons
   return cudaGetLastError();
 }
 
-cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
+cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, int n_rows, double total_mass, const HslCand* cand, const double* dt_in,
                               const double* wframe, const double* fmin_in, const double* fmax_in, const int32_t* status, double* cot,
                               double* work, double* min_cfz, double* max_mu, cudaStream_t st) {
   const int tpb = 256;
   const int64_t threads = n_cand * 32;
-  hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
+  hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, n_rows, total_mass, cand, dt_in, wframe, fmin_in,
                                                                          fmax_in, status, cot, work, min_cfz, max_mu);
   return cudaGetLastError();
 }
