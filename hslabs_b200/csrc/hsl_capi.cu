@@ -125,10 +125,9 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
   const int64_t nfr = C * n_t;
   HSL_CUDA(m->cand.need(sizeof(HslCand) * C));
   HSL_CUDA(m->ttab.need(sizeof(double) * C * (n_t + 4)));
-  const int n_rows = (!dump && m->maxreg == 1) ? 1 : m->pod.nf;  // the pipelined kernel writes one row per frame, the plain one a row per limb
-  HSL_CUDA(m->wframe.need(sizeof(double) * nfr * n_rows));
-  HSL_CUDA(m->fmin.need(sizeof(double) * nfr * n_rows));
-  HSL_CUDA(m->fmax.need(sizeof(double) * nfr * n_rows));
+  HSL_CUDA(m->wframe.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmin.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmax.need(sizeof(double) * nfr));
   int32_t* st_buf = d_status;
   if (!st_buf) { HSL_CUDA(m->status.need(sizeof(int32_t) * C)); st_buf = (int32_t*)m->status.p; }
   HslFrameArgs A;
@@ -190,7 +189,7 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
     }
   }
 #endif
-  HSL_CUDA(hsl_launch_finish(C, n_t, n_rows, m->total_mass, (const HslCand*)m->cand.p, nullptr, A.wframe, A.fmin_cfz, A.fmax_mu, st_buf,
+  HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, (const HslCand*)m->cand.p, nullptr, A.wframe, A.fmin_cfz, A.fmax_mu, st_buf,
                              d_cot, d_work, d_min, d_max, st));
   m->launches += 3;
   return HSL_OK;
@@ -287,9 +286,9 @@ int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* tr
   HSL_CUDA(m->in_b.need(sizeof(double) * C));
   HSL_CUDA(cudaMemcpyAsync(m->in_a.p, traj, tbytes, cudaMemcpyHostToDevice, st));
   HSL_CUDA(cudaMemcpyAsync(m->in_b.p, dt, sizeof(double) * C, cudaMemcpyHostToDevice, st));
-  HSL_CUDA(m->wframe.need(sizeof(double) * nfr * P.nf));
-  HSL_CUDA(m->fmin.need(sizeof(double) * nfr * P.nf));
-  HSL_CUDA(m->fmax.need(sizeof(double) * nfr * P.nf));
+  HSL_CUDA(m->wframe.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmin.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmax.need(sizeof(double) * nfr));
   HSL_CUDA(m->status.need(sizeof(int32_t) * C));
   HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * C, st));
   HSL_CUDA(m->out4.need(sizeof(double) * 4 * C));
@@ -305,7 +304,7 @@ int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* tr
   A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
   HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_TRAJ, true, 32, 1, st));
   double* d4 = (double*)m->out4.p;
-  HSL_CUDA(hsl_launch_finish(C, n_t, P.nf, m->total_mass, nullptr, A.dt_in, A.wframe, A.fmin_cfz, A.fmax_mu, A.status, nullptr, d4 + C,
+  HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, nullptr, A.dt_in, A.wframe, A.fmin_cfz, A.fmax_mu, A.status, nullptr, d4 + C,
                              d4 + 2 * C, d4 + 3 * C, st));
   m->launches += 2;
   HSL_CUDA(m->pin_in.need(sizeof(double) * 4 * C + sizeof(int32_t) * C));

@@ -67,7 +67,7 @@ struct HslFrameArgs {
   const double *f_pos, *f_jpos, *f_jz, *f_momrate, *f_angrate, *f_fpos;
   const uint8_t* f_contacts;  // [frame][nf]
   // per-frame outputs reduced by the finishing kernel
-  double *wframe, *fmin_cfz, *fmax_mu;  // [n_rows][C*n_t]: n_rows = nf (one row per limb; plain kernel) or 1 (pipelined kernel)
+  double *wframe, *fmin_cfz, *fmax_mu;  // [C][n_t]
   int32_t* status;                      // [C], OR of HSL_ST_*
   // optional dumps, component-major [comp][n_frames] (NULL = not written)
   double *x, *z, *tau;
@@ -577,8 +577,7 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
   double* P = sm.part + (limb * SM::PART) * FB + sl.s;
 #pragma unroll
   for (int k = 0; k < 3; k++) { P[k * FB] = F[k]; P[(3 + k) * FB] = T[k]; }
-  const double cflag = st.contact ? 1.0 : 0.0;
-  P[18 * FB] = cflag;
+  P[18 * FB] = st.contact ? 1.0 : 0.0;
   // motor torque of the particular solution and its sensitivity to the contact force:
   // tau_h = a_h . T_h - (a_h x rho_h) . lambda ,  rho_h = fpos - jpos_h     (periodic.cpp:328-343)
   double Hs[6] = {0, 0, 0, 0, 0, 0}, g[3] = {0, 0, 0};
@@ -605,19 +604,16 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     g[1] -= cx * ux[1] + cz * uz[1];
     g[2] -= cx * ux[2] + cy * uy[2];
   }
-  // the 3x3 block is formed for every limb and zeroed for swing feet, so that neither this code nor the trunk's
-  // assembly contains data-dependent branches (straight-line code lets the scheduler overlap the chains)
-  const bool pd = spd3_inverse(Hs, st.W);
-  if (st.contact && !pd) st.bad |= HSL_ST_SOLVER;
+  if (st.contact) {
+    if (!spd3_inverse(Hs, st.W)) st.bad |= HSL_ST_SOLVER;
+    sym3_mul(st.W, g, st.Wg);
 #pragma unroll
-  for (int k = 0; k < 6; k++) st.W[k] = st.contact ? st.W[k] : 0.0;
-  sym3_mul(st.W, g, st.Wg);
+    for (int k = 0; k < 3; k++) st.r[k] = st.fpos[k] - ref[k];
 #pragma unroll
-  for (int k = 0; k < 3; k++) st.r[k] = st.fpos[k] - ref[k];
+    for (int k = 0; k < 6; k++) P[(6 + k) * FB] = st.W[k];
 #pragma unroll
-  for (int k = 0; k < 6; k++) P[(6 + k) * FB] = st.W[k];
-#pragma unroll
-  for (int k = 0; k < 3; k++) { P[(12 + k) * FB] = st.Wg[k]; P[(15 + k) * FB] = st.r[k]; }
+    for (int k = 0; k < 3; k++) { P[(12 + k) * FB] = st.Wg[k]; P[(15 + k) * FB] = st.r[k]; }
+  }
 }
 
 template <int NF, int FB, int MODE, class SM>
@@ -715,19 +711,15 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& 
     const double* P = sm.part + (l * SM::PART) * FB + sl.s;
 #pragma unroll
     for (int k = 0; k < 6; k++) b[k] += P[k * FB];
-    {
+    if (P[18 * FB] != 0.0) {
       double W[6], Wg[3], r[3];
 #pragma unroll
       for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
 #pragma unroll
       for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
-      const bool isc = (P[18 * FB] != 0.0);  // swing feet publish W = 0: their terms vanish, no branch needed
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        rA[k] = (isc && nc == 0) ? r[k] : rA[k];
-        rB[k] = (isc && nc == 1) ? r[k] : rB[k];
-      }
-      nc += isc ? 1 : 0;
+      if (nc == 0) { rA[0] = r[0]; rA[1] = r[1]; rA[2] = r[2]; }
+      if (nc == 1) { rB[0] = r[0]; rB[1] = r[1]; rB[2] = r[2]; }
+      nc++;
       // S += A W A^T with A = [I ; [r]x]:  K = [r]x W ; blocks [[W, K^T],[K, [r]x K^T]]
       const double Wc[3][3] = {{W[0], W[1], W[2]}, {W[1], W[3], W[4]}, {W[2], W[4], W[5]}};
       double K[3][3];  // K[i][j] = (r x W_col_j)_i
@@ -889,9 +881,9 @@ template <int NF, int FB, int MODE, bool DUMP, class SM>
 HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
                         HslLegState<DUMP>& st) {
   const HslLimb& L = M.limb[limb];
+  double lam[3] = {0, 0, 0};
   const bool con = st.contact && (sm.mu[6 * FB + sl.s] != 0.0);
-  double lam[3];
-  {  // lambda = -(W g + W (mu_f + mu_t x r)); straight-line (W = 0 for swing feet)
+  if (con) {
     double mu[6], y[3], Wy[3];
 #pragma unroll
     for (int k = 0; k < 6; k++) mu[k] = sm.mu[k * FB + sl.s];
@@ -900,7 +892,7 @@ HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     for (int k = 0; k < 3; k++) y[k] += mu[k];
     sym3_mul(st.W, y, Wy);
 #pragma unroll
-    for (int k = 0; k < 3; k++) lam[k] = con ? -(st.Wg[k] + Wy[k]) : 0.0;
+    for (int k = 0; k < 3; k++) lam[k] = -(st.Wg[k] + Wy[k]);
   }
   double work = 0, tau[3];
 #pragma unroll
@@ -909,13 +901,15 @@ HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     const double dw = tau[h] * st.qd[h];
     work += (dw > 0) ? dw : 0;  // periodic.cpp:291-304
   }
-  // periodic.cpp:347-357, over the feet that are on the ground
-  const double muq = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
-  const double cfz = con ? lam[2] : 1e300, mu_f = con ? muq : -1e300;
-  // per-limb results go straight to global memory (row `limb`); the finishing kernel adds the limbs of a frame
-  if (A.wframe) A.wframe[(int64_t)limb * A.n_frames + sl.fo] = work;
-  if (A.fmin_cfz) A.fmin_cfz[(int64_t)limb * A.n_frames + sl.fo] = cfz;
-  if (A.fmax_mu) A.fmax_mu[(int64_t)limb * A.n_frames + sl.fo] = mu_f;
+  double cfz = 1e300, mu_f = -1e300;
+  if (con) {  // periodic.cpp:347-357, over the feet that are on the ground
+    cfz = lam[2];
+    mu_f = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
+  }
+  double* P = sm.part + (limb * SM::PART) * FB + sl.s;
+  P[0] = work;
+  P[FB] = cfz;
+  P[2 * FB] = mu_f;
   if (DUMP) {
     const int64_t nfr = A.n_frames, fo = sl.fo;
     if (A.tau) {
@@ -943,6 +937,22 @@ HSL_HD void phase_d_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
       }
     }
   }
+}
+
+// ------------------------------------------------------------------ phase E (trunk)
+template <int NF, int FB, class SM>
+HSL_HD void phase_e_trunk(const HslFrameArgs& A, const SM& sm, const HslSlot& sl) {
+  double work = 0, cfz = 1e300, mu = -1e300;
+#pragma unroll
+  for (int l = 0; l < NF; l++) {
+    const double* P = sm.part + (l * SM::PART) * FB + sl.s;
+    work += P[0];
+    cfz = fmin(cfz, P[FB]);
+    mu = fmax(mu, P[2 * FB]);
+  }
+  if (A.wframe) A.wframe[sl.fo] = work;
+  if (A.fmin_cfz) A.fmin_cfz[sl.fo] = cfz;
+  if (A.fmax_mu) A.fmax_mu[sl.fo] = mu;
 }
 
 // ------------------------------------------------------------------ candidate setup (a1)

@@ -8,7 +8,7 @@
 cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int maxreg, cudaStream_t st);
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
                              int32_t* status, cudaStream_t st);
-cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, int n_rows, double total_mass, const HslCand* cand, const double* dt_in,
+cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
                               const double* wframe, const double* fmin, const double* fmax, const int32_t* status, double* cot,
                               double* work, double* min_cfz, double* max_mu, cudaStream_t st);
 cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, double* out, cudaStream_t st);

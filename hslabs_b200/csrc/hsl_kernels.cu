@@ -85,6 +85,8 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
   __syncthreads();
   HSL_STAMP();
   if (sl.interior && role < NF) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+  __syncthreads();
+  if (sl.interior && role == NF) phase_e_trunk<NF, FB>(A, sm, sl);
   HSL_STAMP();
   if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
 #ifdef HSL_PHASE_CLOCKS
@@ -180,7 +182,7 @@ __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t 
 
 // One warp per candidate.  periodic::work_over_period (periodic.cpp:285-307) and modelplayer::measure_cot
 // (player.cpp:269-285): work = sum_frames (sum_motors max(tau*qdot,0)) * dt ; COT = work / (total mass * step length).
-__global__ void hsl_finish_kernel(int64_t n_cand, int n_t, int n_rows, double total_mass, const HslCand* __restrict__ cand,
+__global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, const HslCand* __restrict__ cand,
                                   const double* __restrict__ dt_in, const double* __restrict__ wframe,
                                   const double* __restrict__ fmin_in, const double* __restrict__ fmax_in,
                                   const int32_t* __restrict__ status, double* __restrict__ cot, double* __restrict__ work,
@@ -190,15 +192,10 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, int n_rows, double to
   if (c >= n_cand) return;
   const double dt = cand ? cand[c].dt : dt_in[c];
   double w = 0, mn = 1e10, mx = -1e10;  // periodic.cpp:380
-  const int64_t nfr = n_cand * n_t;
   for (int f = lane; f < n_t; f += 32) {
-    double wf = 0;  // power of the frame: sum over the limb rows, in limb order
-    for (int r = 0; r < n_rows; r++) {
-      wf += wframe[r * nfr + c * n_t + f];
-      mn = fmin(mn, fmin_in[r * nfr + c * n_t + f]);
-      mx = fmax(mx, fmax_in[r * nfr + c * n_t + f]);
-    }
-    w += wf * dt;
+    w += wframe[c * n_t + f] * dt;
+    mn = fmin(mn, fmin_in[c * n_t + f]);
+    mx = fmax(mx, fmax_in[c * n_t + f]);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -333,12 +330,12 @@ cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, cons
   return cudaGetLastError();
 }
 
-cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, int n_rows, double total_mass, const HslCand* cand, const double* dt_in,
+cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
                               const double* wframe, const double* fmin_in, const double* fmax_in, const int32_t* status, double* cot,
                               double* work, double* min_cfz, double* max_mu, cudaStream_t st) {
   const int tpb = 256;
   const int64_t threads = n_cand * 32;
-  hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, n_rows, total_mass, cand, dt_in, wframe, fmin_in,
+  hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
                                                                          fmax_in, status, cot, work, min_cfz, max_mu);
   return cudaGetLastError();
 }

@@ -107,19 +107,15 @@ HSL_HD int pipe_trunk_finish(const HslFrameArgs& A, const SM& sm, const HslSlot&
     const double* P = sm.part + (l * SM::PART) * FB + sl.s;
 #pragma unroll
     for (int k = 0; k < 6; k++) b[k] += P[k * FB];
-    {
+    if (P[18 * FB] != 0.0) {
       double W[6], Wg[3], r[3];
 #pragma unroll
       for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
 #pragma unroll
       for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
-      const bool isc = (P[18 * FB] != 0.0);  // swing feet publish W = 0: their terms vanish, no branch needed
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        rA[k] = (isc && nc == 0) ? r[k] : rA[k];
-        rB[k] = (isc && nc == 1) ? r[k] : rB[k];
-      }
-      nc += isc ? 1 : 0;
+      if (nc == 0) { rA[0] = r[0]; rA[1] = r[1]; rA[2] = r[2]; }
+      if (nc == 1) { rB[0] = r[0]; rB[1] = r[1]; rB[2] = r[2]; }
+      nc++;
       const double Wc[3][3] = {{W[0], W[1], W[2]}, {W[1], W[3], W[4]}, {W[2], W[4], W[5]}};
       double K[3][3];
 #pragma unroll
@@ -175,9 +171,9 @@ HSL_HD int pipe_trunk_finish(const HslFrameArgs& A, const SM& sm, const HslSlot&
 #pragma unroll
   for (int l = 0; l < NF; l++) {
     const double* P = sm.part + (l * SM::PART) * FB + sl.s;
+    double lam[3] = {0, 0, 0};
     const bool con = (P[18 * FB] != 0.0) && (nc >= 2);
-    double lam[3];
-    {  // lambda = -(W g + W (mu_f + mu_t x r)); W = 0 for swing feet, so no branch is needed
+    if (con) {
       double W[6], r[3], y[3], Wy[3];
 #pragma unroll
       for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
@@ -188,10 +184,9 @@ HSL_HD int pipe_trunk_finish(const HslFrameArgs& A, const SM& sm, const HslSlot&
       for (int k = 0; k < 3; k++) y[k] += mu[k];
       sym3_mul(W, y, Wy);
 #pragma unroll
-      for (int k = 0; k < 3; k++) lam[k] = con ? -(P[(12 + k) * FB] + Wy[k]) : 0.0;
-      const double muf = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
-      cfz = con ? fmin(cfz, lam[2]) : cfz;
-      mu_max = con ? fmax(mu_max, muf) : mu_max;
+      for (int k = 0; k < 3; k++) lam[k] = -(P[(12 + k) * FB] + Wy[k]);
+      cfz = fmin(cfz, lam[2]);
+      mu_max = fmax(mu_max, hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]));
     }
     double wl = 0;
 #pragma unroll

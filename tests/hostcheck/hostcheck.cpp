@@ -69,6 +69,8 @@ void emulate(const HslModelPod& M, const HslFrameArgs& A) {
     for (int r = 0; r < NF; r++)
       for (int s = 0; s < FB; s++)
         if (sls[s].interior) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sls[s], r, lst[r * FB + s]);
+    for (int s = 0; s < FB; s++)
+      if (sls[s].interior) phase_e_trunk<NF, FB>(A, sm, sls[s]);
     for (int r = 0; r < roles; r++)
       for (int s = 0; s < FB; s++)
         if (bad[r * FB + s] && sls[s].valid && A.status) A.status[sls[s].c] |= bad[r * FB + s];
@@ -143,18 +145,13 @@ void transpose_out(const std::vector<double>& src, int comps, int64_t nfr, doubl
   for (int c = 0; c < comps; c++)
     for (int64_t f = 0; f < nfr; f++) dst[f * comps + c] = src[(size_t)c * nfr + f];
 }
-void finish(int64_t C, int n_t, int n_rows, double total_mass, const HslCand* cand, const double* dt_in, const std::vector<double>& wf,
+void finish(int64_t C, int n_t, double total_mass, const HslCand* cand, const double* dt_in, const std::vector<double>& wf,
             const std::vector<double>& fmn, const std::vector<double>& fmx, const int32_t* status, double* cot, double* work,
             double* min_cfz, double* max_mu) {
   for (int64_t c = 0; c < C; c++) {
     const double dt = cand ? cand[c].dt : dt_in[c];
     double w = 0, mn = 1e10, mx = -1e10;
-    const int64_t nfr = C * n_t;
-    for (int f = 0; f < n_t; f++) {
-      double wfr = 0;
-      for (int r = 0; r < n_rows; r++) { wfr += wf[r * nfr + c * n_t + f]; mn = std::fmin(mn, fmn[r * nfr + c * n_t + f]); mx = std::fmax(mx, fmx[r * nfr + c * n_t + f]); }
-      w += wfr * dt;
-    }
+    for (int f = 0; f < n_t; f++) { w += wf[c * n_t + f] * dt; mn = std::fmin(mn, fmn[c * n_t + f]); mx = std::fmax(mx, fmx[c * n_t + f]); }
     const bool fatal = status && (status[c] & (HSL_ST_BAD_PARAMS | HSL_ST_UNREACHABLE));
     if (work) work[c] = fatal ? NAN : w;
     if (cot) cot[c] = (fatal || !cand) ? NAN : w / (total_mass * cand[c].step_length);
@@ -188,7 +185,7 @@ int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int
   if (rc) return rc;
   const int64_t nfr = C * n_t;
   std::vector<HslCand> cand(C);
-  std::vector<double> ttab((size_t)C * (n_t + 4)), wf(nfr * M.nf), fmn(nfr * M.nf), fmx(nfr * M.nf);
+  std::vector<double> ttab((size_t)C * (n_t + 4)), wf(nfr), fmn(nfr), fmx(nfr);
   std::vector<double> dx((size_t)6 * M.n * nfr), dz((size_t)3 * M.nf * nfr), dtau((size_t)M.nmj * nfr), dq((size_t)M.config_dim * C * (n_t + 4));
   std::vector<uint8_t> dc((size_t)M.nf * nfr);
   std::vector<int32_t> st(C, 0);
@@ -202,7 +199,7 @@ int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int
   run_any(M, A, HSL_MODE_GAIT);
   double tm = 0;
   for (int i = 0; i < M.n; i++) tm += 1.0;
-  finish(C, n_t, M.nf, tm, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
+  finish(C, n_t, tm, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
   if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
   transpose_out(dx, 6 * M.n, nfr, x);
   transpose_out(dz, 3 * M.nf, nfr, z);
@@ -232,7 +229,7 @@ int hc_eval_gaits_pipe(const char* xml, int64_t C, int n_t, const double* params
   A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
   if (M.nf == 6) { if (fb == 64) emulate_pipe<6, 64>(M, A, grid); else emulate_pipe<6, 32>(M, A, grid); }
   else { if (fb == 64) emulate_pipe<4, 64>(M, A, grid); else emulate_pipe<4, 32>(M, A, grid); }
-  finish(C, n_t, 1, (double)M.n, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
+  finish(C, n_t, (double)M.n, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
   if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
   return 0;
 }
@@ -244,7 +241,7 @@ int hc_eval_trajectories(const char* xml, int64_t C, int n_t, const double* traj
   int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
   if (rc) return rc;
   const int64_t nfr = C * n_t;
-  std::vector<double> wf(nfr * M.nf), fmn(nfr * M.nf), fmx(nfr * M.nf), dx((size_t)6 * M.n * nfr), dz((size_t)3 * M.nf * nfr), dtau((size_t)M.nmj * nfr);
+  std::vector<double> wf(nfr), fmn(nfr), fmx(nfr), dx((size_t)6 * M.n * nfr), dz((size_t)3 * M.nf * nfr), dtau((size_t)M.nmj * nfr);
   std::vector<int32_t> st(C, 0);
   HslFrameArgs A;
   memset(&A, 0, sizeof A);
@@ -252,7 +249,7 @@ int hc_eval_trajectories(const char* xml, int64_t C, int n_t, const double* traj
   A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
   A.x = dx.data(); A.z = dz.data(); A.tau = dtau.data();
   run_any(M, A, HSL_MODE_TRAJ);
-  finish(C, n_t, M.nf, (double)M.n, nullptr, dt, wf, fmn, fmx, st.data(), nullptr, work, min_cfz, max_mu);
+  finish(C, n_t, (double)M.n, nullptr, dt, wf, fmn, fmx, st.data(), nullptr, work, min_cfz, max_mu);
   if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
   transpose_out(dx, 6 * M.n, nfr, x);
   transpose_out(dz, 3 * M.nf, nfr, z);
