@@ -325,7 +325,7 @@ cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int m
 
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
                              int32_t* status, cudaStream_t st) {
-  const int tpb = 128;
+  const int tpb = 32;  // one candidate per thread with a sequential time table: spread the candidates over many SMs
   hsl_setup_kernel<<<(unsigned)((n_cand + tpb - 1) / tpb), tpb, 0, st>>>(M, n_cand, n_t, params, cand, ttab, status);
   return cudaGetLastError();
 }
