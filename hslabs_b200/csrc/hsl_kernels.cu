@@ -97,8 +97,28 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
 #endif
 }
 
-// Persistent, software-pipelined cost-only kernel (see hsl_pipe.h): the trunk warps finish tile t-1 while the limb
-// warps run phase A of tile t.
+// Persistent, software-pipelined cost-only kernel (schedule and buffer hand-offs in hsl_pipe.h).
+template <int NF, int FB>
+HSL_HD HslSlot hsl_pipe_slot(const HslFrameArgs& A, int64_t tile, int s) {
+  HslSlot sl;
+  sl.s = s;
+  const int per = A.n_t + 4;
+  const int64_t g = tile * (FB - 4) + s;
+  if (g < 0x7fffffffLL) {
+    const uint32_t c32 = (uint32_t)g / (uint32_t)per;
+    sl.c = c32;
+    sl.i = (int32_t)((uint32_t)g - c32 * (uint32_t)per);
+  } else {
+    sl.c = g / per;
+    sl.i = (int32_t)(g - sl.c * per);
+  }
+  sl.valid = sl.c < A.n_cand;
+  if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+  sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+  sl.fo = sl.c * A.n_t + (sl.i - 2);
+  return sl;
+}
+
 template <int NF, int FB>
 __global__ void __maxnreg__(128)
 hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A, const int64_t n_tiles) {
@@ -107,64 +127,58 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
   sm.carve(hsl_smem_raw, M.ntrunk);
   const int role = threadIdx.x / FB;
   const int s = threadIdx.x % FB;
-  const int per = A.n_t + 4;
-#ifdef HSL_PHASE_CLOCKS
-  long long acc[4] = {0, 0, 0, 0};
-  long long t0c, t1c;
-#define HSL_T0() t0c = clock64()
-#define HSL_T1(k) do { t1c = clock64(); acc[k] += t1c - t0c; t0c = t1c; } while (0)
-#else
-#define HSL_T0()
-#define HSL_T1(k)
-#endif
-  HslSlot prev;
-  prev.interior = false; prev.valid = false; prev.c = 0; prev.i = 0; prev.s = s; prev.fo = 0;
+  // slots of the two previous tiles of this block (p1 = t-1, p2 = t-2)
+  bool p1_int = false, p2_int = false;
+  int64_t p1_fo = 0, p2_fo = 0, p1_c = 0;
+  HslTrunkState tst;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    HslSlot sl;
-    sl.s = s;
-    const int64_t g = tile * (FB - 4) + s;
-    sl.c = g / per;
-    sl.i = (int32_t)(g - sl.c * per);
-    sl.valid = sl.c < A.n_cand;
-    if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
-    sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
-    sl.fo = sl.c * A.n_t + (sl.i - 2);
+    const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
     HslLegState<false> lst;
     int bad = 0;
-    HSL_T0();
     if (role < NF) {
       phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
-      pipe_a_trunk_bodies<NF, FB>(M, A, sm, sl, role);
       bad = lst.bad;
-    } else if (prev.interior) {
-      const int tb = pipe_trunk_finish<NF, FB>(A, sm, prev);
-      if (tb && A.status) atomicOr(&A.status[prev.c], tb);
+    } else {
+      if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
+      // C(t-1) needs the trunk wrench kept in tst.F0/T0 since B'(t-1); A'(t) only writes tst.R0/t0
+      if (p1_int) {
+        HslSlot ps = sl;
+        ps.fo = p1_fo; ps.c = p1_c;
+        const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
+        if (tb && A.status) atomicOr(&A.status[p1_c], tb);
+      }
+      phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
     }
-    HSL_T1(0);
     __syncthreads();
-    HSL_T1(1);
-    if (role < NF && sl.interior) {
-      phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
-      pipe_b_extras<NF, FB>(M, A, sm, sl, role, lst);
-      bad |= lst.bad;
+    if (role < NF) {
+      if (p1_int) pipe_d_leg<NF, FB>(sm, s, role);
+      if (sl.interior) {
+        phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
+        pipe_store_dstate<NF, FB>(sm, s, role, lst);
+        bad |= lst.bad;
+      }
+      if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
+    } else if (sl.interior) {
+      phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
     }
-    if (role < NF && bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
-    HSL_T1(2);
     __syncthreads();
-    HSL_T1(3);
-    prev = sl;
+    p2_int = p1_int; p2_fo = p1_fo;
+    p1_int = sl.interior; p1_fo = sl.fo; p1_c = sl.c;
   }
-#ifdef HSL_PHASE_CLOCKS
-  if (A.phase_clk && (threadIdx.x & 31) == 0) {
-    long long* dst = A.phase_clk + ((size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * 8;
-    for (int k = 0; k < 4; k++) dst[k] = acc[k];
-    dst[4] = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  // drain: E(T-1), C(T) | D(T) | E(T)
+  if (role == NF) {
+    if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
+    if (p1_int) {
+      HslSlot ps;
+      ps.s = s; ps.fo = p1_fo; ps.c = p1_c; ps.i = 2; ps.valid = true; ps.interior = true;
+      const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
+      if (tb && A.status) atomicOr(&A.status[p1_c], tb);
+    }
   }
-#endif
-  if (role == NF && prev.interior) {
-    const int tb = pipe_trunk_finish<NF, FB>(A, sm, prev);
-    if (tb && A.status) atomicOr(&A.status[prev.c], tb);
-  }
+  __syncthreads();
+  if (role < NF && p1_int) pipe_d_leg<NF, FB>(sm, s, role);
+  __syncthreads();
+  if (role == NF && p1_int) pipe_e_trunk<NF, FB>(A, sm, s, p1_fo);
 }
 
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,

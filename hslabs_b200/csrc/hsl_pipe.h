@@ -1,205 +1,101 @@
 // Software-pipelined variant of the cost-only gait evaluation (used by hsl_gait_pipe_kernel).
 //
-// In the plain kernel (hsl_frames_kernel) the limb warps wait while the trunk warp of each frame assembles and
-// solves the 6x6 level-0 system, and the trunk warps wait during the limbs' kinematics: with one resident block per
-// SM that serial section is ~30 % of a block's life.  Here a persistent block loops over tiles of FB frame slots and
-// the roles are decoupled:
+// In the plain kernel (hsl_frames_kernel) the limb warps idle while the trunk warps assemble and solve the 6x6
+// level-0 system of each frame (phase C), and the trunk warps idle during the limbs' kinematics; with one resident
+// block per SM those waits are ~1/4 of all warp time (ncu: "barrier" is the largest stall reason).  Here a
+// persistent block loops over tiles of FB frame slots and the phases of consecutive tiles are skewed so that
+// neither role waits for the other:
 //
-//   limb warps, tile t : phase A (gait, IK, FK, + COMs of the trunk bodies they are assigned)      -> barrier 1
-//                        phase B (finite differences, Newton-Euler, 3x3 contact block, + the wrench of their trunk
-//                        bodies) and publish EVERYTHING the per-frame finish needs                  -> barrier 2
-//   trunk warps        : between barrier 2 of tile t-1 and barrier 1 of tile t (i.e. while the limbs run phase A of
-//                        tile t): level-0 solve, contact forces, motor torques, positive power and contact statistics
-//                        of tile t-1, written straight to global memory.
+//               | first half of iteration t  (until barrier 1) | second half (until barrier 2)
+//   limb warps  | A(t): gait, IK, FK                            | D(t-1): contact force, torques, power ; B(t)
+//   trunk warps | E(t-2) ; A'(t) ; C(t-1): 6x6 solve            | B'(t)
 //
-// The finish is possible on the trunk thread because, given the multiplier mu, every limb quantity is affine in it:
-//   lambda_c = -(W_c g_c + W_c (mu_f + mu_t x r_c)),   tau_h = tau_p,h - w_h . lambda_c .
-// The limb threads keep no state across tiles; the single `part` buffer is written by the limbs between barrier 1
-// and barrier 2 and read by the trunk between barrier 2 and the next barrier 1.
+// Phase D needs 24 doubles of limb state from phase B of the same frame; instead of keeping them in registers across
+// a whole tile they are parked in shared memory (`dstate`, written at the end of B(t), read back in D(t) one
+// iteration later, by the same thread).  Buffers and their hand-offs (w = written, r = read):
+//   pos/ust/cs  w A(t),A'(t) | r B(t),B'(t)            part   w B(t)      | r C(t)   (next first half)
+//   mu          w C(t-1)     | r D(t-1) (second half)  dstate w end B(t)  | r D(t)   (same thread, next iteration)
+//   fin         w D(t-1)     | r E(t-1) (next first half)
+// Every writer/reader pair is separated by exactly one of the two block barriers per iteration.
 #pragma once
 #include "hsl_frame.h"
 
-#define HSL_PPART 34  // part layout of the pipelined kernel, see hsl_frame.h
+#define HSL_DSTATE 27  // per limb: tau_p*qd [3], w*qd [9], W [6], W g [3], r [3], results of phase D [3]
 
 template <int NF, int FB>
-using HslPipeSmem = HslSmem<NF, FB, HSL_PPART>;
+struct HslPipeSmem : HslSmem<NF, FB, 19> {
+  double* dstate;  // [NF*HSL_DSTATE][FB]
+  HSL_HD static int doubles_per_slot(int ntrunk) { return HslSmem<NF, FB, 19>::doubles_per_slot(ntrunk) + NF * HSL_DSTATE; }
+  HSL_HD void carve(double* base, int ntrunk) {
+    HslSmem<NF, FB, 19>::carve(base, ntrunk);
+    dstate = this->mu + 7 * FB;
+  }
+};
 
-// Limb thread, phase A extras: COM positions of the trunk bodies assigned to this limb (tb = limb, limb+NF, ...)
-// and, for limb 0, the u*sin(theta) vector shared by all trunk bodies.
+// Limb thread, end of phase B: park what phase D needs.  Swing feet store W = 0, so their contact force vanishes.
 template <int NF, int FB, class SM>
-HSL_HD void pipe_a_trunk_bodies(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb) {
-  if (limb >= M.ntrunk) return;
-  const HslCand& cd = A.cand[sl.c];
-  const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
-  double qt[3], eul[3], R0[9], t0[3];
-  if (torso_values(cd, t, qt, eul)) {
-#pragma unroll
-    for (int k = 0; k < 9; k++) R0[k] = cd.R0[k];
-  } else {
-    euler_to_R(eul[0], eul[1], eul[2], R0);
-  }
-  torso_frame(M, qt, R0, t0);
-  for (int tb = limb; tb < M.ntrunk; tb += NF) {
-    double ob[3], pb[3];
-    m3_affine(R0, M.trunk[tb].off, t0, ob);
-    m3_affine(R0, M.trunk[tb].com, ob, pb);
-#pragma unroll
-    for (int k = 0; k < 3; k++) sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s] = pb[k];
-  }
-  if (limb == 0) {
-    sm.ust[((3 * NF) * 3 + 0) * FB + sl.s] = (R0[5] - R0[7]) / 2;
-    sm.ust[((3 * NF) * 3 + 1) * FB + sl.s] = (R0[6] - R0[2]) / 2;
-    sm.ust[((3 * NF) * 3 + 2) * FB + sl.s] = (R0[1] - R0[3]) / 2;
-  }
-}
-
-// Limb thread, phase B extras (after phase_b_leg): add the wrench of the assigned trunk bodies to the published limb
-// wrench and append tau_p, w, qdot to the partial.
-template <int NF, int FB, class SM>
-HSL_HD void pipe_b_extras(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
-                          const HslLegState<false>& st) {
-  double* P = sm.part + (limb * SM::PART) * FB + sl.s;
-  if (limb < M.ntrunk) {
-    const double hh = A.cand[sl.c].hh;
-    double ref[3], F[3] = {0, 0, 0}, T[3] = {0, 0, 0};
-    root_ref<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, ref);
-    for (int tb = limb; tb < M.ntrunk; tb += NF) {
-      double f[3], d[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        f[k] = fd2(sm.pos + ((3 * NF + tb) * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].mass);
-        T[k] += fd2(sm.ust + ((3 * NF) * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].inertia);
-        d[k] = sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s] - ref[k];
-      }
-      f[2] += M.trunk[tb].mass * M.g;
-#pragma unroll
-      for (int k = 0; k < 3; k++) F[k] += f[k];
-      v3_cross_add(d, f, T);
-    }
-#pragma unroll
-    for (int k = 0; k < 3; k++) { P[k * FB] += F[k]; P[(3 + k) * FB] += T[k]; }
-  }
+HSL_HD void pipe_store_dstate(const SM& sm, int s, int limb, const HslLegState<false>& st) {
+  double* D = sm.dstate + (limb * HSL_DSTATE) * FB + s;
 #pragma unroll
   for (int h = 0; h < 3; h++) {
-    P[(19 + h) * FB] = st.taup[h];
-    P[(31 + h) * FB] = st.qd[h];
+    D[h * FB] = st.taup[h] * st.qd[h];
 #pragma unroll
-    for (int k = 0; k < 3; k++) P[(22 + 3 * h + k) * FB] = st.w[h][k];
+    for (int k = 0; k < 3; k++) D[(3 + 3 * h + k) * FB] = st.w[h][k] * st.qd[h];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) D[(12 + k) * FB] = st.contact ? st.W[k] : 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    D[(18 + k) * FB] = st.contact ? st.Wg[k] : 0.0;
+    D[(21 + k) * FB] = st.contact ? st.r[k] : 0.0;
   }
 }
 
-// Trunk thread: level-0 solve (as phase_c_trunk) + contact forces, motor torques, positive power, statistics of
-// all limbs (as phase_d_leg / phase_e_trunk), from the published partials only.  Returns status bits.
+// Limb thread, phase D of the previous tile (phase_d_leg of the plain kernel, from the parked state):
+// lambda = -(W g + W (mu_f + mu_t x r)),  power = sum_h max((tau_p,h - w_h . lambda) qd_h, 0),  contact statistics.
 template <int NF, int FB, class SM>
-HSL_HD int pipe_trunk_finish(const HslFrameArgs& A, const SM& sm, const HslSlot& sl) {
-  int bad = 0;
-  double b[6] = {0, 0, 0, 0, 0, 0};
-  double S[6][6];
+HSL_HD void pipe_d_leg(const SM& sm, int s, int limb) {
+  double* D = sm.dstate + (limb * HSL_DSTATE) * FB + s;
+  double W[6], Wg[3], r[3], mu[6], y[3], Wy[3], lam[3];
 #pragma unroll
-  for (int i = 0; i < 6; i++)
+  for (int k = 0; k < 6; k++) { W[k] = D[(12 + k) * FB]; mu[k] = sm.mu[k * FB + s]; }
 #pragma unroll
-    for (int j = 0; j < 6; j++) S[i][j] = 0;
-  double v[6] = {0, 0, 0, 0, 0, 0};
-  int nc = 0;
-  double rA[3] = {0, 0, 0}, rB[3] = {0, 0, 0};
+  for (int k = 0; k < 3; k++) { Wg[k] = D[(18 + k) * FB]; r[k] = D[(21 + k) * FB]; }
+  const bool con = (W[0] > 0.0) && (sm.mu[6 * FB + s] != 0.0);  // W is positive definite for a foot on the ground
+  v3_cross(mu + 3, r, y);
+#pragma unroll
+  for (int k = 0; k < 3; k++) y[k] += mu[k];
+  sym3_mul(W, y, Wy);
+#pragma unroll
+  for (int k = 0; k < 3; k++) lam[k] = con ? -(Wg[k] + Wy[k]) : 0.0;
+  double work = 0;
+#pragma unroll
+  for (int h = 0; h < 3; h++) {
+    const double dw = D[h * FB] - (D[(3 + 3 * h) * FB] * lam[0] + D[(4 + 3 * h) * FB] * lam[1] + D[(5 + 3 * h) * FB] * lam[2]);
+    work += (dw > 0) ? dw : 0;  // periodic.cpp:291-304
+  }
+  double cfz = 1e300, mu_f = -1e300;
+  if (con) {  // periodic.cpp:347-357, over the feet that are on the ground
+    cfz = lam[2];
+    mu_f = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
+  }
+  D[24 * FB] = work;
+  D[25 * FB] = cfz;
+  D[26 * FB] = mu_f;
+}
+
+// Trunk thread, phase E: add the limbs' results of a frame and write them out.
+template <int NF, int FB, class SM>
+HSL_HD void pipe_e_trunk(const HslFrameArgs& A, const SM& sm, int s, int64_t fo) {
+  double work = 0, cfz = 1e300, mu = -1e300;
 #pragma unroll
   for (int l = 0; l < NF; l++) {
-    const double* P = sm.part + (l * SM::PART) * FB + sl.s;
-#pragma unroll
-    for (int k = 0; k < 6; k++) b[k] += P[k * FB];
-    if (P[18 * FB] != 0.0) {
-      double W[6], Wg[3], r[3];
-#pragma unroll
-      for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
-#pragma unroll
-      for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
-      if (nc == 0) { rA[0] = r[0]; rA[1] = r[1]; rA[2] = r[2]; }
-      if (nc == 1) { rB[0] = r[0]; rB[1] = r[1]; rB[2] = r[2]; }
-      nc++;
-      const double Wc[3][3] = {{W[0], W[1], W[2]}, {W[1], W[3], W[4]}, {W[2], W[4], W[5]}};
-      double K[3][3];
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        K[0][j] = r[1] * Wc[2][j] - r[2] * Wc[1][j];
-        K[1][j] = r[2] * Wc[0][j] - r[0] * Wc[2][j];
-        K[2][j] = r[0] * Wc[1][j] - r[1] * Wc[0][j];
-      }
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) S[i][j] += Wc[i][j];
-#pragma unroll
-      for (int i = 0; i < 3; i++)
-#pragma unroll
-        for (int j = 0; j < 3; j++) S[3 + i][j] += K[i][j];
-      S[3][3] += r[1] * K[0][2] - r[2] * K[0][1];
-      S[4][3] += r[2] * K[0][0] - r[0] * K[0][2];
-      S[5][3] += r[0] * K[0][1] - r[1] * K[0][0];
-      S[4][4] += r[2] * K[1][0] - r[0] * K[1][2];
-      S[5][4] += r[0] * K[1][1] - r[1] * K[1][0];
-      S[5][5] += r[0] * K[2][1] - r[1] * K[2][0];
-#pragma unroll
-      for (int k = 0; k < 3; k++) v[k] += Wg[k];
-      v3_cross_add(r, Wg, v + 3);
-    }
+    const double* D = sm.dstate + (l * HSL_DSTATE) * FB + s;
+    work += D[24 * FB];
+    cfz = fmin(cfz, D[25 * FB]);
+    mu = fmax(mu, D[26 * FB]);
   }
-  double mu[6] = {0, 0, 0, 0, 0, 0};
-  if (nc >= 2) {
-    if (nc == 2) {
-      double d[3] = {rA[0] - rB[0], rA[1] - rB[1], rA[2] - rB[2]}, nf_[3];
-      v3_cross(rA, d, nf_);
-      const double nn = hsl_rcp(hsl_sqrt(v3_dot(nf_, nf_) + v3_dot(d, d)));
-      const double nv[6] = {nf_[0] * nn, nf_[1] * nn, nf_[2] * nn, d[0] * nn, d[1] * nn, d[2] * nn};
-      double pb = 0;
-#pragma unroll
-      for (int k = 0; k < 6; k++) pb += nv[k] * b[k];
-#pragma unroll
-      for (int k = 0; k < 6; k++) mu[k] = -(b[k] - pb * nv[k] + v[k]);
-#pragma unroll
-      for (int i = 0; i < 6; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) S[i][j] += nv[i] * nv[j];
-    } else {
-#pragma unroll
-      for (int k = 0; k < 6; k++) mu[k] = -(b[k] + v[k]);
-    }
-    if (!spd6_solve(S, mu)) bad |= HSL_ST_SOLVER;
-  } else {
-    bad |= HSL_ST_FEW_CONTACTS;
-  }
-  double work = 0, cfz = 1e300, mu_max = -1e300;
-#pragma unroll
-  for (int l = 0; l < NF; l++) {
-    const double* P = sm.part + (l * SM::PART) * FB + sl.s;
-    double lam[3] = {0, 0, 0};
-    const bool con = (P[18 * FB] != 0.0) && (nc >= 2);
-    if (con) {
-      double W[6], r[3], y[3], Wy[3];
-#pragma unroll
-      for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
-#pragma unroll
-      for (int k = 0; k < 3; k++) r[k] = P[(15 + k) * FB];
-      v3_cross(mu + 3, r, y);
-#pragma unroll
-      for (int k = 0; k < 3; k++) y[k] += mu[k];
-      sym3_mul(W, y, Wy);
-#pragma unroll
-      for (int k = 0; k < 3; k++) lam[k] = -(P[(12 + k) * FB] + Wy[k]);
-      cfz = fmin(cfz, lam[2]);
-      mu_max = fmax(mu_max, hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]));
-    }
-    double wl = 0;
-#pragma unroll
-    for (int h = 0; h < 3; h++) {
-      const double w0 = P[(22 + 3 * h) * FB], w1 = P[(23 + 3 * h) * FB], w2 = P[(24 + 3 * h) * FB];
-      const double tau = P[(19 + h) * FB] - (w0 * lam[0] + w1 * lam[1] + w2 * lam[2]);
-      const double dw = tau * P[(31 + h) * FB];
-      wl += (dw > 0) ? dw : 0;
-    }
-    work += wl;
-  }
-  if (A.wframe) A.wframe[sl.fo] = work;
-  if (A.fmin_cfz) A.fmin_cfz[sl.fo] = cfz;
-  if (A.fmax_mu) A.fmax_mu[sl.fo] = mu_max;
-  return bad;
+  if (A.wframe) A.wframe[fo] = work;
+  if (A.fmin_cfz) A.fmin_cfz[fo] = cfz;
+  if (A.fmax_mu) A.fmax_mu[fo] = mu;
 }

@@ -76,7 +76,9 @@ void emulate(const HslModelPod& M, const HslFrameArgs& A) {
         if (bad[r * FB + s] && sls[s].valid && A.status) A.status[sls[s].c] |= bad[r * FB + s];
   }
 }
-// Serial emulation of hsl_gait_pipe_kernel with `grid` persistent blocks (tile order per block as on the device).
+// Serial emulation of hsl_gait_pipe_kernel with `grid` persistent blocks: the two halves of every iteration are run
+// role by role exactly in the order the device schedule allows (see hsl_pipe.h), so a wrong buffer hand-off shows up
+// here as a wrong result.
 template <int NF, int FB>
 void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
   const int64_t slots = A.n_cand * (A.n_t + 4);
@@ -85,18 +87,25 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
   const int per = A.n_t + 4;
   std::vector<double> smem((size_t)HslPipeSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB);
   std::vector<HslLegState<false> > lst((size_t)NF * FB);
+  std::vector<HslTrunkState> tst(FB);
   for (int blk = 0; blk < grid; blk++) {
     HslPipeSmem<NF, FB> sm;
     sm.carve(smem.data(), M.ntrunk);
     std::fill(smem.begin(), smem.end(), NAN);
-    std::vector<HslSlot> prev(FB), cur(FB);
-    for (int s = 0; s < FB; s++) { prev[s].interior = false; prev[s].valid = false; }
-    auto finish = [&](std::vector<HslSlot>& sls) {
+    std::vector<HslSlot> cur(FB), p1(FB), p2(FB);
+    for (int s = 0; s < FB; s++) { p1[s].interior = p2[s].interior = false; p1[s].s = p2[s].s = s; }
+    auto trunk_c = [&](std::vector<HslSlot>& ps) {
       for (int s = 0; s < FB; s++)
-        if (sls[s].interior) {
-          int tb = pipe_trunk_finish<NF, FB>(A, sm, sls[s]);
-          if (tb && A.status) A.status[sls[s].c] |= tb;
+        if (ps[s].interior) {
+          int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps[s], tst[s]);
+          if (tb && A.status) A.status[ps[s].c] |= tb;
         }
+    };
+    auto trunk_e = [&](std::vector<HslSlot>& ps) {
+      for (int s = 0; s < FB; s++) if (ps[s].interior) pipe_e_trunk<NF, FB>(A, sm, s, ps[s].fo);
+    };
+    auto legs_d = [&](std::vector<HslSlot>& ps) {
+      for (int r = 0; r < NF; r++) for (int s = 0; s < FB; s++) if (ps[s].interior) pipe_d_leg<NF, FB>(sm, s, r);
     };
     for (int64_t tile = blk; tile < n_tiles; tile += grid) {
       for (int s = 0; s < FB; s++) {
@@ -109,25 +118,31 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
         sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
         sl.fo = sl.c * A.n_t + (sl.i - 2);
       }
-      // trunk finishes the previous tile from `part` BEFORE the limbs overwrite it in phase B (same order as on the device)
-      finish(prev);
+      // first half: trunk E(t-2), C(t-1), A'(t) ; limbs A(t)   (any interleaving is legal on the device; limbs first here)
       for (int r = 0; r < NF; r++)
-        for (int s = 0; s < FB; s++) {
-          phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, cur[s], r, lst[r * FB + s]);
-          pipe_a_trunk_bodies<NF, FB>(M, A, sm, cur[s], r);
-        }
+        for (int s = 0; s < FB; s++) phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, cur[s], r, lst[r * FB + s]);
+      trunk_e(p2);
+      trunk_c(p1);
+      for (int s = 0; s < FB; s++) phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, cur[s], tst[s]);
+      // second half: limbs D(t-1), B(t) ; trunk B'(t)
+      legs_d(p1);
       for (int r = 0; r < NF; r++)
         for (int s = 0; s < FB; s++) {
           HslLegState<false>& st = lst[r * FB + s];
           if (cur[s].interior) {
             phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, cur[s], r, st);
-            pipe_b_extras<NF, FB>(M, A, sm, cur[s], r, st);
+            pipe_store_dstate<NF, FB>(sm, s, r, st);
           }
           if (st.bad && cur[s].valid && A.status) A.status[cur[s].c] |= st.bad;
         }
-      prev = cur;
+      for (int s = 0; s < FB; s++) if (cur[s].interior) phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, cur[s], tst[s]);
+      p2 = p1;
+      p1 = cur;
     }
-    finish(prev);
+    trunk_e(p2);
+    trunk_c(p1);
+    legs_d(p1);
+    trunk_e(p1);
   }
 }
 
