@@ -131,10 +131,22 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
   bool p1_int = false, p2_int = false;
   int64_t p1_fo = 0, p2_fo = 0, p1_c = 0;
   HslTrunkState tst;
+#ifdef HSL_PHASE_CLOCKS
+  long long acc[4] = {0, 0, 0, 0};
+  long long t0c = 0, t1c = 0;
+  bool first_tile = true;
+#define HSL_CLK(x) asm volatile("mov.u64 %0, %%clock64;" : "=l"(x)::"memory")
+#define HSL_T0() do { if (first_tile) HSL_CLK(t0c); } while (0)
+#define HSL_T1(k) do { HSL_CLK(t1c); acc[k] += t1c - t0c; t0c = t1c; } while (0)
+#else
+#define HSL_T0()
+#define HSL_T1(k)
+#endif
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
     HslLegState<false> lst;
     int bad = 0;
+    HSL_T0();
     if (role < NF) {
       phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
       bad = lst.bad;
@@ -149,7 +161,9 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
       }
       phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
     }
+    HSL_T1(0);
     __syncthreads();
+    HSL_T1(1);
     if (role < NF) {
       if (p1_int) pipe_d_leg<NF, FB>(sm, s, role);
       if (sl.interior) {
@@ -161,10 +175,22 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
     } else if (sl.interior) {
       phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
     }
+    HSL_T1(2);
     __syncthreads();
+    HSL_T1(3);
+#ifdef HSL_PHASE_CLOCKS
+    first_tile = false;
+#endif
     p2_int = p1_int; p2_fo = p1_fo;
     p1_int = sl.interior; p1_fo = sl.fo; p1_c = sl.c;
   }
+#ifdef HSL_PHASE_CLOCKS
+  if (A.phase_clk && (threadIdx.x & 31) == 0) {
+    long long* dst = A.phase_clk + ((size_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32) * 8;
+    for (int k = 0; k < 4; k++) dst[k] = acc[k];
+    dst[4] = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  }
+#endif
   // drain: E(T-1), C(T) | D(T) | E(T)
   if (role == NF) {
     if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
