@@ -117,9 +117,31 @@ HSL_HD void wrap_pm_pi(double& a) {  // visualization.cpp:73-79
 }
 
 // ------------------------------------------------------------------ gait generator (a2)
+// Register copy of the candidate constants one thread needs.  Loading them all up front (before any branch that
+// depends on them) puts every global load of the prologue in flight at once: one L2 round trip instead of one per
+// dependent use.
+struct HslCandView {
+  double R0[9], tp0[3], eul[3];
+  double period, step_length, step_height, v, t_step, curvature, max_radius;
+  double pos0[3], ts, xs;  // of the thread's limb (unused by the trunk)
+};
+HSL_HD void load_cand(const HslCand& c, int limb, HslCandView& o) {
+#pragma unroll
+  for (int k = 0; k < 9; k++) o.R0[k] = c.R0[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { o.tp0[k] = c.tp0[k]; o.eul[k] = c.eul[k]; }
+  o.period = c.period; o.step_length = c.step_length; o.step_height = c.step_height; o.v = c.v;
+  o.t_step = c.t_step; o.curvature = c.curvature; o.max_radius = c.max_radius;
+  if (limb >= 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) o.pos0[k] = c.pos0[limb][k];
+    o.ts = c.ts[limb]; o.xs = c.xs[limb];
+  }
+}
+
 // Torso joint values (position + Euler angles) at time t: pergensetup::turn_torso, pergen.cpp:386-397.
 // Returns true when the orientation is unchanged from the candidate's (straight walking).
-HSL_HD bool torso_values(const HslCand& cd, double t, double* qt, double* eul) {
+HSL_HD bool torso_values(const HslCandView& cd, double t, double* qt, double* eul) {
   const double tv = t * cd.v;
   double psi = 0;
   if (cd.curvature != 0) {
@@ -153,23 +175,23 @@ HSL_HD void torso_frame(const HslModelPod& M, const double* qt, const double* R0
   for (int i = 0; i < 3; i++) t0[i] = R0[i] * M.Qt[0] + R0[3 + i] * M.Qt[1] + R0[6 + i] * M.Qt[2] + (qt[i] + M.Pt[i]);
 }
 // Foot target of one limb at time t: periodicgenerator::limb_positions / turn_position, pergen.cpp:62-94,160-183.
-HSL_HD void foot_target(const HslCand& cd, int limb, double t, double* p) {
+HSL_HD void foot_target(const HslCandView& cd, double t, double* p) {
   const double tr = hsl_div(t, cd.period);
   const int t_int = (int)tr;
   const double tf = tr - t_int;
-  const double tl = cd.ts[limb];
+  const double tl = cd.ts;
   double sf;
   if (tf < tl) sf = 0;
   else if (tf < tl + cd.t_step) sf = hsl_div(tf - tl, cd.t_step);
   else sf = 1;
   double sn, cs;
   hsl_sincos_0_pi(M_PI * sf, &sn, &cs);
-  double dx = (t_int + cd.xs[limb] + (1 - cs) / 2) * cd.step_length;
+  double dx = (t_int + cd.xs + (1 - cs) / 2) * cd.step_length;
   double dy = 0;
   const double dz = sn * sn * cd.step_height;
   if (cd.curvature != 0) {
     const int s = (cd.curvature > 0) ? 1 : -1;
-    const double rc = 1. / cd.curvature, rx = cd.pos0[limb][0], ry = cd.pos0[limb][1] - rc;
+    const double rc = 1. / cd.curvature, rx = cd.pos0[0], ry = cd.pos0[1] - rc;
     const double r = sqrt(rx * rx + ry * ry);
     const double alpha = atan2(ry, rx), beta = -s * dx / cd.max_radius, gamma = alpha - beta / 2;
     const double sb = 2 * sin(beta / 2);
@@ -178,9 +200,9 @@ HSL_HD void foot_target(const HslCand& cd, int limb, double t, double* p) {
     dx = r * sg * sb;
     dy += -r * cg * sb;
   }
-  p[0] = dx + cd.pos0[limb][0];
-  p[1] = dy + cd.pos0[limb][1];
-  p[2] = dz + cd.pos0[limb][2];
+  p[0] = dx + cd.pos0[0];
+  p[1] = dy + cd.pos0[1];
+  p[2] = dz + cd.pos0[2];
 }
 
 // ------------------------------------------------------------------ closed-form limb IK (a3)
@@ -355,7 +377,8 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
   }
   double R0[9], t0[3], qt[3], eul[3], qa[3], cq[3], sq[3];
   if (MODE == HSL_MODE_GAIT) {
-    const HslCand& cd = A.cand[sl.c];
+    HslCandView cd;
+    load_cand(A.cand[sl.c], limb, cd);
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
     if (torso_values(cd, t, qt, eul)) {
 #pragma unroll
@@ -366,7 +389,7 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     torso_frame(M, qt, R0, t0);
     // foot target into the hip joint frame (lik.cpp:341-347), then the closed-form solver
     double p[3], Rh[9], th[3], oj[3], d[3], pl[3];
-    foot_target(cd, limb, t, p);
+    foot_target(cd, t, p);
 #pragma unroll
     for (int k = 0; k < 3; k++) oj[k] = L.oatt[k];
     double ta[3];
@@ -429,7 +452,8 @@ HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM&
   if (MODE == HSL_MODE_FIELDS) return;
   double qt[3], eul[3];
   if (MODE == HSL_MODE_GAIT) {
-    const HslCand& cd = A.cand[sl.c];
+    HslCandView cd;
+    load_cand(A.cand[sl.c], -1, cd);
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
     if (torso_values(cd, t, qt, eul)) {
 #pragma unroll
@@ -467,14 +491,15 @@ HSL_HD void root_ref(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, 
     ref[k] = (MODE == HSL_MODE_FIELDS) ? A.f_pos[((int64_t)sl.i * M.n + M.trunk[0].body) * 3 + k]
                                        : sm.pos[((3 * NF + 0) * 3 + k) * FB + sl.s];
 }
-// Second central difference exactly as the reference stages it (dynrec.cpp:175-224):
-//   first  = (f(s+1)-f(s-1)) * hh  at frames s+-1, scaled by the mass / inertia,
-//   second = (first(s+1)-first(s-1)) * hh.
+// Second central difference over +-2 frames.  The reference stages it (dynrec.cpp:175-224): first differences
+// (f(s+1)-f(s-1))*hh at frames s+-1, scaled by the mass / inertia, then their difference times hh again
+// (hh = 1/(2 dt)).  The two first differences f(s+2)-f(s) and f(s)-f(s-2) are exact in floating point (neighbouring
+// frames differ by far less than a factor 2), so the staged result equals ((p2-c0) + (m2-c0)) * hh^2 * scale up to
+// the rounding of the staged products; this form needs 4 FP64 instructions instead of 7.
 HSL_HD double fd2(const double* a, int s, int FB_, double hh, double scale) {
   const double m2 = a[s - 2], c0 = a[s], p2 = a[s + 2];
   (void)FB_;
-  const double hi = (p2 - c0) * hh * scale, lo = (c0 - m2) * hh * scale;
-  return (hi - lo) * hh;
+  return ((p2 - c0) + (m2 - c0)) * (hh * hh * scale);
 }
 // In-place inverse of a symmetric positive definite 3x3 stored as (00,01,02,11,12,22), via LDL^T.
 HSL_HD bool spd3_inverse(const double* H, double* W) {

@@ -1,0 +1,121 @@
+"""Gait search around the batched evaluator: the reference's 1-D `pgssweeper` sweep (pergen.cpp:417-449,
+player.cpp:311-321) generalised to N-D grids, random search and a cross-entropy loop over
+(step_duration, period, step_length, step_height), with the candidates evaluated on the GPU(s).
+
+Candidates live on the device between generation, evaluation and selection (torch tensors are the plumbing;
+the evaluation is `hsl_eval_gaits` through the C ABI).  With torch.distributed initialised every rank evaluates
+its shard and the costs are all-gathered (NCCL) before selection, so all ranks agree on the ranking.
+"""
+import itertools
+
+import numpy as np
+
+from .api import HSL_NPARAM, SWEEP_NAMES
+
+BOUNDS = {"step_duration": (0.0, 1.0), "period": (0.3, 20.0), "step_length": (1e-6, 1.0), "step_height": (1e-6, 0.5)}
+
+
+def grid_candidates(base, axes):
+    """Cartesian product of per-parameter value lists.  axes = {name: values}; for one axis built as
+    val0 + i*(val1-val0)/n_val, i = 0..n_val, this is exactly pgssweeper::sweep/next."""
+    names = list(axes)
+    for n in names:
+        if n not in SWEEP_NAMES:
+            raise ValueError("ERROR: cannot sweep over " + n)
+    combos = list(itertools.product(*[np.asarray(axes[n], np.float64) for n in names]))
+    cand = np.tile(np.asarray(base, np.float64), (len(combos), 1))
+    for j, n in enumerate(names):
+        cand[:, SWEEP_NAMES[n]] = [c[j] for c in combos]
+    return cand
+
+
+class DeviceEvaluator:
+    """Evaluates candidate rows resident on the device; shards over ranks when torch.distributed is initialised."""
+
+    def __init__(self, model, n_t, flags=0):
+        import torch
+        self.torch, self.model, self.n_t, self.flags = torch, model, n_t, flags
+        self.dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.rank = self.dist.get_rank() if self.dist else 0
+
+    def __call__(self, cand):
+        """cand: float64 CUDA tensor [C][13] (identical on every rank).  Returns (cot[C], status[C]) CUDA tensors."""
+        torch = self.torch
+        c = cand.shape[0]
+        per = -(-c // self.world)
+        lo, hi = min(self.rank * per, c), min(self.rank * per + per, c)
+        cot = torch.full((per,), float("nan"), dtype=torch.float64, device=cand.device)
+        st = torch.zeros(per, dtype=torch.int32, device=cand.device)
+        if hi > lo:
+            local = cand[lo:hi].contiguous()
+            self.model.eval_gaits_device(hi - lo, self.n_t, local.data_ptr(), cot.data_ptr(), 0, 0, 0, st.data_ptr(), self.flags,
+                                         torch.cuda.current_stream().cuda_stream)
+        if self.dist:
+            allc = torch.empty(self.world * per, dtype=torch.float64, device=cand.device)
+            alls = torch.empty(self.world * per, dtype=torch.int32, device=cand.device)
+            self.dist.all_gather_into_tensor(allc, cot)
+            self.dist.all_gather_into_tensor(alls, st)
+            cot, st = allc, alls
+        return cot[:c], st[:c]
+
+
+def top_k(cot, k):
+    """Indices and costs of the k cheapest valid candidates (NaN = failed candidate, ranked last; ties by index)."""
+    import torch
+    key = torch.nan_to_num(cot, nan=float("inf"))
+    order = torch.argsort(key, stable=True)[:k]
+    return order, cot[order]
+
+
+def grid_search(model, base, axes, n_t, k=1, flags=0, device="cuda"):
+    import torch
+    cand = torch.from_numpy(grid_candidates(base, axes)).to(device)
+    cot, st = DeviceEvaluator(model, n_t, flags)(cand)
+    idx, best = top_k(cot, k)
+    return dict(candidates=cand, cot=cot, status=st, best_index=idx, best_cot=best)
+
+
+def random_search(model, base, ranges, n_cand, n_t, seed=0, k=1, flags=0, device="cuda"):
+    """Uniform sampling of the named parameters inside `ranges` = {name: (lo, hi)}; generated on the device."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cand = torch.from_numpy(np.asarray(base, np.float64)).to(device).repeat(n_cand, 1)
+    for name, (lo, hi) in ranges.items():
+        cand[:, SWEEP_NAMES[name]] = lo + (hi - lo) * torch.rand(n_cand, dtype=torch.float64, device=device, generator=g)
+    cot, st = DeviceEvaluator(model, n_t, flags)(cand)
+    idx, best = top_k(cot, k)
+    return dict(candidates=cand, cot=cot, status=st, best_index=idx, best_cot=best)
+
+
+def cem_search(model, base, ranges, n_t, pop=1024, elite=64, iters=8, seed=0, flags=0, device="cuda"):
+    """Cross-entropy method over the named parameters: sample a Gaussian population, evaluate, refit to the elite."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    names = list(ranges)
+    lo = torch.tensor([ranges[n][0] for n in names], dtype=torch.float64, device=device)
+    hi = torch.tensor([ranges[n][1] for n in names], dtype=torch.float64, device=device)
+    mean, std = (lo + hi) / 2, (hi - lo) / 2
+    cols = [SWEEP_NAMES[n] for n in names]
+    base_t = torch.from_numpy(np.asarray(base, np.float64)).to(device)
+    ev = DeviceEvaluator(model, n_t, flags)
+    history, best = [], (float("inf"), None)
+    for _ in range(iters):
+        z = torch.randn(pop, len(names), dtype=torch.float64, device=device, generator=g)
+        x = torch.minimum(torch.maximum(mean + std * z, lo), hi)
+        cand = base_t.repeat(pop, 1)
+        cand[:, cols] = x
+        cot, st = ev(cand)
+        idx, c = top_k(cot, elite)
+        ok = torch.isfinite(c)
+        if int(ok.sum()) == 0:
+            break
+        el = x[idx][ok]
+        mean, std = el.mean(0), el.std(0, unbiased=False) + 1e-6 * (hi - lo)
+        cbest = float(c[0])
+        history.append(cbest)
+        if cbest < best[0]:
+            best = (cbest, cand[idx[0]].clone())
+    return dict(best_cot=best[0], best_candidate=best[1], history=history, mean=mean, std=std)

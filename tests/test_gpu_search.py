@@ -1,0 +1,51 @@
+"""GPU tier: candidate search around the batched evaluator (BASELINE config 4): grid = the reference's sweep
+generalised to N dimensions, ranking identical to the oracle's."""
+import numpy as np
+import pytest
+
+from conftest import PRESETS, model_xml
+
+pytestmark = pytest.mark.gpu
+
+
+def test_one_axis_grid_is_the_reference_sweep(hsl, orc):
+    from hslabs_b200 import search
+    params, name = orc.load_preset(PRESETS, 8)
+    vals = [3 + i * (18 - 3) / 15 for i in range(16)]       # pgssweeper: val0 + i*delval
+    res = search.grid_search(hsl.Model(model_xml(name)), params, {"period": vals}, 20, k=3)
+    ov, oc = orc.Model(model_xml(name)).measure_cot_sweep(params, 20, "period", 3, 18, 15)
+    got = res["cot"].cpu().numpy()
+    assert np.abs(got - oc).max() <= 1e-9 * np.abs(oc).max()
+    assert list(res["best_index"].cpu().numpy()) == list(np.argsort(oc, kind="stable")[:3])
+
+
+@pytest.mark.parametrize("pid", [8, 9])
+def test_grid_4d_ranking_matches_oracle(hsl, orc, pid):
+    from hslabs_b200 import search
+    params, name = orc.load_preset(PRESETS, pid)
+    axes = {"step_duration": [0.0, 0.5, 1.0], "period": [2.0, 3.0, 5.0], "step_length": [0.2, 0.4], "step_height": [0.05, 0.1]}
+    res = search.grid_search(hsl.Model(model_xml(name)), params, axes, 20, k=5)
+    cand = res["candidates"].cpu().numpy()
+    assert cand.shape == (36, 13)
+    ref = orc.Model(model_xml(name)).eval_batch(cand, 20, nthreads=8)
+    ok = ref["status"] == 0
+    got = res["cot"].cpu().numpy()
+    assert np.array_equal(np.isfinite(got), ok)
+    assert np.abs(got[ok] - ref["cot"][ok]).max() <= 1e-9 * np.abs(ref["cot"][ok]).max()
+    key = np.where(ok, ref["cot"], np.inf)
+    assert list(res["best_index"].cpu().numpy()) == list(np.argsort(key, kind="stable")[:5])
+
+
+def test_random_and_cem_improve(hsl):
+    from hslabs_b200 import search
+    params, name = hsl.load_preset(PRESETS, 8)
+    m = hsl.Model(model_xml(name))
+    ranges = {"step_duration": (0, 1), "period": (1, 6), "step_length": (0.1, 0.5), "step_height": (0.02, 0.12)}
+    rs = search.random_search(m, params, ranges, 2048, 32, seed=1, k=4)
+    assert rs["cot"].shape[0] == 2048 and float(rs["best_cot"][0]) <= float(rs["best_cot"][3])
+    again = search.random_search(m, params, ranges, 2048, 32, seed=1, k=4)
+    assert np.array_equal(again["cot"].cpu().numpy(), rs["cot"].cpu().numpy(), equal_nan=True)   # reproducible
+    cem = search.cem_search(m, params, ranges, 32, pop=512, elite=32, iters=5, seed=2)
+    assert cem["best_cot"] <= cem["history"][0] and cem["best_cot"] < float(np.nanmedian(rs["cot"].cpu().numpy()))
+    base_cot = hsl.measure_cot(m, params, 32)
+    assert cem["best_cot"] < base_cot
