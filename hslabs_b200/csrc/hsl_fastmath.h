@@ -74,6 +74,15 @@ HSL_HD double hsl_sqrt(double x) {
   return (x == 0.0) ? 0.0 : g;
 }
 
+// 1/sqrt(x), x > 0: seed + two Newton steps y <- y + y*(1 - x y^2)/2  (2^-23 -> 2^-45 -> 2^-89), ~1 ulp
+HSL_HD double hsl_rsqrt(double x) {
+  double y = hsl_rsqrt_seed(x);
+  double e = fma(-(x * y), y, 1.0);
+  y = fma(y * 0.5, e, y);
+  e = fma(-(x * y), y, 1.0);
+  return fma(y * 0.5, e, y);
+}
+
 // sin and cos of x in [0, pi] (the argument range of the gait generator's stepx / stepz, pergen.cpp:62-71).
 // Quadrant reduction r = x - k*pi/2 with a two-part pi/2 (k in {0,1,2}; k*PIO2_HI is exact), then the Taylor
 // series of sin and cos on |r| <= pi/4 (9 terms each, truncation < 1e-19; coefficients are exact reciprocals of

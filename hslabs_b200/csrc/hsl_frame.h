@@ -219,18 +219,39 @@ HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, doubl
   const bool yxx = (L.kind == HSL_IK_YXX);
   const double zoff = yxx ? pl[2] - s0 * l0 : pl[2] + l0;
   const double rho2 = pl[0] * pl[0] + pl[1] * pl[1];
-  double l = hsl_sqrt(rho2 + zoff * zoff);
+  const double l2sq = rho2 + zoff * zoff;
+  // Quotients by l are formed with one reciprocal square root (products, ~1.5 ulp).  When the angles are requested
+  // (trajectory dump) the reference's own operation order -- l = sqrt(.), then IEEE divisions -- is used instead, so
+  // that the dumped angles match it bit for bit wherever acos / atan2 are well conditioned.
+  double l, c, cb, cg;
   bool ok = true;
-  if (l1 + l2 - l < 0) {
-    if (ignore_reach) l = l1 + l2; else ok = false;
-  }
-  const double c = hsl_div(zoff, l);
-  const double ll = l * l, del = l2 * l2 - l1 * l1;
+  const double del = l2 * l2 - l1 * l1;
   const int sg = yxx ? s1 * s0 : s1;
-  const double cb = hsl_div(ll - del, 2 * l1 * l);
-  const double cg = hsl_div(ll + del, 2 * l2 * l);
+  if (ang) {
+    l = hsl_sqrt(l2sq);
+    if (l1 + l2 - l < 0) { if (ignore_reach) l = l1 + l2; else ok = false; }
+    const double ll = l * l;
+    c = hsl_div(zoff, l);
+    cb = hsl_div(ll - del, 2 * l1 * l);
+    cg = hsl_div(ll + del, 2 * l2 * l);
+  } else {
+    double rl = hsl_rsqrt(l2sq);
+    l = l2sq * rl;
+    if (l1 + l2 - l < 0) {
+      if (ignore_reach) { l = l1 + l2; rl = hsl_rcp(l); } else ok = false;
+    }
+    const double ll = l * l;
+    c = zoff * rl;
+    cb = (ll - del) * rl * L.inv2l1;
+    cg = (ll + del) * rl * L.inv2l2;
+    // products can overshoot +-1 by an ulp exactly at the boundary (leg fully stretched, l == l1 + l2), where the
+    // IEEE quotient is exactly 1; pull such values back so that the square roots below stay real
+    c = (fabs(c) > 1.0 && fabs(c) < 1.0 + 1e-15) ? copysign(1.0, c) : c;
+    cb = (cb > 1.0 && cb < 1.0 + 1e-15) ? 1.0 : cb;
+    cg = (cg > 1.0 && cg < 1.0 + 1e-15) ? 1.0 : cg;
+  }
   // phi = atan2(x, y): cos(phi) = y / rho, sin(phi) = x / rho  (atan2(0,0) = 0)
-  const double rrho = hsl_rcp(hsl_sqrt(rho2));
+  const double rrho = hsl_rsqrt(rho2);
   const double cphi = (rho2 > 0) ? pl[1] * rrho : 1.0, sphi = (rho2 > 0) ? pl[0] * rrho : 0.0;
   const double st0 = hsl_sqrt((1 - c) * (1 + c));  // sin(acos(c)) >= 0 ; NaN when |c| > 1, as acos would be
   double cth, sth;

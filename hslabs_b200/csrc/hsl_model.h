@@ -38,6 +38,7 @@ typedef struct HslLimb {
   double foot[3];   // odepart::capsule_to_pos of the last link (foot point), visualization.cpp:503,565
   double oatt[3];   // offset of the trunk body the limb hangs from, in the torso frame
   double ls[3];     // link lengths used by the closed-form IK (lik.cpp:226-227)
+  double inv2l1, inv2l2;  // 1/(2 l1), 1/(2 l2)
   int32_t ysign;    // lik.cpp:231,237,243
   int32_t kind;     // HSL_IK_YXX / HSL_IK_ZXX
   int32_t bend;     // liklimb::limb_bend (true), lik.cpp:300

@@ -285,6 +285,7 @@ int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* errbuf, in
     L.bend = 1;
     const double l0 = (M.lik_index == 2) ? .1 : .05;
     L.ls[0] = l0; L.ls[1] = .4; L.ls[2] = .4;  // lik.cpp:226-227
+    L.inv2l1 = 1.0 / (2 * L.ls[1]); L.inv2l2 = 1.0 / (2 * L.ls[2]);
     L.kind = (M.lik_index == 2) ? HSL_IK_ZXX : HSL_IK_YXX;
     L.ysign = (M.lik_index == 0) ? ((l < 2) ? 1 : -1) : ((l % 2 == 0) ? 1 : -1);  // lik.cpp:231,237,243
   }

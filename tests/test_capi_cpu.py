@@ -41,11 +41,11 @@ def test_packed_model_matches_oracle_tree(hsl, orc, name):
     n, nf = int(ints[0]), int(ints[1])
     dbl = pod[24:].view(np.float64)
     assert dbl[0] == 0.08 and dbl[1] == 1.0
-    # limbs: HslLimb = 3 x HslHinge (30 doubles each) + 9 doubles + 6 int32 ; trunk: 8 doubles + 2 int32 = 9 doubles
+    # limbs: HslLimb = 3 x HslHinge (30 doubles each) + 11 doubles + 6 int32 ; trunk: 8 doubles + 2 int32 = 9 doubles
     trunk0 = 2 + 6
     limb0 = trunk0 + 8 * 9
     for l in range(nf):
-        base = limb0 + l * (3 * 30 + 9 + 3)
+        base = limb0 + l * (3 * 30 + 11 + 3)
         body = int(cons["limb_top"][l])
         for h in range(3):
             hb = base + 30 * h

@@ -192,7 +192,8 @@ def test_kernel_variants_agree(hsl):
         assert np.array_equal(full["status"], det["status"]), (fb, mr)
         for k in ("work", "min_cfz", "max_mu"):
             okk = det["status"] == 0
-            assert np.abs(full[k][okk] - det[k][okk]).max() <= 1e-12 * np.abs(det[k][okk]).max(), (fb, mr, k)
+            tol = 1e-9 if k == "max_mu" else 1e-12  # max_mu is a ratio with a small denominator
+            assert np.abs(full[k][okk] - det[k][okk]).max() <= tol * np.abs(det[k][okk]).max(), (fb, mr, k)
         assert np.array_equal(np.isnan(got), np.isnan(ref)), (fb, mr)
         assert np.nanmax(np.abs(got - ref) / np.abs(ref)) < 1e-12, (fb, mr)
 
