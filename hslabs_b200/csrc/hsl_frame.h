@@ -413,14 +413,18 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     foot_target(cd, t, p);
 #pragma unroll
     for (int k = 0; k < 3; k++) oj[k] = L.oatt[k];
-    double ta[3];
+    double ta[3], e[3];
     m3_affine(R0, oj, t0, ta);           // frame of the trunk body the limb hangs from
-    m3_mul(R0, L.h[0].Rjp, Rh);
-    m3_affine(R0, L.h[0].tjp, ta, th);
+    m3_affine(R0, L.h[0].tjp, ta, th);   // hip joint origin
 #pragma unroll
     for (int k = 0; k < 3; k++) d[k] = p[k] - th[k];
+    // (R0 Rjp)^T d = Rjp^T (R0^T d): two matrix-vector products instead of a matrix-matrix product
 #pragma unroll
-    for (int k = 0; k < 3; k++) pl[k] = Rh[3 * k] * d[0] + Rh[3 * k + 1] * d[1] + Rh[3 * k + 2] * d[2];
+    for (int k = 0; k < 3; k++) e[k] = R0[3 * k] * d[0] + R0[3 * k + 1] * d[1] + R0[3 * k + 2] * d[2];
+    const double* Rj0 = L.h[0].Rjp;
+#pragma unroll
+    for (int k = 0; k < 3; k++) pl[k] = Rj0[3 * k] * e[0] + Rj0[3 * k + 1] * e[1] + Rj0[3 * k + 2] * e[2];
+    (void)Rh;
     const bool want_angles = DUMP && A.q_out != nullptr;
     if (!limb_ik(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, cq, sq, want_angles ? qa : nullptr)) st.bad |= HSL_ST_UNREACHABLE;
   } else {  // HSL_MODE_TRAJ
@@ -522,26 +526,19 @@ HSL_HD double fd2(const double* a, int s, int FB_, double hh, double scale) {
   (void)FB_;
   return ((p2 - c0) + (m2 - c0)) * (hh * hh * scale);
 }
-// In-place inverse of a symmetric positive definite 3x3 stored as (00,01,02,11,12,22), via LDL^T.
+// Inverse of a symmetric positive definite 3x3 stored as (00,01,02,11,12,22): adjugate over determinant (one
+// reciprocal, all cofactors independent of each other -- a short dependency chain).  Returns false unless the
+// leading minors are positive relative to the trace (the matrix is then not safely positive definite).
 HSL_HD bool spd3_inverse(const double* H, double* W) {
-  const double d0 = H[0];
-  const double i0 = hsl_rcp(d0);
-  const double l10 = H[1] * i0, l20 = H[2] * i0;
-  const double d1 = H[3] - l10 * H[1];
-  const double i1 = hsl_rcp(d1);
-  const double l21 = (H[4] - l20 * H[1]) * i1;
-  const double d2 = H[5] - l20 * H[2] - l21 * l21 * d1;
-  const double i2 = hsl_rcp(d2);
-  // inverse of L (unit lower): m10 = -l10, m21 = -l21, m20 = l10*l21 - l20
-  const double m10 = -l10, m21 = -l21, m20 = l10 * l21 - l20;
-  W[5] = i2;
-  W[4] = m21 * i2;
-  W[2] = m20 * i2;
-  W[3] = i1 + m21 * m21 * i2;
-  W[1] = m10 * i1 + m21 * m20 * i2;
-  W[0] = i0 + m10 * m10 * i1 + m20 * m20 * i2;
-  const double tol = 1e-13 * (H[0] + H[3] + H[5]);
-  return (d0 > tol) && (d1 > tol) && (d2 > tol);
+  const double a = H[0], b = H[1], c = H[2], d = H[3], e = H[4], f = H[5];
+  const double c00 = d * f - e * e, c01 = c * e - b * f, c02 = b * e - c * d;
+  const double c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
+  const double det = a * c00 + b * c01 + c * c02;
+  const double id = hsl_rcp(det);
+  W[0] = c00 * id; W[1] = c01 * id; W[2] = c02 * id;
+  W[3] = c11 * id; W[4] = c12 * id; W[5] = c22 * id;
+  const double tr = a + d + f, tol = 1e-13;
+  return (a > tol * tr) && (c22 > tol * tr * tr) && (det > tol * tr * tr * tr);
 }
 HSL_HD void sym3_mul(const double* W, const double* x, double* y) {
   y[0] = W[0] * x[0] + W[1] * x[1] + W[2] * x[2];
