@@ -142,6 +142,42 @@ class pgssweeper {
   int number_of_values() const { return n_val_ + 1; }
 };
 
+// dynrecord (dynrec.h:76-106): the per-frame quantities the force-torque system is assembled from, as plain arrays
+// ([body][3] for pos, jpos, jzaxis, mom_rate, ang_mom_rate; [foot][3] for fpos; [foot] for contacts).
+struct dynrecord {
+  int n, nf;
+  std::vector<double> pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos;
+  std::vector<uint8_t> contacts;
+  dynrecord(int n_, int nf_) : n(n_), nf(nf_), pos(3 * n_), jpos(3 * n_), jzaxis(3 * n_), mom_rate(3 * n_), ang_mom_rate(3 * n_),
+                               fpos(3 * nf_), contacts(nf_) {}
+  int get_ncontacts() const { int s = 0; for (int i = 0; i < nf; i++) s += contacts[i]; return s; }
+};
+
+// forcetorquesolver (ftsolver.h:37-69): solve_forcetorques on one populated dynrecord.  x = joint forces then joint
+// torques (6n), z = contact forces of all feet in LIK order (3 nf); get_fts / motor torques as in the reference.
+class forcetorquesolver {
+  const kinematicmodel* model_;
+  std::vector<double> fts_, tau_;
+  bool pen_force_, pen_torque_;
+ public:
+  explicit forcetorquesolver(const kinematicmodel* model) : model_(model), pen_force_(false), pen_torque_(false) {}
+  void switch_torso_penalty(bool force_flag, bool torque_flag) { pen_force_ = force_flag; pen_torque_ = torque_flag; }
+  void solve_forcetorques(const dynrecord* rec, std::vector<double>& x, std::vector<double>& z) {
+    if (!(pen_force_ && pen_torque_)) {
+      if (!pen_force_ && !pen_torque_) throw error("ERROR: mask0 not set");  // ftsolver.cpp:245
+      throw error("only switch_torso_penalty(1,1) is supported on the GPU path");
+    }
+    const int n = model_->number_of_parts(), nf = model_->number_of_limbs(), nmj = model_->number_of_motor_joints();
+    x.assign(6 * n, 0.0); z.assign(3 * nf, 0.0); tau_.assign(nmj, 0.0);
+    int32_t status = 0;
+    check(hsl_solve_frames_host(model_->handle(), 1, rec->pos.data(), rec->jpos.data(), rec->jzaxis.data(), rec->mom_rate.data(),
+                                rec->ang_mom_rate.data(), rec->fpos.data(), rec->contacts.data(), x.data(), z.data(), tau_.data(), &status));
+    fts_ = x;
+  }
+  const std::vector<double>* get_fts() const { return &fts_; }
+  const std::vector<double>& get_motor_torques() const { return tau_; }  // periodic::get_motor_torques
+};
+
 // periodic (periodic.h:27-87)
 class periodic {
   const kinematicmodel* model_;
