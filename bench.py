@@ -168,16 +168,19 @@ def main():
     d_work = torch.empty_like(d_cot)
     d_status = torch.empty(n_cand, dtype=torch.int32, device=dev)
     gathered = torch.empty(world * n_cand, dtype=torch.float64, device=dev) if world > 1 else None
+    best = torch.empty(1, dtype=torch.int64, device=dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
         model.eval_gaits_device(n_cand, n_t, d_params.data_ptr(), d_cot.data_ptr(), d_work.data_ptr(), 0, 0,
                                 d_status.data_ptr(), 0, stream)
+        costs = d_cot
         if world > 1:
             dist.all_gather_into_tensor(gathered, d_cot)
-            return int(torch.argmin(torch.nan_to_num(gathered, nan=float("inf"))))
-        return int(torch.argmin(torch.nan_to_num(d_cot, nan=float("inf"))))
+            costs = gathered
+        api.select_best_device(costs.data_ptr(), costs.numel(), best.data_ptr(), 0, stream)   # selection on every rank
+        return best
 
     def barrier():
         if world > 1:
@@ -200,7 +203,7 @@ def main():
         b.record()
     barrier()
     clocks = sampler.stop()
-    launches = model.launch_count() - launches0
+    launches = model.launch_count() - launches0 + args.steps  # setup + frames + finish per step, + the selection kernel
     ms = sum(a.elapsed_time(b) for a, b in ev)
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:

@@ -63,6 +63,7 @@ def _load():
     lib.hsl_launch_count.argtypes = [vp]
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
     lib.hsl_math_selftest.argtypes = [i32, vp, vp, vp]
+    lib.hsl_select_best.argtypes = [vp, i64, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -72,7 +73,7 @@ def exported_symbols():
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_set_tuning", "hsl_launch_count",
-            "hsl_dfma_probe", "hsl_math_selftest"]
+            "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
 
 
 def _check(rc):
@@ -198,6 +199,11 @@ class Model:
                           stream=0):
         _check(_load().hsl_eval_gaits(self._h, n_cand, n_t, d_params, flags, d_cot or None, d_work or None,
                                       d_min_cfz or None, d_max_mu or None, d_status or None, stream or None))
+
+
+def select_best_device(d_cost, n, d_index, d_value=0, stream=0):
+    """Argmin over device-resident costs (NaN skipped); arguments are integer device addresses."""
+    _check(_load().hsl_select_best(d_cost, n, d_index or None, d_value or None, stream or None))
 
 
 def dfma_probe(blocks=148 * 8, threads=256, iters=4096):

@@ -204,6 +204,12 @@ int hsl_eval_gaits(HslModel* m, int64_t n_cand, int n_t, const double* d_params,
   return eval_gaits_dev(m, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, false, (cudaStream_t)stream);
 }
 
+int hsl_select_best(const double* d_cost, int64_t n, int64_t* d_index, double* d_value, void* stream) {
+  if (!d_cost || n < 1) return set_err(HSL_ERR_ARG, "bad argument");
+  HSL_CUDA(hsl_launch_argmin(d_cost, n, d_index, d_value, (cudaStream_t)stream));
+  return HSL_OK;
+}
+
 static int ensure_stream(HslModel* m) {
   if (!m->stream) HSL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
   return HSL_OK;

@@ -254,6 +254,43 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
   }
 }
 
+// Selection: index and value of the cheapest valid candidate (NaN = failed candidate, never selected; ties go to
+// the lowest index, as a stable sort of the costs would).  One block; used after the all-gather of the costs.
+__global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, int64_t* __restrict__ out_index, double* __restrict__ out_value) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  double best = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+  long long bi = -1;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double c = cost[i];
+    if (c < best) { best = c; bi = i; }  // NaN compares false; strided scan visits ascending indices per thread
+  }
+  auto better = [](double v, long long i, double bv, long long bidx) { return i >= 0 && (bidx < 0 || v < bv || (v == bv && i < bidx)); };
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = (blockDim.x + 31) / 32;
+    best = (threadIdx.x < nw) ? sv[threadIdx.x] : __longlong_as_double(0x7ff0000000000000LL);
+    bi = (threadIdx.x < nw) ? si[threadIdx.x] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      if (out_index) *out_index = bi;
+      if (out_value) *out_value = (bi >= 0) ? best : __longlong_as_double(0x7ff8000000000000LL);
+    }
+  }
+}
+
 // FP64 FMA throughput probe: register-resident dependent chains, 8 per thread.  Used by bench.py for the
 // roofline denominator of this FP64-bound path (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void hsl_dfma_probe_kernel(double* out, int iters, double a, double b) {
@@ -377,6 +414,11 @@ cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const 
   const int64_t threads = n_cand * 32;
   hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
                                                                          fmax_in, status, cot, work, min_cfz, max_mu);
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_argmin(const double* cost, int64_t n, int64_t* out_index, double* out_value, cudaStream_t st) {
+  hsl_argmin_kernel<<<1, 1024, 0, st>>>(cost, n, out_index, out_value);
   return cudaGetLastError();
 }
 

@@ -57,6 +57,10 @@ int hsl_device_count(void);
  * d_params [n_cand][13], outputs [n_cand] (any output may be NULL); all DEVICE pointers. */
 int hsl_eval_gaits(HslModel* m, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
                    double* d_min_cfz, double* d_max_mu, int32_t* d_status, void* stream);
+/* Selection after the (all-gathered) costs: index and value of the cheapest valid candidate; NaN costs (failed
+ * candidates) are never selected, ties go to the lowest index; index -1 / value NaN when nothing is valid.
+ * DEVICE pointers. */
+int hsl_select_best(const double* d_cost, int64_t n, int64_t* d_index, double* d_value, void* stream);
 /* same, HOST pointers (pinned staging inside). */
 int hsl_eval_gaits_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, double* cot, double* work,
                         double* min_cfz, double* max_mu, int32_t* status);

@@ -225,3 +225,41 @@ def test_full_size_properties(hsl, orc):
     # unreachable candidates report NaN and a status bit, never garbage
     badrows = a["status"] & 3 != 0
     assert np.isnan(a["cot"][badrows]).all() and np.isfinite(a["cot"][~badrows]).all()
+
+
+def test_config3_shard_size_properties(hsl, orc):
+    """BASELINE config 3, one GPU's shard: spider.xml, 8192 candidates x 512 frames (4.2 M frame solves): runs,
+    is reproducible, agrees with the oracle on a sampled subset and ranks it identically."""
+    n, n_t = 8192, 512
+    p = _random_candidates("spider", n, 20261019)
+    m = hsl.Model(model_xml("spider"))
+    a = m.eval_gaits(p, n_t)
+    b = m.eval_gaits(p, n_t)
+    assert np.array_equal(a["cot"], b["cot"], equal_nan=True)
+    ok = np.where(a["status"] == 0)[0]
+    assert ok.size > n // 2
+    sample = ok[np.linspace(0, ok.size - 1, 8).astype(int)]
+    ref = orc.Model(model_xml("spider")).eval_batch(p[sample], n_t, nthreads=8)
+    assert (ref["status"] == 0).all()
+    assert np.abs(a["cot"][sample] - ref["cot"]).max() <= TOL * np.abs(ref["cot"]).max()
+    assert np.abs(a["work"][sample] - ref["work"]).max() <= TOL * np.abs(ref["work"]).max()
+    assert np.array_equal(np.argsort(a["cot"][sample]), np.argsort(ref["cot"]))
+
+
+def test_small_and_ragged_batches(hsl, orc):
+    """Edge sizes: one candidate, n_t = 1 and 2 (fewer frames than the finite-difference stencil is wide), batches that
+    do not fill a block, many short candidates per block."""
+    xml = model_xml("hexapod")
+    p, _ = orc.load_preset(PRESETS, 8)
+    m = hsl.Model(xml)
+    om = orc.Model(xml)
+    for n_t in (1, 2, 3, 5, 27, 29, 61):
+        ref = om.measure_cot(p, n_t)
+        got = m.eval_gaits(p, n_t)
+        assert got["status"][0] == 0 and ref["status"] == 0
+        assert abs(got["cot"][0] - ref["cot"]) <= TOL * max(abs(ref["cot"]), 1e-300), n_t
+    batch = np.tile(p, (37, 1))
+    batch[:, 7] = np.linspace(2.0, 6.0, 37)
+    ref = om.eval_batch(batch, 6, nthreads=8)
+    got = m.eval_gaits(batch, 6)      # 37 candidates x 10 slots: several candidates per block
+    assert np.abs(got["cot"] - ref["cot"]).max() <= TOL * np.abs(ref["cot"]).max()

@@ -49,3 +49,28 @@ def test_random_and_cem_improve(hsl):
     assert cem["best_cot"] <= cem["history"][0] and cem["best_cot"] < float(np.nanmedian(rs["cot"].cpu().numpy()))
     base_cot = hsl.measure_cot(m, params, 32)
     assert cem["best_cot"] < base_cot
+
+
+def test_select_best_kernel(hsl):
+    import torch
+    from hslabs_b200 import api
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 1024, 4096 * 8 + 5):
+        c = rng.uniform(0.1, 5.0, n)
+        c[rng.integers(0, n, max(1, n // 7))] = np.nan
+        if n > 40:
+            c[37] = c[11] = np.nanmin(c) - 0.01          # a tie: the lower index wins
+        t = torch.from_numpy(c).cuda()
+        idx = torch.empty(1, dtype=torch.int64, device="cuda")
+        val = torch.empty(1, dtype=torch.float64, device="cuda")
+        api.select_best_device(t.data_ptr(), n, idx.data_ptr(), val.data_ptr())
+        torch.cuda.synchronize()
+        if np.isnan(c).all():
+            assert int(idx) == -1
+        else:
+            assert int(idx) == int(np.nanargmin(c)) and float(val) == float(np.nanmin(c))
+    allnan = torch.full((100,), float("nan"), dtype=torch.float64, device="cuda")
+    idx = torch.empty(1, dtype=torch.int64, device="cuda")
+    api.select_best_device(allnan.data_ptr(), 100, idx.data_ptr())
+    torch.cuda.synchronize()
+    assert int(idx) == -1
