@@ -257,7 +257,9 @@ def test_small_and_ragged_batches(hsl, orc):
         ref = om.measure_cot(p, n_t)
         got = m.eval_gaits(p, n_t)
         assert got["status"][0] == 0 and ref["status"] == 0
-        assert abs(got["cot"][0] - ref["cot"]) <= TOL * max(abs(ref["cot"]), 1e-300), n_t
+        # n_t = 1, 2: every frame is a whole number of periods apart, the joints do not move and the work is 0 up to
+        # round-off (FMA contraction on the device leaves ~1e-17 where the host gets an exact 0)
+        assert abs(got["cot"][0] - ref["cot"]) <= TOL * max(abs(ref["cot"]), 1e-3), n_t
     batch = np.tile(p, (37, 1))
     batch[:, 7] = np.linspace(2.0, 6.0, 37)
     ref = om.eval_batch(batch, 6, nthreads=8)
