@@ -11,8 +11,9 @@
 //   trunk warps | E(t-2) ; A'(t) ; C(t-1): 6x6 solve            | B'(t)
 //
 // Phase D needs 24 doubles of limb state from phase B of the same frame; instead of keeping them in registers across
-// a whole tile they are parked in shared memory (`dstate`, written at the end of B(t), read back in D(t) one
-// iteration later, by the same thread).  Buffers and their hand-offs (w = written, r = read):
+// a whole tile they are parked in shared memory: 12 in `dstate` (written at the end of B(t), read back in D(t) one
+// iteration later, by the same thread) and W, W g, r in the limb's own `part` entries, which nobody overwrites
+// before that same thread runs B(t+1) -- after D(t).  Buffers and their hand-offs (w = written, r = read):
 //   pos/ust/cs  w A(t),A'(t) | r B(t),B'(t)            part   w B(t)      | r C(t)   (next first half)
 //   mu          w C(t-1)     | r D(t-1) (second half)  dstate w end B(t)  | r D(t)   (same thread, next iteration)
 //   fin         w D(t-1)     | r E(t-1) (next first half)
@@ -20,7 +21,7 @@
 #pragma once
 #include "hsl_frame.h"
 
-#define HSL_DSTATE 27  // per limb: tau_p*qd [3], w*qd [9], W [6], W g [3], r [3], results of phase D [3]
+#define HSL_DSTATE 15  // per limb: tau_p*qd [3], w*qd [9], results of phase D [3]  (W, W g, r are re-read from `part`)
 
 template <int NF, int FB>
 struct HslPipeSmem : HslSmem<NF, FB, 19> {
@@ -32,7 +33,7 @@ struct HslPipeSmem : HslSmem<NF, FB, 19> {
   }
 };
 
-// Limb thread, end of phase B: park what phase D needs.  Swing feet store W = 0, so their contact force vanishes.
+// Limb thread, end of phase B: park what phase D needs besides W, W g, r.
 template <int NF, int FB, class SM>
 HSL_HD void pipe_store_dstate(const SM& sm, int s, int limb, const HslLegState<false>& st) {
   double* D = sm.dstate + (limb * HSL_DSTATE) * FB + s;
@@ -42,13 +43,6 @@ HSL_HD void pipe_store_dstate(const SM& sm, int s, int limb, const HslLegState<f
 #pragma unroll
     for (int k = 0; k < 3; k++) D[(3 + 3 * h + k) * FB] = st.w[h][k] * st.qd[h];
   }
-#pragma unroll
-  for (int k = 0; k < 6; k++) D[(12 + k) * FB] = st.contact ? st.W[k] : 0.0;
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    D[(18 + k) * FB] = st.contact ? st.Wg[k] : 0.0;
-    D[(21 + k) * FB] = st.contact ? st.r[k] : 0.0;
-  }
 }
 
 // Limb thread, phase D of the previous tile (phase_d_leg of the plain kernel, from the parked state):
@@ -56,18 +50,22 @@ HSL_HD void pipe_store_dstate(const SM& sm, int s, int limb, const HslLegState<f
 template <int NF, int FB, class SM>
 HSL_HD void pipe_d_leg(const SM& sm, int s, int limb) {
   double* D = sm.dstate + (limb * HSL_DSTATE) * FB + s;
-  double W[6], Wg[3], r[3], mu[6], y[3], Wy[3], lam[3];
+  const double* P = sm.part + (limb * SM::PART) * FB + s;
+  const bool con = (P[18 * FB] != 0.0) && (sm.mu[6 * FB + s] != 0.0);
+  double lam[3] = {0, 0, 0};
+  if (con) {
+    double W[6], Wg[3], r[3], mu[6], y[3], Wy[3];
 #pragma unroll
-  for (int k = 0; k < 6; k++) { W[k] = D[(12 + k) * FB]; mu[k] = sm.mu[k * FB + s]; }
+    for (int k = 0; k < 6; k++) { W[k] = P[(6 + k) * FB]; mu[k] = sm.mu[k * FB + s]; }
 #pragma unroll
-  for (int k = 0; k < 3; k++) { Wg[k] = D[(18 + k) * FB]; r[k] = D[(21 + k) * FB]; }
-  const bool con = (W[0] > 0.0) && (sm.mu[6 * FB + s] != 0.0);  // W is positive definite for a foot on the ground
-  v3_cross(mu + 3, r, y);
+    for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
+    v3_cross(mu + 3, r, y);
 #pragma unroll
-  for (int k = 0; k < 3; k++) y[k] += mu[k];
-  sym3_mul(W, y, Wy);
+    for (int k = 0; k < 3; k++) y[k] += mu[k];
+    sym3_mul(W, y, Wy);
 #pragma unroll
-  for (int k = 0; k < 3; k++) lam[k] = con ? -(Wg[k] + Wy[k]) : 0.0;
+    for (int k = 0; k < 3; k++) lam[k] = -(Wg[k] + Wy[k]);
+  }
   double work = 0;
 #pragma unroll
   for (int h = 0; h < 3; h++) {
@@ -79,9 +77,9 @@ HSL_HD void pipe_d_leg(const SM& sm, int s, int limb) {
     cfz = lam[2];
     mu_f = hsl_div(hsl_sqrt(lam[0] * lam[0] + lam[1] * lam[1]), lam[2]);
   }
-  D[24 * FB] = work;
-  D[25 * FB] = cfz;
-  D[26 * FB] = mu_f;
+  D[12 * FB] = work;
+  D[13 * FB] = cfz;
+  D[14 * FB] = mu_f;
 }
 
 // Trunk thread, phase E: add the limbs' results of a frame and write them out.
@@ -91,9 +89,9 @@ HSL_HD void pipe_e_trunk(const HslFrameArgs& A, const SM& sm, int s, int64_t fo)
 #pragma unroll
   for (int l = 0; l < NF; l++) {
     const double* D = sm.dstate + (l * HSL_DSTATE) * FB + s;
-    work += D[24 * FB];
-    cfz = fmin(cfz, D[25 * FB]);
-    mu = fmax(mu, D[26 * FB]);
+    work += D[12 * FB];
+    cfz = fmin(cfz, D[13 * FB]);
+    mu = fmax(mu, D[14 * FB]);
   }
   if (A.wframe) A.wframe[fo] = work;
   if (A.fmin_cfz) A.fmin_cfz[fo] = cfz;
