@@ -117,6 +117,19 @@ HSL_HD void hsl_sincos_0_pi(double x, double* sn, double* cs) {
   *cs = k1 ? -sr : (k2 ? -cr : cr);
 }
 
+// sin and cos for |x| <= pi (turn angles of curved gaits); larger arguments take the library routine.
+HSL_HD void hsl_sincos_pm_pi(double x, double* sn, double* cs) {
+  const double ax = fabs(x);
+  if (ax <= 3.2) {
+    double s, c;
+    hsl_sincos_0_pi(ax, &s, &c);
+    *sn = (x < 0) ? -s : s;
+    *cs = c;
+  } else {
+    sincos(x, sn, cs);
+  }
+}
+
 // Angle in (-pi, pi) of the unit vector (cd, sd) = (cos D, sin D):  D = 2 atan(sd / (1 + cd)).
 // Used for the wrapped joint-angle difference over two frames (periodic.cpp:271-278), which is small, so the
 // half-angle tangent t is small and the Taylor series of atan (coefficients +-1/(2k+1), exact) converges fast.

@@ -123,7 +123,7 @@ HSL_HD void wrap_pm_pi(double& a) {  // visualization.cpp:73-79
 struct HslCandView {
   double R0[9], tp0[3], eul[3];
   double period, step_length, step_height, v, t_step, curvature, max_radius;
-  double pos0[3], ts, xs;  // of the thread's limb (unused by the trunk)
+  double pos0[3], ts, xs, turn_r, turn_sa, turn_ca;  // of the thread's limb (unused by the trunk)
 };
 HSL_HD void load_cand(const HslCand& c, int limb, HslCandView& o) {
 #pragma unroll
@@ -136,12 +136,17 @@ HSL_HD void load_cand(const HslCand& c, int limb, HslCandView& o) {
 #pragma unroll
     for (int k = 0; k < 3; k++) o.pos0[k] = c.pos0[limb][k];
     o.ts = c.ts[limb]; o.xs = c.xs[limb];
+    o.turn_r = c.turn_r[limb]; o.turn_sa = c.turn_sa[limb]; o.turn_ca = c.turn_ca[limb];
   }
 }
 
-// Torso joint values (position + Euler angles) at time t: pergensetup::turn_torso, pergen.cpp:386-397.
-// Returns true when the orientation is unchanged from the candidate's (straight walking).
-HSL_HD bool torso_values(const HslCandView& cd, double t, double* qt, double* eul) {
+// Torso pose at time t: pergensetup::turn_torso, pergen.cpp:386-397.  qt = torso joint translation, R0 = torso rotation.
+// Straight walking (no turn): the candidate's rotation, x advanced by t*v.  Curved walking: the reference composes
+// the turn [Rz(psi) | arc] with the candidate orientation (pergen.cpp:187-198, 377-383), extracts Euler angles from
+// the product (visualization.cpp:81-101) and the FK rebuilds the rotation from them; that round trip is the identity
+// away from gimbal lock, so the rotation is taken directly as Rz(psi) * R0 and the Euler angles (asin / atan2) are
+// only evaluated when a trajectory dump asks for them (eul != nullptr).
+HSL_HD void torso_pose(const HslCandView& cd, double t, double* qt, double* R0, double* eul) {
   const double tv = t * cd.v;
   double psi = 0;
   if (cd.curvature != 0) {
@@ -150,24 +155,30 @@ HSL_HD bool torso_values(const HslCandView& cd, double t, double* qt, double* eu
   }
   if (psi == 0) {
     qt[0] = cd.tp0[0] + tv; qt[1] = cd.tp0[1]; qt[2] = cd.tp0[2];
-    eul[0] = cd.eul[0]; eul[1] = cd.eul[1]; eul[2] = cd.eul[2];
-    return true;
+#pragma unroll
+    for (int k = 0; k < 9; k++) R0[k] = cd.R0[k];
+    if (eul) { eul[0] = cd.eul[0]; eul[1] = cd.eul[1]; eul[2] = cd.eul[2]; }
+    return;
   }
-  // curved path: compose the turn with the candidate orientation and re-extract Euler angles
-  // (pergen.cpp:187-198, 377-383; visualization.cpp:81-101)
-  const double rc = 1. / cd.curvature;
+  const double rc = hsl_rcp(cd.curvature);
   double sp, cp;
-  sincos(psi, &sp, &cp);
-  const double tA[3] = {rc * sp, rc * (1 - cp), 0};
-  double RA[9], R1[9];
-  euler_to_R(0, 0, psi, RA);
-  m3_mul(RA, cd.R0, R1);
-  m3_affine(RA, cd.tp0, tA, qt);
-  const double th = -asin(R1[2]), ct = cos(th);
-  eul[0] = atan2(R1[5] / ct, R1[8] / ct);
-  eul[1] = th;
-  eul[2] = atan2(R1[1] / ct, R1[0] / ct);
-  return false;
+  hsl_sincos_pm_pi(psi, &sp, &cp);
+  // [Rz(psi) | (rc sin psi, rc (1 - cos psi), 0)] applied to the candidate pose
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+    R0[3 * j] = cp * cd.R0[3 * j] - sp * cd.R0[3 * j + 1];
+    R0[3 * j + 1] = sp * cd.R0[3 * j] + cp * cd.R0[3 * j + 1];
+    R0[3 * j + 2] = cd.R0[3 * j + 2];
+  }
+  qt[0] = cp * cd.tp0[0] - sp * cd.tp0[1] + rc * sp;
+  qt[1] = sp * cd.tp0[0] + cp * cd.tp0[1] + rc * (1 - cp);
+  qt[2] = cd.tp0[2];
+  if (eul) {
+    const double th = -asin(R0[2]), ct = cos(th);
+    eul[0] = atan2(R0[5] / ct, R0[8] / ct);
+    eul[1] = th;
+    eul[2] = atan2(R0[1] / ct, R0[0] / ct);
+  }
 }
 // Torso body frame from its joint values: model.cpp:183-195 with the free joint (model.cpp:40-48).
 HSL_HD void torso_frame(const HslModelPod& M, const double* qt, const double* R0, double* t0) {
@@ -190,15 +201,16 @@ HSL_HD void foot_target(const HslCandView& cd, double t, double* p) {
   double dy = 0;
   const double dz = sn * sn * cd.step_height;
   if (cd.curvature != 0) {
+    // arc about the turning centre (pergen.cpp:160-183); r and the polar angle alpha of pos0 are per-candidate
+    // constants (setup_candidate), so sin/cos(alpha - beta/2) come from one sincos of the small angle beta/2
     const int s = (cd.curvature > 0) ? 1 : -1;
-    const double rc = 1. / cd.curvature, rx = cd.pos0[0], ry = cd.pos0[1] - rc;
-    const double r = sqrt(rx * rx + ry * ry);
-    const double alpha = atan2(ry, rx), beta = -s * dx / cd.max_radius, gamma = alpha - beta / 2;
-    const double sb = 2 * sin(beta / 2);
-    double sg, cg;
-    sincos(gamma, &sg, &cg);
-    dx = r * sg * sb;
-    dy += -r * cg * sb;
+    const double hb = -s * dx / cd.max_radius / 2;
+    double shb, chb;
+    hsl_sincos_pm_pi(hb, &shb, &chb);
+    const double sg = cd.turn_sa * chb - cd.turn_ca * shb, cg = cd.turn_ca * chb + cd.turn_sa * shb;
+    const double sb = 2 * shb;
+    dx = cd.turn_r * sg * sb;
+    dy += -cd.turn_r * cg * sb;
   }
   p[0] = dx + cd.pos0[0];
   p[1] = dy + cd.pos0[1];
@@ -401,12 +413,7 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     HslCandView cd;
     load_cand(A.cand[sl.c], limb, cd);
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
-    if (torso_values(cd, t, qt, eul)) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) R0[k] = cd.R0[k];
-    } else {
-      euler_to_R(eul[0], eul[1], eul[2], R0);
-    }
+    torso_pose(cd, t, qt, R0, (DUMP && A.q_out != nullptr) ? eul : nullptr);
     torso_frame(M, qt, R0, t0);
     // foot target into the hip joint frame (lik.cpp:341-347), then the closed-form solver
     double p[3], Rh[9], th[3], oj[3], d[3], pl[3];
@@ -480,12 +487,7 @@ HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM&
     HslCandView cd;
     load_cand(A.cand[sl.c], -1, cd);
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
-    if (torso_values(cd, t, qt, eul)) {
-#pragma unroll
-      for (int k = 0; k < 9; k++) st.R0[k] = cd.R0[k];
-    } else {
-      euler_to_R(eul[0], eul[1], eul[2], st.R0);
-    }
+    torso_pose(cd, t, qt, st.R0, nullptr);
   } else {
     const double* qrow = A.traj + (sl.c * (A.n_t + 5) + sl.i) * M.config_dim;
 #pragma unroll
@@ -1045,13 +1047,22 @@ HSL_HD void setup_candidate(const HslModelPod& M, const double* p, int n_t, HslC
     const int k = L.pg_index, grp = k / jmax, j = k % jmax;
     cd.ts[i] = j * (1. / 2 - cd.t_step) / z + double(grp) / 2;
     cd.xs[i] = cd.ts[i] + cd.t_step / 2 - 1. / 2;
+    cd.turn_r[i] = 0; cd.turn_sa[i] = 0; cd.turn_ca[i] = 1;
     if (cd.curvature != 0) {
       const double dy = hp[1] - 1. / cd.curvature;
       const double rad = sqrt(hp[0] * hp[0] + dy * dy + M.rcap * M.rcap);
       if (rad > cd.max_radius) cd.max_radius = rad;
+      // polar coordinates of the default foot position about the turning centre (0, 1/curvature)
+      const double rr = sqrt(hp[0] * hp[0] + dy * dy);
+      cd.turn_r[i] = rr;
+      cd.turn_sa[i] = (rr > 0) ? dy / rr : 0.0;
+      cd.turn_ca[i] = (rr > 0) ? hp[0] / rr : 1.0;
     }
   }
-  for (int i = n; i < HSL_MAX_LIMBS; i++) { cd.pos0[i][0] = cd.pos0[i][1] = cd.pos0[i][2] = 0; cd.ts[i] = cd.xs[i] = 0; }
+  for (int i = n; i < HSL_MAX_LIMBS; i++) {
+    cd.pos0[i][0] = cd.pos0[i][1] = cd.pos0[i][2] = 0; cd.ts[i] = cd.xs[i] = 0;
+    cd.turn_r[i] = 0; cd.turn_sa[i] = 0; cd.turn_ca[i] = 1;
+  }
   if (ttab) {
     double t = 0;
     for (int i = 0; i < n_t + 4; i++) { ttab[i] = t; t += cd.dt; }

@@ -75,6 +75,8 @@ typedef struct HslCand {
   double period, step_length, step_height, v, t_step, curvature, max_radius, dt, hh;  // hh = 1/(2 dt)
   double pos0[HSL_MAX_LIMBS][3];  // default foot positions, LIK order
   double ts[HSL_MAX_LIMBS], xs[HSL_MAX_LIMBS];  // lift-off tables, LIK order
+  double turn_r[HSL_MAX_LIMBS], turn_sa[HSL_MAX_LIMBS], turn_ca[HSL_MAX_LIMBS];  // curved gaits: radius and sin/cos of the
+                                                                               // polar angle of pos0 about the turning centre
   int32_t status, pad;
 } HslCand;
 

@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--candidates", type=int, default=4096)
     ap.add_argument("--frames", type=int, default=256)
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--curved", action="store_true", help="BASELINE config 2, second batch: curvature U[-.1,.1], lateral foot shift U[0,.3]")
     ap.add_argument("--variants", default="32:128,64:128,64:1,32:1")
     args = ap.parse_args()
     import torch
@@ -30,6 +31,9 @@ def main():
         p[:, 12] = np.random.default_rng(2).uniform(0.3, 0.5, p.shape[0])
     if args.model == "myant":
         p[:, 2] = -0.07
+    if args.curved:
+        rc = np.random.default_rng(3)
+        p[:, 10] = rc.uniform(-0.1, 0.1, p.shape[0]); p[:, 11] = 0; p[:, 12] = rc.uniform(0, 0.3, p.shape[0])
     st = m.eval_gaits(p, 20)["status"]
     p = np.ascontiguousarray(p[st == 0][:args.candidates])
     n = p.shape[0]
