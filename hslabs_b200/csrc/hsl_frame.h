@@ -1,4 +1,4 @@
-// Per-thread frame math of the fused gait-evaluation kernel (host + device).
+// Per-thread frame math of the gait-evaluation kernels (host + device).
 //
 // One thread owns one (frame, role) pair: role 0..NF-1 is a limb (its three
 // hinge bodies), role NF is the trunk (torso + jointless bodies).  The work of
@@ -6,32 +6,37 @@
 // function below so that hsl_kernels.cu (device) and tests/hostcheck (a serial
 // CPU emulation used to validate the very same code without a GPU) share it.
 //
-//   phase A  gait target + closed-form IK + FK of the role's bodies   (a2,a3,a5,a6)
-//            -> publish COM positions, u*sin(theta) vectors, joint angles
+//   phase A  gait target + closed-form IK + FK of the role's bodies     (a2,a3,a5,a6)
+//            -> publish COM positions, u*sin(theta) vectors, cos/sin of the joint angles
 //   ---- barrier ----
-//   phase B  5-point finite differences from the neighbour frames       (a7)
-//            recursive Newton-Euler pass up the limb                    (a8,a9)
-//            per-contact 3x3 level-1 block                              (a10,a11)
+//   phase B  second differences over the +-2 neighbour frames, joint rates (a7)
+//            recursive Newton-Euler pass up the limb                      (a8,a9)
+//            per-contact 3x3 level-1 block                                (a10,a11)
 //            -> publish limb wrench + contact block
 //   ---- barrier ----
-//   phase C  (trunk) level-0 6x6 Schur system over the contacts         (a11)
+//   phase C  (trunk) level-0 6x6 Schur system over the contacts           (a11)
 //            -> publish the multiplier
 //   ---- barrier ----
-//   phase D  contact force, motor torques, positive work of the limb    (a12-a14)
+//   phase D  contact force, motor torques, positive power of the limb     (a12-a14)
 //   ---- barrier ----
-//   phase E  (trunk) per-frame work and contact statistics
+//   phase E  (trunk) per-frame power and contact statistics -> global memory
 //
 // References (file:line in /root/reference): pergen.cpp:62-94,160-198,225-239,
 // 386-397; lik.cpp:151-223,316-347; model.cpp:37-62,183-201; dynrec.cpp:134-155,
 // 175-224,227-344; ftsolver.cpp:78-146,185-246; periodic.cpp:261-357.
-// The reference builds the 6n x 6n force-torque matrix B and factorises it
-// twice per frame with a sparse QR; because the bodies form a tree, B^-1 f is
-// the backward Newton-Euler recursion, and the null space added by the contact
-// columns is {dF_j = -lambda_c, dT_j = -(fpos_c - jpos_j) x lambda_c for j on the
-// chain foot -> root}.  With both torso penalties on, level 0 is "torso wrench
-// = 0" (6 equations in the contact forces) and the level-1 Hessian is block
-// diagonal 3x3 per contact, so the lexicographic least-squares solution is a
-// 6x6 symmetric solve plus one 3x3 solve per contact.
+//
+// What replaces the reference's linear algebra.  The reference builds the
+// 6n x 6n force-torque matrix B and factorises it twice per frame with a sparse
+// QR.  Because the bodies form a tree, B^-1 f is the backward Newton-Euler
+// recursion, and the null space added by the contact columns is
+// {dF_j = -lambda_c, dT_j = -(fpos_c - jpos_j) x lambda_c for j on the chain
+// foot -> root}.  With both torso penalties on, level 0 is "torso joint force = 0
+// and torso joint torque about the torso COM = 0" (the root's torque row of B has
+// no (jpos - pos) x F term, dynrec.cpp:282-287) -- 6 equations in the contact
+// forces -- and the level-1 Hessian is block diagonal 3x3 per contact, so the
+// lexicographic least-squares solution is one 6x6 symmetric solve per frame plus
+// one 3x3 inverse per contact.  tests/test_hostcheck_parity.py checks this code
+// against the reference-shaped algorithm of oracle/ to round-off.
 #pragma once
 #include <math.h>
 #include <stdint.h>
