@@ -27,7 +27,10 @@ def orc():
 
 @pytest.fixture(scope="session")
 def hsl():
+    """The product package, with its CUDA library built (nvcc cross-compiles without a GPU)."""
     import hslabs_b200
+    from hslabs_b200 import build
+    build.build()
     return hslabs_b200
 
 
