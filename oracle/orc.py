@@ -11,6 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "liborc.so")
+LIBQ = os.path.join(HERE, "_build", "liborcq.so")
 NPARAM = 13
 _lib = None
 
@@ -39,6 +40,22 @@ def lib():
     return _lib
 
 
+_libq = None
+
+
+def libq():
+    """Quad-precision build of the same oracle headers (orc_capi_quad.cpp); conditioning yardstick only."""
+    global _libq
+    if _libq is None:
+        if not os.path.exists(LIBQ):
+            build(force=True)
+        _libq = C.CDLL(LIBQ)
+        _libq.orcq_model_load.restype = C.c_void_p
+        _libq.orcq_model_load.argtypes = [C.c_char_p]
+        _libq.orcq_model_free.argtypes = [C.c_void_p]
+    return _libq
+
+
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -60,6 +77,7 @@ def load_preset(path, pid):
 
 class Model:
     def __init__(self, xml_path):
+        self.path = xml_path
         self.h = C.c_void_p(lib().orc_model_load(xml_path.encode()))
         if not self.h:
             raise RuntimeError("oracle could not load " + xml_path)
@@ -128,6 +146,21 @@ class Model:
         if detail:
             res.update(traj=traj, x=x, z=z, tau=tau)
         return res
+
+    def measure_cot_quad(self, params, n_t):
+        """measure_cot evaluated in __float128 (results rounded to double); always returns the detail arrays."""
+        params = np.ascontiguousarray(params, np.float64)
+        hq = C.c_void_p(libq().orcq_model_load(self.path.encode()))
+        if not hq:
+            raise RuntimeError("quad oracle could not load %s" % self.path)
+        out = np.zeros(4)
+        traj = np.zeros((n_t + 5, self.config_dim)); x = np.zeros((n_t, 6 * self.n))
+        z = np.zeros((n_t, 3 * self.nf)); tau = np.zeros((n_t, self.nmj))
+        try:
+            rc = libq().orcq_measure_cot(hq, _p(params), C.c_int(n_t), _p(out), _p(traj), _p(x), _p(z), _p(tau))
+        finally:
+            libq().orcq_model_free(hq)
+        return dict(status=rc, cot=out[0], work=out[1], min_cfz=out[2], max_mu=out[3], traj=traj, x=x, z=z, tau=tau)
 
     def frame_fields(self, params, n_t):
         params = np.ascontiguousarray(params, np.float64)

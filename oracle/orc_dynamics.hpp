@@ -28,7 +28,7 @@ struct FrameRecord {  // dynrecord
   int ncontacts() const { int s = 0; for (int i = 0; i < nf; i++) s += contacts[i]; return s; }
 };
 
-inline void central_diff(std::vector<V4>& der, const std::vector<V4>& prev, const std::vector<V4>& next, double dt) {
+inline void central_diff(std::vector<V4>& der, const std::vector<V4>& prev, const std::vector<V4>& next, real dt) {
   for (size_t i = 0; i < der.size(); i++) {  // dynrec.cpp:192-203
     der[i] = next[i];
     der[i].sub4(prev[i]);
@@ -58,10 +58,10 @@ class GaitEvaluator {  // periodic + forcetorquesolver
   int n, nf, nmj, n_t, traj_size, config_dim;
   std::vector<int> parentis, footis, hinge_ids;
   std::vector<char> is_foot;
-  std::vector<double> masses;
+  std::vector<real> masses;
   std::vector<M4> inertia;
-  double dt, rcap, min_cfz, max_mu;
-  std::vector<std::vector<double> > traj, vel_traj, torques;
+  real dt, rcap, min_cfz, max_mu;
+  std::vector<std::vector<real> > traj, vel_traj, torques;
   std::vector<FrameRecord> recs;
   bool pen_force, pen_torque, mask_set;
   Vec fts, jz;  // last solution, last joint z axes
@@ -80,15 +80,15 @@ class GaitEvaluator {  // periodic + forcetorquesolver
       if (m->b[i].jk == J_HINGE) hinge_ids.push_back(i);
     }
   }
-  double total_mass() const { double s = 0; for (int i = 0; i < n; i++) s += masses[i]; return s; }
+  real total_mass() const { real s = 0; for (int i = 0; i < n; i++) s += masses[i]; return s; }
 
   // periodic.cpp:77-96 ; false where the reference would exit(1) in IK
   bool record_trajectory(GaitSetup* g, int n_t_) {
     n_t = n_t_; traj_size = n_t + 5; config_dim = g->config_dim();
-    double t = 0;
+    real t = 0;
     dt = g->period() / n_t;
-    std::vector<double> rec(config_dim);
-    traj.assign(traj_size, std::vector<double>(config_dim));
+    std::vector<real> rec(config_dim);
+    traj.assign(traj_size, std::vector<real>(config_dim));
     for (int i = 0; i < traj_size; i++) {
       g->set_rec(&rec[0], t);
       if (!model->set_jvalues_with_lik(&rec[0])) return false;
@@ -98,9 +98,9 @@ class GaitEvaluator {  // periodic + forcetorquesolver
     rcap = model->rcap;
     return true;
   }
-  void set_trajectory(const double* q, int n_t_, double dt_) {  // externally supplied trajectory (L2 entry tests)
+  void set_trajectory(const real* q, int n_t_, real dt_) {  // externally supplied trajectory (L2 entry tests)
     n_t = n_t_; traj_size = n_t + 5; config_dim = model->config_dim(); dt = dt_; rcap = model->rcap;
-    traj.assign(traj_size, std::vector<double>(config_dim));
+    traj.assign(traj_size, std::vector<real>(config_dim));
     for (int i = 0; i < traj_size; i++) for (int j = 0; j < config_dim; j++) traj[i][j] = q[(size_t)i * config_dim + j];
   }
   void compute_dynrecs() {  // periodic.cpp:149-160 + dynrec.cpp:31-93, 134-155
@@ -176,7 +176,7 @@ class GaitEvaluator {  // periodic + forcetorquesolver
     z.assign(3 * nf, 0.0);  // z = -N_cont y (ftsolver.cpp:90-92, 276-284)
     for (int i = 0; i < nf; i++)
       for (int j = 0; j < 3; j++) {
-        double s = 0;
+        real s = 0;
         for (int c = 0; c < delm; c++) s += N(3 * footis[i] + j, c) * y[c];
         z[3 * i + j] = -s;
       }
@@ -186,25 +186,25 @@ class GaitEvaluator {  // periodic + forcetorquesolver
     return true;
   }
   // periodic.cpp:328-343
-  void motor_torques(double* out) const {
+  void motor_torques(real* out) const {
     for (size_t h = 0; h < hinge_ids.size(); h++) {
       int k = 3 * hinge_ids[h], k1 = 3 * n + k;
-      double s = 0;
+      real s = 0;
       for (int j = 0; j < 3; j++) s += jz[k + j] * fts[k1 + j];
       out[h] = s;
     }
   }
   // periodic.cpp:377-391 ; optional per-frame dumps (x [n_t][6n], z [n_t][3nf]) in solve order i = 2..n_t+1
-  bool compute_torques_over_period(double* x_dump = 0, double* z_dump = 0) {
-    torques.assign(n_t, std::vector<double>(nmj));
+  bool compute_torques_over_period(real* x_dump = 0, real* z_dump = 0) {
+    torques.assign(n_t, std::vector<real>(nmj));
     min_cfz = 1e10; max_mu = -1e10;
     for (int i = 2; i < n_t + 2; i++) {
       Vec x, y;
       if (!solve_forcetorques(recs[i], x, y)) return false;
       for (int fi = 0; fi < nf; fi++) {  // periodic.cpp:347-357
-        double cx = y[3 * fi], cy = y[3 * fi + 1], cz = y[3 * fi + 2];
+        real cx = y[3 * fi], cy = y[3 * fi + 1], cz = y[3 * fi + 2];
         if (cz < min_cfz) min_cfz = cz;
-        double mu = std::sqrt(cx * cx + cy * cy) / cz;
+        real mu = orc::m_sqrt(cx * cx + cy * cy) / cz;
         if (mu > max_mu) max_mu = mu;
       }
       motor_torques(&torques[i % n_t][0]);
@@ -214,22 +214,22 @@ class GaitEvaluator {  // periodic + forcetorquesolver
     return true;
   }
   void compute_vel_traj() {  // periodic.cpp:261-282
-    vel_traj.assign(traj_size, std::vector<double>(config_dim, 0.0));
+    vel_traj.assign(traj_size, std::vector<real>(config_dim, 0.0));
     for (int i = 2; i < traj_size; i++)
       for (int j = 0; j < config_dim; j++) {
-        double d = traj[i][j] - traj[i - 2][j];
+        real d = traj[i][j] - traj[i - 2][j];
         if (d > M_PI) d -= 2 * M_PI; else if (d < -M_PI) d += 2 * M_PI;
         vel_traj[i - 1][j] = d / (2 * dt);
       }
   }
-  bool work_over_period(double& work, double* x_dump = 0, double* z_dump = 0) {  // periodic.cpp:285-307
+  bool work_over_period(real& work, real* x_dump = 0, real* z_dump = 0) {  // periodic.cpp:285-307
     if (!compute_torques_over_period(x_dump, z_dump)) return false;
     compute_vel_traj();
-    double wp = 0;
+    real wp = 0;
     for (int i = 2; i < n_t + 2; i++) {
-      double wd = 0;
+      real wd = 0;
       for (int j = 0; j < nmj; j++) {
-        double dw = torques[i % n_t][j] * vel_traj[i][6 + j];
+        real dw = torques[i % n_t][j] * vel_traj[i][6 + j];
         dw = (dw > 0) ? dw : 0;
         wd += dw;
       }
@@ -240,7 +240,7 @@ class GaitEvaluator {  // periodic + forcetorquesolver
     return true;
   }
   // ftsolver.cpp:331-378 : contact forces of ALL feet for given motor torques, torso columns zeroed
-  void solve_forces(const FrameRecord& r, const double* tau, double* cf) {
+  void solve_forces(const FrameRecord& r, const real* tau, real* cf) {
     load_jz(r);
     const int m0 = 6 * n, m1 = m0 + 3 * nf;
     Mat B0(m0, m0); Vec f(m0, 0.0);
@@ -325,7 +325,7 @@ class GaitEvaluator {  // periodic + forcetorquesolver
     Vec ntx0 = matvec(N0t, x0), ntx1 = matvec(N1t, x1);
     Mat ntn0 = matmul(N0t, N0), ntn1 = matmul(N1t, N1);
     if (K == 0) { y.clear(); return true; }
-    double rel_error;
+    real rel_error;
     int rank0 = K, guard = 0;
     do {
       FullPivLU lu(ntn0);
@@ -360,9 +360,9 @@ class GaitEvaluator {  // periodic + forcetorquesolver
 };
 
 // modelplayer::prepare_per_traj_dyn + measure_cot (player.cpp:259-285)
-struct CotResult { double cot, work, min_cfz, max_mu; int status; };
-inline CotResult measure_cot(Model& model, GaitSetup& g, int n_t, double* traj_out = 0, double* x_dump = 0,
-                             double* z_dump = 0, double* tau_dump = 0) {
+struct CotResult { real cot, work, min_cfz, max_mu; int status; };
+inline CotResult measure_cot(Model& model, GaitSetup& g, int n_t, real* traj_out = 0, real* x_dump = 0,
+                             real* z_dump = 0, real* tau_dump = 0) {
   CotResult r; r.cot = r.work = r.min_cfz = r.max_mu = 0; r.status = 0;
   GaitEvaluator ev(&model);
   if (!ev.record_trajectory(&g, n_t)) { r.status = 1; return r; }  // IK target unreachable

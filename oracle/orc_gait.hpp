@@ -15,93 +15,93 @@ namespace orc {
 struct GaitParams {  // pgsconfigparams
   std::string fname;
   V4 orientation[2];
-  double step_duration;
-  double TLh[3];
-  double curvature;
+  real step_duration;
+  real TLh[3];
+  real curvature;
   int shift_type;      // -1 none, 0 lateral, 1 radial
-  double shift_value;
+  real shift_value;
   GaitParams() : step_duration(0), curvature(0), shift_type(-1), shift_value(0) { TLh[0] = TLh[1] = TLh[2] = 0; }
 };
 
 class FootPattern {  // periodicgenerator
  public:
   int n;
-  double t_step;
-  std::vector<double> ts, xs;
-  double period, step_length, step_height;
+  real t_step;
+  std::vector<real> ts, xs;
+  real period, step_length, step_height;
   std::vector<V4> pos0;  // default foot positions, pergen order
-  double step_duration, curvature, max_radius;
+  real step_duration, curvature, max_radius;
 
   explicit FootPattern(int n_) : n(n_), t_step(0), ts(n_), xs(n_), period(0), step_length(0), step_height(0),
                                  step_duration(0), curvature(0), max_radius(0) {
     if (n_ % 2) throw Failure("number of limbs must be even");
   }
-  void set_step_duration(double f) {  // pergen.cpp:30-51
+  void set_step_duration(real f) {  // pergen.cpp:30-51
     if (f < 0 || f > 1) throw Failure("step_duration out of bounds");
     t_step = f * (1. / 2 - 1. / n) + 1. / n;
     for (int i = 0; i < 2; i++) {
       int jmax = n / 2, z = (jmax == 1) ? 1 : jmax - 1;
       for (int j = 0; j < jmax; j++) {
         int k = j + i * jmax;
-        ts[k] = j * (1. / 2 - t_step) / z + double(i) / 2;
+        ts[k] = j * (1. / 2 - t_step) / z + real(i) / 2;
         xs[k] = ts[k] + t_step / 2 - 1. / 2;
       }
     }
     step_duration = f;
   }
   void set_pos0s(const std::vector<V4>& p) { pos0 = p; compute_max_radius(); }
-  void set_curvature(double c) { curvature = c; compute_max_radius(); }
-  double step_frac(int li, double t) const {  // pergen.cpp:73-78
-    double tl = ts[li];
+  void set_curvature(real c) { curvature = c; compute_max_radius(); }
+  real step_frac(int li, real t) const {  // pergen.cpp:73-78
+    real tl = ts[li];
     if (t < tl) return 0;
     else if (t < tl + t_step) return (t - tl) / t_step;
     else return 1;
   }
-  void limb_positions(double time, std::vector<V4>& out) const {  // pergen.cpp:82-94
-    double t = time / period;
+  void limb_positions(real time, std::vector<V4>& out) const {  // pergen.cpp:82-94
+    real t = time / period;
     int t_int = int(t);
-    double t_frac = t - t_int;
+    real t_frac = t - t_int;
     for (int i = 0; i < n; i++) {
-      double sf = step_frac(i, t_frac);
-      double delx = (t_int + xs[i] + (1 - std::cos(M_PI * sf)) / 2) * step_length;
-      double a = std::sin(M_PI * sf);
-      double delz = a * a * step_height;
+      real sf = step_frac(i, t_frac);
+      real delx = (t_int + xs[i] + (1 - orc::m_cos(M_PI * sf)) / 2) * step_length;
+      real a = orc::m_sin(M_PI * sf);
+      real delz = a * a * step_height;
       turn_position(pos0[i], V4(delx, 0, delz), out[i]);
     }
   }
   void turn_position(const V4& p0, const V4& del, V4& pos) const {  // pergen.cpp:160-183
-    double dx = del.v[0], dy = del.v[1], dz = del.v[2];
+    real dx = del.v[0], dy = del.v[1], dz = del.v[2];
     if (curvature != 0) {
       int s = (curvature > 0) ? 1 : -1;
-      double x0 = p0.v[0], y0 = p0.v[1];
-      double rc = 1. / curvature, rx = x0, ry = y0 - rc;
-      double r = std::sqrt(rx * rx + ry * ry);
-      double alpha = std::atan2(ry, rx), beta = -s * dx / max_radius, gamma = alpha - beta / 2;
-      double sb = 2 * std::sin(beta / 2);
-      dx = r * std::sin(gamma) * sb;
-      dy += -r * std::cos(gamma) * sb;
+      real x0 = p0.v[0], y0 = p0.v[1];
+      real rc = 1. / curvature, rx = x0, ry = y0 - rc;
+      real r = orc::m_sqrt(rx * rx + ry * ry);
+      real alpha = orc::m_atan2(ry, rx), beta = -s * dx / max_radius, gamma = alpha - beta / 2;
+      real sb = 2 * orc::m_sin(beta / 2);
+      dx = r * orc::m_sin(gamma) * sb;
+      dy += -r * orc::m_cos(gamma) * sb;
     }
     V4 d(dx, dy, dz);
     d.add3(p0);
     pos = d;
   }
-  void turn_orientation(double dx, V4 o[2]) const {  // pergen.cpp:187-198
+  void turn_orientation(real dx, V4 o[2]) const {  // pergen.cpp:187-198
     if (curvature != 0) {
       int s = (curvature > 0) ? 1 : -1;
-      double psi = s * dx / max_radius, rc = 1. / curvature;
-      o[0] = V4(rc * std::sin(psi), rc * (1 - std::cos(psi)), 0);
+      real psi = s * dx / max_radius, rc = 1. / curvature;
+      o[0] = V4(rc * orc::m_sin(psi), rc * (1 - orc::m_cos(psi)), 0);
       o[1] = V4(0, 0, psi);
     } else { o[0] = V4(dx, 0, 0); o[1] = V4(0, 0, 0); }
   }
  private:
   void compute_max_radius() {  // pergen.cpp:144-154
     if (curvature == 0) return;
-    double c[3] = {0, 1. / curvature, 0};
+    real c[3] = {0, 1. / curvature, 0};
     max_radius = 0;
     for (size_t i = 0; i < pos0.size(); i++) {
-      double s = 0;
-      for (int k = 0; k < 3; k++) { double d = pos0[i].v[k] - c[k]; s += d * d; }
-      double rad = std::sqrt(s);
+      real s = 0;
+      for (int k = 0; k < 3; k++) { real d = pos0[i].v[k] - c[k]; s += d * d; }
+      real rad = orc::m_sqrt(s);
       if (rad > max_radius) max_radius = rad;
     }
   }
@@ -113,11 +113,11 @@ class GaitSetup {  // pergensetup
   FootPattern pattern;
   std::vector<int> lik2pg;  // LIK limb index -> pergen index (pergen.cpp:243-262)
   std::vector<V4> limb_poss;
-  double v;
+  real v;
   V4 torso_pos0, euler;
   M4 rec_transform;
   bool rec_transform_flag;
-  int shift_type; double shift_value;
+  int shift_type; real shift_value;
 
   explicit GaitSetup(int n_) : n(n_), pattern(n_), limb_poss(n_), v(0), rec_transform_flag(false), shift_type(-1), shift_value(0) {
     static const int m4[] = {0, 3, 1, 2}, m6[] = {0, 3, 4, 1, 2, 5};
@@ -126,9 +126,9 @@ class GaitSetup {  // pergensetup
     else throw Failure("likpergen map undefined for this limb count");
   }
   int config_dim() const { return 6 + 3 * n; }
-  double period() const { return pattern.period; }
-  void set_TLh(double T, double L, double h) { pattern.period = T; pattern.step_length = L; pattern.step_height = h; v = L / T; }
-  void set_limb_pos0(int lik_i, const V4& pos, double rcap) { V4 p(pos); p.v[2] = rcap; limb_poss[lik2pg[lik_i]] = p; }  // pergen.cpp:268-275
+  real period() const { return pattern.period; }
+  void set_TLh(real T, real L, real h) { pattern.period = T; pattern.step_length = L; pattern.step_height = h; v = L / T; }
+  void set_limb_pos0(int lik_i, const V4& pos, real rcap) { V4 p(pos); p.v[2] = rcap; limb_poss[lik2pg[lik_i]] = p; }  // pergen.cpp:268-275
   void commit_pos0s() { pattern.set_pos0s(limb_poss); }
   void set_rec_rotation(const V4& eas) {  // pergen.cpp:309-322
     V4 o[2] = {rec_transform.translation_part(), eas};
@@ -136,7 +136,7 @@ class GaitSetup {  // pergensetup
     rec_transform_flag = true;
   }
   // pergen.cpp:225-239
-  void set_rec(double* rec, double t) {
+  void set_rec(real* rec, real t) {
     V4 o[2] = {torso_pos0, euler};
     turn_torso(t, o);
     for (int k = 0; k < 3; k++) { rec[k] = o[0].v[k]; rec[3 + k] = o[1].v[k]; }
@@ -158,14 +158,14 @@ class GaitSetup {  // pergensetup
     o[0] = A1.translation_part();
     euler_from_m4(A1, o[1].v);
   }
-  void turn_torso(double t, V4 o[2]) const {  // pergen.cpp:386-397
-    double tv = t * v;
+  void turn_torso(real t, V4 o[2]) const {  // pergen.cpp:386-397
+    real tv = t * v;
     V4 to[2];
     pattern.turn_orientation(tv, to);
     if (to[1].v[2] == 0) o[0].v[0] += tv;
     else { M4 A = m4_from_orientation(to); transform_orientation(A, o); }
   }
-  void transform_rec(double* rec) const {  // pergen.cpp:325-337
+  void transform_rec(real* rec) const {  // pergen.cpp:325-337
     V4 o[2]; o[0].set3(rec); o[1].set3(rec + 3);
     transform_orientation(rec_transform, o);
     for (int k = 0; k < 3; k++) { rec[k] = o[0].v[k]; rec[3 + k] = o[1].v[k]; }
@@ -184,15 +184,15 @@ inline void setup_gait(GaitSetup& g, Model& model, const GaitParams& p) {
   model.orient_torso(p.orientation);
   g.pattern.set_step_duration(p.step_duration);
   if (g.n != model.nlimbs()) throw Failure("limb count mismatch");
-  double rcap = model.rcap;
-  V4 lat_shift; double rad_shift = 0;
+  real rcap = model.rcap;
+  V4 lat_shift; real rad_shift = 0;
   if (p.shift_type == 0) lat_shift = model.b[0].A_ground.apply(V4(0, p.shift_value, 0));  // includes the torso translation
   else if (p.shift_type == 1) rad_shift = p.shift_value;
   for (int i = 0; i < g.n; i++) {
     V4 pos = model.limb_hip_pos(i);
     if (p.shift_type == 0) { V4 d = lat_shift; if (i % 2) d.scale3(-1); pos.add3(d); }
     else if (p.shift_type == 1) {
-      double x = pos.v[0], y = pos.v[1], f = rad_shift / std::sqrt(x * x + y * y);
+      real x = pos.v[0], y = pos.v[1], f = rad_shift / orc::m_sqrt(x * x + y * y);
       pos.add3(V4(x * f, y * f, 0));
     }
     g.set_limb_pos0(i, pos, rcap);
@@ -207,10 +207,10 @@ inline void setup_gait(GaitSetup& g, Model& model, const GaitParams& p) {
 class GaitSweeper {
  public:
   const GaitSetup* g0; Model* model; GaitSetup* g;
-  int parami, n_val, vali; double val0, delval, val;
+  int parami, n_val, vali; real val0, delval, val;
   GaitSweeper(const GaitSetup* g0_, Model* m) : g0(g0_), model(m), g(0), parami(-1), n_val(0), vali(0), val0(0), delval(0), val(0) {}
   ~GaitSweeper() { delete g; }
-  void sweep(const std::string& name, double v0, double v1, int nv) {
+  void sweep(const std::string& name, real v0, real v1, int nv) {
     val0 = v0; n_val = nv; delval = (v1 - v0) / nv; vali = 0;
     static const char* names[] = {"step_duration", "period", "step_length", "step_height"};
     parami = -1;
@@ -233,18 +233,18 @@ class GaitSweeper {
 // player.cpp:230-244 + 170-208: preset row "id key value ..." -> GaitParams
 inline bool parse_preset_row(const std::string& row, GaitParams& p) {
   std::stringstream ss(row);
-  std::string key; double period = 0, sl = 0, sh = 0;
+  std::string key; real period = 0, sl = 0, sh = 0;
   while (ss >> key) {
     if (key == "xml_file") ss >> p.fname;
-    else if (key == "torso_pos") { double x, y, z; ss >> x >> y >> z; p.orientation[0] = V4(x, y, z); }
-    else if (key == "torso_angles") { double x, y, z; ss >> x >> y >> z; p.orientation[1] = V4(x, y, z); }
-    else if (key == "step_duration") ss >> p.step_duration;
-    else if (key == "period") ss >> period;
-    else if (key == "step_length") ss >> sl;
-    else if (key == "step_height") ss >> sh;
-    else if (key == "curvature") ss >> p.curvature;
-    else if (key == "lateral_foot_shift") { p.shift_type = 0; ss >> p.shift_value; }
-    else if (key == "radial_foot_shift") { p.shift_type = 1; ss >> p.shift_value; }
+    else if (key == "torso_pos") { real x = 0, y = 0, z = 0; ss >> RealIn(x) >> RealIn(y) >> RealIn(z); p.orientation[0] = V4(x, y, z); }
+    else if (key == "torso_angles") { real x = 0, y = 0, z = 0; ss >> RealIn(x) >> RealIn(y) >> RealIn(z); p.orientation[1] = V4(x, y, z); }
+    else if (key == "step_duration") ss >> RealIn(p.step_duration);
+    else if (key == "period") ss >> RealIn(period);
+    else if (key == "step_length") ss >> RealIn(sl);
+    else if (key == "step_height") ss >> RealIn(sh);
+    else if (key == "curvature") ss >> RealIn(p.curvature);
+    else if (key == "lateral_foot_shift") { p.shift_type = 0; ss >> RealIn(p.shift_value); }
+    else if (key == "radial_foot_shift") { p.shift_type = 1; ss >> RealIn(p.shift_value); }
     else throw Failure("unknown key " + key);
   }
   p.TLh[0] = period; p.TLh[1] = sl; p.TLh[2] = sh;

@@ -14,6 +14,7 @@
 // including their default rank thresholds (epsilon * diagonalSize), because
 // the reference's rank decisions go through them.
 #pragma once
+#include "orc_real.hpp"
 #include <cmath>
 #include <cstddef>
 #include <limits>
@@ -21,15 +22,15 @@
 
 namespace orc {
 
-typedef std::vector<double> Vec;
+typedef std::vector<real> Vec;
 
 struct Mat {  // column-major dense matrix
   int r, c;
-  std::vector<double> d;
+  std::vector<real> d;
   Mat() : r(0), c(0) {}
   Mat(int r_, int c_) : r(r_), c(c_), d((size_t)r_ * c_, 0.0) {}
-  double& operator()(int i, int j) { return d[(size_t)j * r + i]; }
-  double operator()(int i, int j) const { return d[(size_t)j * r + i]; }
+  real& operator()(int i, int j) { return d[(size_t)j * r + i]; }
+  real operator()(int i, int j) const { return d[(size_t)j * r + i]; }
 };
 
 inline Mat transpose(const Mat& A) {
@@ -42,7 +43,7 @@ inline Mat matmul(const Mat& A, const Mat& B) {
   Mat C(A.r, B.c);
   for (int j = 0; j < B.c; j++)
     for (int k = 0; k < A.c; k++) {
-      double b = B(k, j);
+      real b = B(k, j);
       if (b == 0) continue;
       for (int i = 0; i < A.r; i++) C(i, j) += A(i, k) * b;
     }
@@ -54,10 +55,10 @@ inline Vec matvec(const Mat& A, const Vec& x) {
     for (int i = 0; i < A.r; i++) y[i] += A(i, k) * x[k];
   return y;
 }
-inline double norm2(const Vec& v) {
-  double s = 0;
+inline real norm2(const Vec& v) {
+  real s = 0;
   for (size_t i = 0; i < v.size(); i++) s += v[i] * v[i];
-  return std::sqrt(s);
+  return orc::m_sqrt(s);
 }
 
 // Householder QR of an m x n matrix (m >= n), reflectors kept in place.
@@ -73,7 +74,7 @@ class HouseholderQR {
     const int m = qr.r, n = qr.c;
     for (int j = 0; j < n; j++) perm[j] = j;
     Vec cn(n, 0.0);
-    double maxcn = 0;
+    real maxcn = 0;
     for (int j = 0; j < n; j++) {
       for (int i = 0; i < m; i++) cn[j] += qr(i, j) * qr(i, j);
       if (cn[j] > maxcn) maxcn = cn[j];
@@ -84,9 +85,9 @@ class HouseholderQR {
     for (int k = 0; k < steps; k++) {
       if (pivot) {
         int best = k;
-        double bn = -1;
+        real bn = -1;
         for (int j = k; j < n; j++) {
-          double s = 0;
+          real s = 0;
           for (int i = k; i < m; i++) s += qr(i, j) * qr(i, j);
           if (s > bn) { bn = s; best = j; }
         }
@@ -96,18 +97,18 @@ class HouseholderQR {
           std::swap(perm[k], perm[best]);
         }
       }
-      double s = 0;
+      real s = 0;
       for (int i = k + 1; i < m; i++) s += qr(i, k) * qr(i, k);
-      double a0 = qr(k, k);
+      real a0 = qr(k, k);
       if (s == 0) { beta[k] = 0; continue; }
-      double nrm = std::sqrt(a0 * a0 + s);
-      double alpha = (a0 >= 0) ? -nrm : nrm;
-      double v0 = a0 - alpha;
+      real nrm = orc::m_sqrt(a0 * a0 + s);
+      real alpha = (a0 >= 0) ? -nrm : nrm;
+      real v0 = a0 - alpha;
       for (int i = k + 1; i < m; i++) qr(i, k) /= v0;  // v = [1; essential]
       beta[k] = -v0 / alpha;                            // H = I - beta v v^T
       qr(k, k) = alpha;
       for (int j = k + 1; j < n; j++) {
-        double w = qr(k, j);
+        real w = qr(k, j);
         for (int i = k + 1; i < m; i++) w += qr(i, k) * qr(i, j);
         w *= beta[k];
         qr(k, j) -= w;
@@ -120,7 +121,7 @@ class HouseholderQR {
     const int m = qr.r, steps = qr.c < qr.r ? qr.c : qr.r;
     for (int k = 0; k < steps; k++) {
       if (beta[k] == 0) continue;
-      double w = b[k];
+      real w = b[k];
       for (int i = k + 1; i < m; i++) w += qr(i, k) * b[i];
       w *= beta[k];
       b[k] -= w;
@@ -131,7 +132,7 @@ class HouseholderQR {
     const int m = qr.r, steps = qr.c < qr.r ? qr.c : qr.r;
     for (int k = steps - 1; k >= 0; k--) {
       if (beta[k] == 0) continue;
-      double w = b[k];
+      real w = b[k];
       for (int i = k + 1; i < m; i++) w += qr(i, k) * b[i];
       w *= beta[k];
       b[k] -= w;
@@ -145,7 +146,7 @@ class HouseholderQR {
     const int n = qr.c, rk = rank_;
     Vec y(n, 0.0);
     for (int i = rk - 1; i >= 0; i--) {
-      double s = b[i];
+      real s = b[i];
       for (int j = i + 1; j < rk; j++) s -= qr(i, j) * y[j];
       y[i] = s / qr(i, i);
     }
@@ -167,7 +168,7 @@ class FullPivLU {
   Mat lu;
   std::vector<int> p, q;  // row / column permutations: (P A Q)(i,j) = A(p[i], q[j])
   int nonzero_pivots;
-  double maxpivot, thresh;
+  real maxpivot, thresh;
   explicit FullPivLU(const Mat& A) : lu(A), p(A.r), q(A.c) {
     const int rows = lu.r, cols = lu.c, size = rows < cols ? rows : cols;
     for (int i = 0; i < rows; i++) p[i] = i;
@@ -177,10 +178,10 @@ class FullPivLU {
     thresh = std::numeric_limits<double>::epsilon() * size;
     for (int k = 0; k < size; k++) {
       int br = k, bc = k;
-      double big = -1;
+      real big = -1;
       for (int j = k; j < cols; j++)  // column-major visit order, first maximum wins
         for (int i = k; i < rows; i++) {
-          double a = std::fabs(lu(i, j));
+          real a = orc::m_fabs(lu(i, j));
           if (a > big) { big = a; br = i; bc = j; }
         }
       if (big == 0) { nonzero_pivots = k; break; }
@@ -189,18 +190,18 @@ class FullPivLU {
       if (bc != k) { for (int i = 0; i < rows; i++) std::swap(lu(i, k), lu(i, bc)); std::swap(q[k], q[bc]); }
       for (int i = k + 1; i < rows; i++) lu(i, k) /= lu(k, k);
       for (int j = k + 1; j < cols; j++) {
-        double u = lu(k, j);
+        real u = lu(k, j);
         if (u == 0) continue;
         for (int i = k + 1; i < rows; i++) lu(i, j) -= lu(i, k) * u;
       }
     }
   }
-  double threshold() const { return thresh; }
-  void setThreshold(double t) { thresh = t; }
+  real threshold() const { return thresh; }
+  void setThreshold(real t) { thresh = t; }
   int rank() const {
-    double pt = std::fabs(maxpivot) * thresh;
+    real pt = orc::m_fabs(maxpivot) * thresh;
     int r = 0;
-    for (int i = 0; i < nonzero_pivots; i++) r += (std::fabs(lu(i, i)) > pt);
+    for (int i = 0; i < nonzero_pivots; i++) r += (orc::m_fabs(lu(i, i)) > pt);
     return r;
   }
   // Square systems only (that is all the path uses).
@@ -211,7 +212,7 @@ class FullPivLU {
     for (int j = 0; j < n; j++)  // unit lower
       for (int i = j + 1; i < n; i++) c[i] -= lu(i, j) * c[j];
     for (int i = rk - 1; i >= 0; i--) {
-      double s = c[i];
+      real s = c[i];
       for (int j = i + 1; j < rk; j++) s -= lu(i, j) * c[j];
       c[i] = s / lu(i, i);
     }
@@ -220,10 +221,10 @@ class FullPivLU {
     return x;
   }
   std::vector<int> pivots() const {
-    double pt = std::fabs(maxpivot) * thresh;
+    real pt = orc::m_fabs(maxpivot) * thresh;
     std::vector<int> pv;
     for (int i = 0; i < nonzero_pivots; i++)
-      if (std::fabs(lu(i, i)) > pt) pv.push_back(i);
+      if (orc::m_fabs(lu(i, i)) > pt) pv.push_back(i);
     return pv;
   }
   Mat kernel() const {
@@ -239,7 +240,7 @@ class FullPivLU {
       if (pv[i] != i) for (int r = 0; r < rk; r++) std::swap(m(r, i), m(r, pv[i]));
     for (int k = 0; k < dimker; k++)  // upper-triangular solve on the trailing block
       for (int i = rk - 1; i >= 0; i--) {
-        double s = m(i, rk + k);
+        real s = m(i, rk + k);
         for (int j = i + 1; j < rk; j++) s -= m(i, j) * m(j, rk + k);
         m(i, rk + k) = s / m(i, i);
       }
@@ -267,35 +268,35 @@ inline Vec colpiv_qr_solve(const Mat& A, const Vec& b) {
   Vec cn(cols), hb(size, 0.0);
   for (int j = 0; j < cols; j++) {
     perm[j] = j;
-    double s = 0;
+    real s = 0;
     for (int i = 0; i < rows; i++) s += qr(i, j) * qr(i, j);
-    cn[j] = std::sqrt(s);
+    cn[j] = orc::m_sqrt(s);
   }
-  double mx = 0;
+  real mx = 0;
   for (int j = 0; j < cols; j++) if (cn[j] > mx) mx = cn[j];
-  const double eps = std::numeric_limits<double>::epsilon();
-  double helper = (mx * eps / rows) * (mx * eps / rows);
+  const real eps = std::numeric_limits<double>::epsilon();
+  real helper = (mx * eps / rows) * (mx * eps / rows);
   int nonzero = size;
   for (int k = 0; k < size; k++) {
     int best = k;
-    double bn = -1;
+    real bn = -1;
     for (int j = k; j < cols; j++) {  // recomputed norms (Eigen down-dates; same pivots away from ties)
-      double s = 0;
+      real s = 0;
       for (int i = k; i < rows; i++) s += qr(i, j) * qr(i, j);
       if (s > bn) { bn = s; best = j; }
     }
     if (nonzero == size && bn < helper * (rows - k)) nonzero = k;
     if (best != k) { for (int i = 0; i < rows; i++) std::swap(qr(i, k), qr(i, best)); std::swap(perm[k], perm[best]); }
-    double s = 0;
+    real s = 0;
     for (int i = k + 1; i < rows; i++) s += qr(i, k) * qr(i, k);
-    double a0 = qr(k, k);
+    real a0 = qr(k, k);
     if (s == 0) { hb[k] = 0; continue; }
-    double nrm = std::sqrt(a0 * a0 + s), alpha = (a0 >= 0) ? -nrm : nrm, v0 = a0 - alpha;
+    real nrm = orc::m_sqrt(a0 * a0 + s), alpha = (a0 >= 0) ? -nrm : nrm, v0 = a0 - alpha;
     for (int i = k + 1; i < rows; i++) qr(i, k) /= v0;
     hb[k] = -v0 / alpha;
     qr(k, k) = alpha;
     for (int j = k + 1; j < cols; j++) {
-      double w = qr(k, j);
+      real w = qr(k, j);
       for (int i = k + 1; i < rows; i++) w += qr(i, k) * qr(i, j);
       w *= hb[k];
       qr(k, j) -= w;
@@ -305,14 +306,14 @@ inline Vec colpiv_qr_solve(const Mat& A, const Vec& b) {
   Vec c(b);
   for (int k = 0; k < nonzero; k++) {
     if (hb[k] == 0) continue;
-    double w = c[k];
+    real w = c[k];
     for (int i = k + 1; i < rows; i++) w += qr(i, k) * c[i];
     w *= hb[k];
     c[k] -= w;
     for (int i = k + 1; i < rows; i++) c[i] -= w * qr(i, k);
   }
   for (int i = nonzero - 1; i >= 0; i--) {
-    double s = c[i];
+    real s = c[i];
     for (int j = i + 1; j < nonzero; j++) s -= qr(i, j) * c[j];
     c[i] = s / qr(i, i);
   }

@@ -11,6 +11,7 @@
 //   per-body geometry constants       visualization.cpp:442-504, 541-568
 //   closed-form limb IK               lik.cpp:7-99, 142-245, 295-366
 #pragma once
+#include "orc_real.hpp"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -30,15 +31,15 @@ struct Failure : std::runtime_error {  // the reference prints "ERROR ..." and e
 
 // ---------------------------------------------------------------- 4-vectors
 struct V4 {  // reference extvec: (x,y,z,1)
-  double v[4];
+  real v[4];
   V4() { v[0] = v[1] = v[2] = 0; v[3] = 1; }
-  V4(double x, double y, double z) { v[0] = x; v[1] = y; v[2] = z; v[3] = 1; }
-  void set3(const double* a) { v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; }
+  V4(real x, real y, real z) { v[0] = x; v[1] = y; v[2] = z; v[3] = 1; }
+  void set3(const real* a) { v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; }
   void sub4(const V4& u) { for (int i = 0; i < 4; i++) v[i] -= u.v[i]; }  // matrix.cpp:250-254 (all 4!)
   void add3(const V4& u) { for (int i = 0; i < 3; i++) v[i] += u.v[i]; }
-  void scale3(double f) { for (int i = 0; i < 3; i++) v[i] *= f; }
-  double norm3() const { double s = 0; for (int i = 0; i < 3; i++) s += v[i] * v[i]; return std::sqrt(s); }
-  double dot3(const V4& u) const { double s = 0; for (int i = 0; i < 3; i++) s += v[i] * u.v[i]; return s; }
+  void scale3(real f) { for (int i = 0; i < 3; i++) v[i] *= f; }
+  real norm3() const { real s = 0; for (int i = 0; i < 3; i++) s += v[i] * v[i]; return orc::m_sqrt(s); }
+  real dot3(const V4& u) const { real s = 0; for (int i = 0; i < 3; i++) s += v[i] * u.v[i]; return s; }
   V4 cross(const V4& u) const {
     return V4(v[1] * u.v[2] - v[2] * u.v[1], v[2] * u.v[0] - v[0] * u.v[2], v[0] * u.v[1] - v[1] * u.v[0]);
   }
@@ -46,17 +47,17 @@ struct V4 {  // reference extvec: (x,y,z,1)
 
 // ------------------------------------------------- rigid transform, col-major
 struct M4 {  // reference affine: element (i,j) at a[4j+i]
-  double a[16];
+  real a[16];
   M4() { identity(); }
   void identity() { for (int i = 0; i < 16; i++) a[i] = (i % 5 == 0) ? 1.0 : 0.0; }
-  static M4 translation(const double* t) { M4 m; m.a[12] = t[0]; m.a[13] = t[1]; m.a[14] = t[2]; return m; }
-  double at(int i, int j) const { return a[4 * j + i]; }
+  static M4 translation(const real* t) { M4 m; m.a[12] = t[0]; m.a[13] = t[1]; m.a[14] = t[2]; return m; }
+  real at(int i, int j) const { return a[4 * j + i]; }
   // this <- this * b, sums accumulated k = 0..3 starting from 0 (matrix.cpp:78-97)
   void mul(const M4& b) {
-    double r[16];
+    real r[16];
     for (int j = 0; j < 4; j++)
       for (int i = 0; i < 4; i++) {
-        double s = 0;
+        real s = 0;
         for (int k = 0; k < 4; k++) s += a[4 * k + i] * b.a[4 * j + k];
         r[4 * j + i] = s;
       }
@@ -65,13 +66,13 @@ struct M4 {  // reference affine: element (i,j) at a[4j+i]
   V4 apply(const V4& x) const {  // full 4x4 times (x,y,z,w), matrix.cpp:149-163
     V4 y;
     for (int i = 0; i < 4; i++) {
-      double s = 0;
+      real s = 0;
       for (int j = 0; j < 4; j++) s += a[4 * j + i] * x.v[j];
       y.v[i] = s;
     }
     return y;
   }
-  void set_rot_raw12(const double* r12) {  // raw copy of an ODE dMatrix3 (=> transpose), matrix.cpp:107-113
+  void set_rot_raw12(const real* r12) {  // raw copy of an ODE dMatrix3 (=> transpose), matrix.cpp:107-113
     for (int i = 0; i < 12; i++) a[i] = r12[i];
     a[12] = a[13] = a[14] = 0; a[15] = 1;
   }
@@ -88,62 +89,62 @@ struct M4 {  // reference affine: element (i,j) at a[4j+i]
   V4 translation_part() const { return V4(a[12], a[13], a[14]); }
 };
 
-// ---------------------------------------------------- ODE helpers [ext], dReal=double
+// ---------------------------------------------------- ODE helpers [ext], dReal=real
 // Row-major 3x4 ("dMatrix3") outputs.
-inline void ode_R_from_axis_angle(double R[12], double ax, double ay, double az, double angle) {
-  double q[4];
-  double l = ax * ax + ay * ay + az * az;
+inline void ode_R_from_axis_angle(real R[12], real ax, real ay, real az, real angle) {
+  real q[4];
+  real l = ax * ax + ay * ay + az * az;
   if (l > 0) {
     angle *= 0.5;
-    q[0] = std::cos(angle);
-    l = std::sin(angle) * (1.0 / std::sqrt(l));
+    q[0] = orc::m_cos(angle);
+    l = orc::m_sin(angle) * (1.0 / orc::m_sqrt(l));
     q[1] = ax * l; q[2] = ay * l; q[3] = az * l;
   } else { q[0] = 1; q[1] = q[2] = q[3] = 0; }
-  double qq1 = 2 * q[1] * q[1], qq2 = 2 * q[2] * q[2], qq3 = 2 * q[3] * q[3];
+  real qq1 = 2 * q[1] * q[1], qq2 = 2 * q[2] * q[2], qq3 = 2 * q[3] * q[3];
   R[0] = 1 - qq2 - qq3;                 R[1] = 2 * (q[1] * q[2] - q[0] * q[3]); R[2] = 2 * (q[1] * q[3] + q[0] * q[2]);  R[3] = 0;
   R[4] = 2 * (q[1] * q[2] + q[0] * q[3]); R[5] = 1 - qq1 - qq3;                 R[6] = 2 * (q[2] * q[3] - q[0] * q[1]);  R[7] = 0;
   R[8] = 2 * (q[1] * q[3] - q[0] * q[2]); R[9] = 2 * (q[2] * q[3] + q[0] * q[1]); R[10] = 1 - qq1 - qq2;                R[11] = 0;
 }
-inline void ode_R_from_euler(double R[12], double phi, double theta, double psi) {
-  double sphi = std::sin(phi), cphi = std::cos(phi), sth = std::sin(theta), cth = std::cos(theta),
-         spsi = std::sin(psi), cpsi = std::cos(psi);
+inline void ode_R_from_euler(real R[12], real phi, real theta, real psi) {
+  real sphi = orc::m_sin(phi), cphi = orc::m_cos(phi), sth = orc::m_sin(theta), cth = orc::m_cos(theta),
+         spsi = orc::m_sin(psi), cpsi = orc::m_cos(psi);
   R[0] = cpsi * cth;                      R[1] = spsi * cth;                      R[2] = -sth;        R[3] = 0;
   R[4] = cpsi * sth * sphi - spsi * cphi; R[5] = spsi * sth * sphi + cpsi * cphi; R[6] = cth * sphi;  R[7] = 0;
   R[8] = cpsi * sth * cphi + spsi * sphi; R[9] = spsi * sth * cphi - cpsi * sphi; R[10] = cth * cphi; R[11] = 0;
 }
 
 // visualization.cpp:11-25 -- rotation (as ODE matrix) whose raw copy into M4 takes z to v.
-inline void rot_z_to_v(double R[12], const V4& v) {
+inline void rot_z_to_v(real R[12], const V4& v) {
   const V4 z(0, 0, 1);
   V4 a = v.cross(z);
-  double an = a.norm3();
+  real an = a.norm3();
   if (an < 1e-10) a = V4(0, 1, 0);
-  double angle = std::asin(an / v.norm3());
+  real angle = orc::m_asin(an / v.norm3());
   if (v.dot3(z) < 0) angle = M_PI - angle;
   ode_R_from_axis_angle(R, a.v[0], a.v[1], a.v[2], angle);
   M4 A; A.set_rot_raw12(R);                       // the reference's inline self-check (line 24)
-  V4 b = A.apply(z), c = v; double n = c.norm3();
+  V4 b = A.apply(z), c = v; real n = c.norm3();
   for (int i = 0; i < 3; i++) c.v[i] /= n;
   c.sub4(b);
   if (c.norm3() > 1e-3) throw Failure("rot_ztov self-check failed");
 }
-inline M4 m4_from_posrot(const double* pos, const double* R12) {  // visualization.cpp:54-60
+inline M4 m4_from_posrot(const real* pos, const real* R12) {  // visualization.cpp:54-60
   M4 A; A.set_rot_raw12(R12); A.a[12] = pos[0]; A.a[13] = pos[1]; A.a[14] = pos[2]; return A;
 }
 inline M4 m4_from_orientation(const V4 o[2]) {  // visualization.cpp:62-69
-  double R[12]; ode_R_from_euler(R, o[1].v[0], o[1].v[1], o[1].v[2]);
+  real R[12]; ode_R_from_euler(R, o[1].v[0], o[1].v[1], o[1].v[2]);
   return m4_from_posrot(o[0].v, R);
 }
-inline void wrap_pm_pi(double& a) {  // visualization.cpp:73-79
+inline void wrap_pm_pi(real& a) {  // visualization.cpp:73-79
   if (a < -M_PI) { while (a < -M_PI) a += 2 * M_PI; }
   else if (a > M_PI) { while (a > M_PI) a -= 2 * M_PI; }
 }
-inline void euler_from_m4(const M4& A, double* ang) {  // visualization.cpp:81-101
-  double r11 = A.a[0], r21 = A.a[1], r31 = A.a[2], r32 = A.a[6], r33 = A.a[10];
-  double th = -std::asin(r31), ct = std::cos(th);
-  ang[0] = std::atan2(r32 / ct, r33 / ct);
+inline void euler_from_m4(const M4& A, real* ang) {  // visualization.cpp:81-101
+  real r11 = A.a[0], r21 = A.a[1], r31 = A.a[2], r32 = A.a[6], r33 = A.a[10];
+  real th = -orc::m_asin(r31), ct = orc::m_cos(th);
+  ang[0] = orc::m_atan2(r32 / ct, r33 / ct);
   ang[1] = th;
-  ang[2] = std::atan2(r21 / ct, r11 / ct);
+  ang[2] = orc::m_atan2(r21 / ct, r11 / ct);
 }
 
 // --------------------------------------------------------------- tiny XML reader
@@ -200,9 +201,9 @@ class XParser {
     return true;
   }
 };
-inline int parse_doubles(const std::string& str, double* out, int maxn) {  // core.cpp:8-12
-  std::stringstream ss(str); int n = 0; double v;
-  while (n < maxn && (ss >> v)) out[n++] = v;
+inline int parse_doubles(const std::string& str, real* out, int maxn) {  // core.cpp:8-12
+  std::stringstream ss(str); int n = 0; real v = 0;
+  while (n < maxn && (ss >> RealIn(v))) out[n++] = v;
   return n;
 }
 
@@ -218,7 +219,7 @@ struct Body {  // modelnode + modeljoint + odepart of one XML <body>
   int qoff;                 // offset of this joint's values in the configuration vector
   M4 A_body_geom;           // odepart
   V4 capsule_to_pos;
-  double rcap;
+  real rcap;
   std::string name;
   Body() : id(0), parent(-1), jk(J_NONE), qoff(-1), rcap(0) {}
 };
@@ -229,12 +230,12 @@ typedef bool (*LimbSolver)(int limbi, const V4& pos_limb, V4& angles, bool bend,
 class Model {  // kinematicmodel (+ liksolver, which the reference keys on the file name)
  public:
   std::vector<Body> b;
-  std::vector<double> q;  // joint values: torso x,y,z,phi,theta,psi then hinges in DFS order
+  std::vector<real> q;  // joint values: torso x,y,z,phi,theta,psi then hinges in DFS order
   std::string xmlname;
   int lik_index;          // 0 myant, 1 hexapod, 2 spider, -1 none (lik.cpp:8-16)
   std::vector<int> limb_top;
   std::vector<bool> limb_bend;
-  double rcap;
+  real rcap;
   bool ignore_reach;      // the reference's global ignore_reach_flag (lik.cpp:142)
 
   explicit Model(const std::string& path) : lik_index(-1), rcap(0), ignore_reach(false) {
@@ -264,29 +265,29 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
   M4 joint_transform(const Body& bd) const {  // model.cpp:37-62
     M4 A;
     if (bd.jk == J_FREE6) {
-      double R[12];
+      real R[12];
       ode_R_from_euler(R, q[bd.qoff + 3], q[bd.qoff + 4], q[bd.qoff + 5]);
       A.set_rot_raw12(R);
       A.shift(V4(q[bd.qoff], q[bd.qoff + 1], q[bd.qoff + 2]));
     } else {
-      double val = q[bd.qoff], c = std::cos(val), s = std::sin(val);
+      real val = q[bd.qoff], c = orc::m_cos(val), s = orc::m_sin(val);
       A.a[0] = c; A.a[5] = c; A.a[4] = -s; A.a[1] = s;
     }
     return A;
   }
-  void set_jvalues(const double* v) { for (size_t i = 0; i < q.size(); i++) q[i] = v[i]; }
-  void get_jvalues(double* v) const { for (size_t i = 0; i < q.size(); i++) v[i] = q[i]; }
+  void set_jvalues(const real* v) { for (size_t i = 0; i < q.size(); i++) q[i] = v[i]; }
+  void get_jvalues(real* v) const { for (size_t i = 0; i < q.size(); i++) v[i] = q[i]; }
   void orient_torso(const V4 o[2]) {  // model.cpp:403-409
     for (int i = 0; i < 2; i++) for (int j = 0; j < 3; j++) q[j + 3 * i] = o[i].v[j];
     fk();
   }
   // model.cpp:354-359 ; returns false where the reference would exit(1) (unreachable target)
-  bool set_jvalues_with_lik(const double* rec) {
+  bool set_jvalues_with_lik(const real* rec) {
     for (int i = 0; i < 6; i++) q[i] = rec[i];
     fk();
     return place_limbs(rec + 6);
   }
-  bool place_limbs(const double* p) {  // lik.cpp:89-99
+  bool place_limbs(const real* p) {  // lik.cpp:89-99
     if (lik_index < 0) return true;
     for (int i = 0; i < nlimbs(); i++) if (!place_limb(i, V4(p[3 * i], p[3 * i + 1], p[3 * i + 2]))) return false;
     return true;
@@ -301,7 +302,7 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
   int build(const XNode& x, int parent, const M4& A_parent_ground) {  // model.cpp:246-289
     Body bd;
     bd.id = (int)b.size(); bd.parent = parent;
-    double pos[3] = {0, 0, 0};
+    real pos[3] = {0, 0, 0};
     if (const std::string* a = x.attr("pos")) parse_doubles(*a, pos, 3);
     if (const std::string* a = x.attr("name")) bd.name = *a;
     bd.A_pj_body = M4::translation(pos);
@@ -323,16 +324,16 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
     if (!g) throw Failure("body without geom");
     const std::string* type = g->attr("type");
     if (!type) throw Failure("geom without type");
-    double r = 0;
+    real r = 0;
     if (const std::string* a = g->attr("size")) parse_doubles(*a, &r, 1);
     if (*type == "sphere") {
-      double pos[3] = {0, 0, 0};
+      real pos[3] = {0, 0, 0};
       if (const std::string* a = g->attr("pos")) parse_doubles(*a, pos, 3);
       bd.A_body_geom = M4::translation(pos);
     } else if (*type == "capsule" || *type == "cylinder") {
-      double ft[6] = {0, 0, 0, 0, 0, 0};
+      real ft[6] = {0, 0, 0, 0, 0, 0};
       if (const std::string* a = g->attr("fromto")) parse_doubles(*a, ft, 6);
-      double pos[3], R[12];
+      real pos[3], R[12];
       for (int i = 0; i < 3; i++) pos[i] = (ft[i] + ft[i + 3]) / 2.;
       V4 r1, r2; r1.set3(ft); r2.set3(ft + 3); r2.sub4(r1);
       rot_z_to_v(R, r2);
@@ -345,7 +346,7 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
     const XNode* j = x.first("joint");
     if (!j) return;
     const std::string* type = j->attr("type");
-    double pos[3] = {0, 0, 0}, axis[3] = {0, 0, 1};
+    real pos[3] = {0, 0, 0}, axis[3] = {0, 0, 1};
     if (const std::string* a = j->attr("pos")) parse_doubles(*a, pos, 3);
     if (type && *type == "free") {
       bd.jk = J_FREE6; bd.qoff = (int)q.size(); q.resize(q.size() + 6, 0.0);
@@ -358,7 +359,7 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
       if (const std::string* a = j->attr("axis")) parse_doubles(*a, axis, 3);
       bd.jk = J_HINGE; bd.qoff = (int)q.size(); q.resize(q.size() + 1, 0.0);
       V4 p, v; p.set3(pos); v.set3(axis);
-      double R[12]; rot_z_to_v(R, v);
+      real R[12]; rot_z_to_v(R, v);
       M4 A1; A1.set_rot_raw12(R);
       M4 A = bd.A_pj_body; A.mul(A1); A.shift(p);
       bd.J_A_parent = A;
@@ -390,7 +391,7 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
     if (lik_index == 2) limb_top.assign(t2, t2 + 6);
     limb_bend.assign(limb_top.size(), true);
     for (size_t i = 0; i < limb_top.size(); i++) {
-      double r1 = b[limb_top[i] + 2].rcap;
+      real r1 = b[limb_top[i] + 2].rcap;
       if (rcap > 0 && r1 != rcap) throw Failure("rcaps must be same for all feet");
       rcap = r1;
     }
@@ -398,42 +399,42 @@ class Model {  // kinematicmodel (+ liksolver, which the reference keys on the f
 };
 
 // ------------------------------------------------------------- limb IK (lik.cpp:151-245)
-static const double kLimbLs[3] = {.05, .4, .4};   // hexapod / quadruped links
-static const double kLimbLs1[3] = {.1, .4, .4};   // spider links
+static const real kLimbLs[3] = {.05, .4, .4};   // hexapod / quadruped links
+static const real kLimbLs1[3] = {.1, .4, .4};   // spider links
 
-inline bool limb_solver_yxx(const V4& pos_limb, V4& ja, const double* ls, int ysign, bool bend, bool ignore_reach) {
-  double l0 = ls[0], l1 = ls[1], l2 = ls[2];
+inline bool limb_solver_yxx(const V4& pos_limb, V4& ja, const real* ls, int ysign, bool bend, bool ignore_reach) {
+  real l0 = ls[0], l1 = ls[1], l2 = ls[2];
   int s0 = ysign, s1 = 2 * int(bend) - 1;
   V4 pos0(0, 0, s0 * l0), pos1(pos_limb);
   pos1.sub4(pos0);
-  double l = pos1.norm3();
+  real l = pos1.norm3();
   if (l1 + l2 - l < 0) { if (ignore_reach) l = l1 + l2; else return false; }
-  double x1 = pos_limb.v[0], y1 = pos_limb.v[1], z1 = pos_limb.v[2];
-  double c = (z1 - s0 * l0) / l;
-  double phi = std::atan2(x1, y1);
-  double theta = std::acos(c) + (1 - s0) * M_PI / 2;
+  real x1 = pos_limb.v[0], y1 = pos_limb.v[1], z1 = pos_limb.v[2];
+  real c = (z1 - s0 * l0) / l;
+  real phi = orc::m_atan2(x1, y1);
+  real theta = orc::m_acos(c) + (1 - s0) * M_PI / 2;
   wrap_pm_pi(phi); wrap_pm_pi(theta);
-  double ll = l * l, del = l2 * l2 - l1 * l1;
-  double beta = s1 * s0 * std::acos((ll - del) / (2 * l1 * l));
-  double gamma = s1 * s0 * std::acos((ll + del) / (2 * l2 * l));
+  real ll = l * l, del = l2 * l2 - l1 * l1;
+  real beta = s1 * s0 * orc::m_acos((ll - del) / (2 * l1 * l));
+  real gamma = s1 * s0 * orc::m_acos((ll + del) / (2 * l2 * l));
   ja = V4(-phi, -theta + beta, -(beta + gamma));
   return true;
 }
-inline bool limb_solver_zxx(const V4& pos_limb, V4& ja, const double* ls, int ysign, bool bend, bool ignore_reach) {
-  double l0 = ls[0], l1 = ls[1], l2 = ls[2];
+inline bool limb_solver_zxx(const V4& pos_limb, V4& ja, const real* ls, int ysign, bool bend, bool ignore_reach) {
+  real l0 = ls[0], l1 = ls[1], l2 = ls[2];
   int s0 = ysign, s1 = 2 * int(bend) - 1;
   V4 pos0(0, 0, l0), pos1(pos_limb);
   pos1.add3(pos0);
-  double l = pos1.norm3();
+  real l = pos1.norm3();
   if (l1 + l2 - l < 0) { if (ignore_reach) l = l1 + l2; else return false; }
-  double x = pos_limb.v[0], y = pos_limb.v[1], z = pos_limb.v[2];
-  double c = (z + l0) / l;
-  double phi = std::atan2(x, y);
-  double theta = std::acos(c) - s0 * M_PI / 2;
+  real x = pos_limb.v[0], y = pos_limb.v[1], z = pos_limb.v[2];
+  real c = (z + l0) / l;
+  real phi = orc::m_atan2(x, y);
+  real theta = orc::m_acos(c) - s0 * M_PI / 2;
   wrap_pm_pi(phi); wrap_pm_pi(theta);
-  double ll = l * l, del = l2 * l2 - l1 * l1;
-  double beta = s1 * std::acos((ll - del) / (2 * l1 * l));
-  double gamma = s1 * std::acos((ll + del) / (2 * l2 * l));
+  real ll = l * l, del = l2 * l2 - l1 * l1;
+  real beta = s1 * orc::m_acos((ll - del) / (2 * l1 * l));
+  real gamma = s1 * orc::m_acos((ll + del) / (2 * l2 * l));
   ja = V4(-phi, -theta + beta, -(beta + gamma));
   return true;
 }
@@ -446,16 +447,16 @@ inline bool limb_solve(int lik_index, int limbi, const V4& p, V4& ja, bool bend,
 }
 // Forward map of the y-x-x limb in the hip joint frame (lik.cpp:248-274, pos_flag branch); used by the
 // IK round-trip pin (lik.cpp:371-404).
-inline bool bend_solver_yxx(V4& pos, const V4& ang, const double* ls, int ysign, bool pos_flag) {
+inline bool bend_solver_yxx(V4& pos, const V4& ang, const real* ls, int ysign, bool pos_flag) {
   int s0 = ysign;
-  double a0 = ang.v[0], a1 = ang.v[1], a2 = ang.v[2];
+  real a0 = ang.v[0], a1 = ang.v[1], a2 = ang.v[2];
   if (pos_flag) {
-    double l0 = ls[0], l1 = ls[1], l2 = ls[2];
+    real l0 = ls[0], l1 = ls[1], l2 = ls[2];
     int s1 = (a2 < 0) ? 1 : -1;
-    double ca = std::cos(a2), l = std::sqrt(l1 * l1 + l2 * l2 + 2 * l1 * l2 * ca);
-    double theta = s1 * std::acos((l1 + l2 * ca) / l) - a1 + (1 - s0) * M_PI / 2, phi = -a0;
-    double stl = std::sin(theta) * l;
-    pos = V4(stl * std::sin(phi), stl * std::cos(phi), s0 * l0 + std::cos(theta) * l);
+    real ca = orc::m_cos(a2), l = orc::m_sqrt(l1 * l1 + l2 * l2 + 2 * l1 * l2 * ca);
+    real theta = s1 * orc::m_acos((l1 + l2 * ca) / l) - a1 + (1 - s0) * M_PI / 2, phi = -a0;
+    real stl = orc::m_sin(theta) * l;
+    pos = V4(stl * orc::m_sin(phi), stl * orc::m_cos(phi), s0 * l0 + orc::m_cos(theta) * l);
   }
   return (a2 * s0 < 0);
 }
