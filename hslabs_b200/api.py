@@ -60,6 +60,7 @@ def _load():
     lib.hsl_eval_trajectories_host.argtypes = [vp, i64, i32] + [vp] * 9
     lib.hsl_solve_frames_host.argtypes = [vp, i64] + [vp] * 11
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
+    lib.hsl_set_rec_transform.argtypes = [vp, vp, vp]
     lib.hsl_launch_count.argtypes = [vp]
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
     lib.hsl_math_selftest.argtypes = [i32, vp, vp, vp]
@@ -72,7 +73,7 @@ def exported_symbols():
     """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
-            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_set_tuning", "hsl_launch_count",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
 
 
@@ -139,6 +140,13 @@ class Model:
                 self._h = None
         except Exception:
             pass
+
+    def set_rec_transform(self, transl=None, eas=None):
+        """pergensetup::set_rec_rotation / set_rec_transform (pergen.cpp:309-320): rigid map applied to every generated
+        frame record of the following eval_gaits* calls; no arguments switch it off."""
+        tr = None if transl is None else np.ascontiguousarray(transl, np.float64)
+        ea = None if eas is None else np.ascontiguousarray(eas, np.float64)
+        _check(_load().hsl_set_rec_transform(self._h, _p(tr), _p(ea)))
 
     # ---- measurement helpers
     def set_tuning(self, fb=64, maxreg=128):

@@ -58,6 +58,8 @@ struct HslModel {
   double total_mass;
   int fb = 64, maxreg = 128;
   int64_t launches = 0;
+  bool rec_on = false;           // pergensetup::rec_transform_flag
+  double rec_R[9], rec_t[3];
   // workspace
   DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b;
   PinBuf pin_in, pin_out;
@@ -121,6 +123,17 @@ int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
   return HSL_OK;
 }
 int64_t hsl_launch_count(const HslModel* m) { return m ? m->launches : 0; }
+int hsl_set_rec_transform(HslModel* m, const double* transl, const double* eas) {
+  if (!m) return set_err(HSL_ERR_ARG, "null model");
+  if (!transl && !eas) { m->rec_on = false; return HSL_OK; }
+  const double z3[3] = {0, 0, 0};
+  const double* e = eas ? eas : z3;
+  const double* t = transl ? transl : z3;
+  euler_to_R(e[0], e[1], e[2], m->rec_R);  // affine_from_orientation, pergen.cpp:316-319
+  for (int k = 0; k < 3; k++) m->rec_t[k] = t[k];
+  m->rec_on = true;
+  return HSL_OK;
+}
 
 // ---------------------------------------------------------------- device-pointer entry
 static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
@@ -140,6 +153,13 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
   A.cand = (const HslCand*)m->cand.p; A.ttab = (const double*)m->ttab.p;
   A.wframe = (double*)m->wframe.p; A.fmin_cfz = (double*)m->fmin.p; A.fmax_mu = (double*)m->fmax.p;
   A.status = st_buf;
+  if (m->rec_on) {
+    A.flags |= HSL_FLAG_REC_TRANSFORM;
+    memcpy(A.rec_R, m->rec_R, sizeof A.rec_R);
+    memcpy(A.rec_t, m->rec_t, sizeof A.rec_t);
+  } else {
+    A.flags &= ~HSL_FLAG_REC_TRANSFORM;
+  }
   if (dump) {
     const HslModelPod& P = m->pod;
     HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * nfr));

@@ -59,6 +59,7 @@
 #define HSL_MODE_FIELDS 2  // per-frame dynrec fields -> x,z,tau (a8-a13)
 
 #define HSL_FLAG_IGNORE_REACH 1
+#define HSL_FLAG_REC_TRANSFORM 2  // internal: set by the library when hsl_set_rec_transform is active
 
 struct HslFrameArgs {
   int64_t n_cand;
@@ -79,6 +80,8 @@ struct HslFrameArgs {
   double* q_out;       // [config_dim][C*(n_t+4)] generated joint values (GAIT)
   uint8_t* contacts;   // [nf][n_frames]
   long long* phase_clk;  // [blocks][warps][8] cycle stamps, only written by -DHSL_PHASE_CLOCKS builds (profiling aid)
+  // pergensetup::rec_transform (pergen.cpp:309-335): rigid map applied to every generated frame record
+  double rec_R[9], rec_t[3];  // column-major rotation, translation; used when flags & HSL_FLAG_REC_TRANSFORM
 };
 
 // ------------------------------------------------------------------ small vector helpers
@@ -151,6 +154,13 @@ HSL_HD void load_cand(const HslCand& c, int limb, HslCandView& o) {
 // the product (visualization.cpp:81-101) and the FK rebuilds the rotation from them; that round trip is the identity
 // away from gimbal lock, so the rotation is taken directly as Rz(psi) * R0 and the Euler angles (asin / atan2) are
 // only evaluated when a trajectory dump asks for them (eul != nullptr).
+// euler_angles_from_affine, visualization.cpp:81-101 (column-major R)
+HSL_HD void euler_from_R(const double* R, double* eul) {
+  const double th = -asin(R[2]), ct = cos(th);
+  eul[0] = atan2(R[5] / ct, R[8] / ct);
+  eul[1] = th;
+  eul[2] = atan2(R[1] / ct, R[0] / ct);
+}
 HSL_HD void torso_pose(const HslCandView& cd, double t, double* qt, double* R0, double* eul) {
   const double tv = t * cd.v;
   double psi = 0;
@@ -178,12 +188,26 @@ HSL_HD void torso_pose(const HslCandView& cd, double t, double* qt, double* R0, 
   qt[0] = cp * cd.tp0[0] - sp * cd.tp0[1] + rc * sp;
   qt[1] = sp * cd.tp0[0] + cp * cd.tp0[1] + rc * (1 - cp);
   qt[2] = cd.tp0[2];
-  if (eul) {
-    const double th = -asin(R0[2]), ct = cos(th);
-    eul[0] = atan2(R0[5] / ct, R0[8] / ct);
-    eul[1] = th;
-    eul[2] = atan2(R0[1] / ct, R0[0] / ct);
-  }
+  if (eul) euler_from_R(R0, eul);
+}
+// pergensetup::transform_rec, pergen.cpp:325-335 with transform_orientation :377-383: the torso pose becomes
+// A * pose (Euler angles re-extracted only for a trajectory dump, as in torso_pose) ...
+HSL_HD void rec_transform_pose(const HslFrameArgs& A, double* qt, double* R0, double* eul) {
+  double Rn[9], tn[3];
+  m3_mul(A.rec_R, R0, Rn);
+  m3_affine(A.rec_R, qt, A.rec_t, tn);
+#pragma unroll
+  for (int k = 0; k < 9; k++) R0[k] = Rn[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) qt[k] = tn[k];
+  if (eul) euler_from_R(R0, eul);
+}
+// ... and every foot target becomes A * p.
+HSL_HD void rec_transform_point(const HslFrameArgs& A, double* p) {
+  double pn[3];
+  m3_affine(A.rec_R, p, A.rec_t, pn);
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[k] = pn[k];
 }
 // Torso body frame from its joint values: model.cpp:183-195 with the free joint (model.cpp:40-48).
 HSL_HD void torso_frame(const HslModelPod& M, const double* qt, const double* R0, double* t0) {
@@ -419,10 +443,12 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     load_cand(A.cand[sl.c], limb, cd);
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
     torso_pose(cd, t, qt, R0, (DUMP && A.q_out != nullptr) ? eul : nullptr);
+    if (A.flags & HSL_FLAG_REC_TRANSFORM) rec_transform_pose(A, qt, R0, (DUMP && A.q_out != nullptr) ? eul : nullptr);
     torso_frame(M, qt, R0, t0);
     // foot target into the hip joint frame (lik.cpp:341-347), then the closed-form solver
     double p[3], Rh[9], th[3], oj[3], d[3], pl[3];
     foot_target(cd, t, p);
+    if (A.flags & HSL_FLAG_REC_TRANSFORM) rec_transform_point(A, p);
 #pragma unroll
     for (int k = 0; k < 3; k++) oj[k] = L.oatt[k];
     double ta[3], e[3];
@@ -493,6 +519,7 @@ HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM&
     load_cand(A.cand[sl.c], -1, cd);
     const double t = A.ttab[sl.c * (A.n_t + 4) + sl.i];
     torso_pose(cd, t, qt, st.R0, nullptr);
+    if (A.flags & HSL_FLAG_REC_TRANSFORM) rec_transform_pose(A, qt, st.R0, nullptr);
   } else {
     const double* qrow = A.traj + (sl.c * (A.n_t + 5) + sl.i) * M.config_dim;
 #pragma unroll

@@ -84,6 +84,12 @@ int hsl_solve_frames_host(HslModel* m, int64_t n_frames, const double* pos, cons
                           const double* mom_rate, const double* ang_mom_rate, const double* fpos, const uint8_t* contacts,
                           double* x, double* z, double* tau, int32_t* status);
 
+/* pergensetup::set_rec_rotation / set_rec_transform (pergen.cpp:309-320): a rigid map [Rz(psi)Ry(theta)Rx(phi) | transl]
+ * applied to every generated frame record (torso pose and foot targets, pergen.cpp:325-335) of the following
+ * hsl_eval_gaits* calls on this handle -- the reference copies one rec_transform to every candidate of a sweep
+ * (pergen.cpp:446).  eas = (phi, theta, psi); either pointer may be NULL (= zero); both NULL switches it off. */
+int hsl_set_rec_transform(HslModel* m, const double* transl /*[3]*/, const double* eas /*[3]*/);
+
 /* tuning / measurement helpers */
 int hsl_set_tuning(HslModel* m, int fb, int maxreg);          /* cost-only kernel variant: frame slots per block (32|64), register cap per thread */
 int64_t hsl_launch_count(const HslModel* m);                  /* kernels launched through this handle so far */

@@ -88,13 +88,27 @@ class periodicgenerator_view {
 };
 
 // pergensetup (pergen.h:68-112): a candidate gait
+// rec_transform of a pergensetup (pergen.h:75-76): Euler angles + translation of the rigid map, and its flag
+struct rectransform {
+  bool flag;
+  double transl[3], eas[3];
+  rectransform() : flag(false) { for (int k = 0; k < 3; k++) transl[k] = eas[k] = 0; }
+  // hands the map to the library handle (hsl_set_rec_transform); every evaluation call of the mirrors does this first
+  void apply(HslModel* h) const { check(flag ? hsl_set_rec_transform(h, transl, eas) : hsl_set_rec_transform(h, nullptr, nullptr)); }
+};
+
 class pergensetup {
   int n_;
   pgsconfigparams pcp_;
   periodicgenerator_view view_;
+  rectransform rec_;
  public:
   explicit pergensetup(int n) : n_(n), view_(&pcp_) {}
-  pergensetup(const pergensetup& o) : n_(o.n_), pcp_(o.pcp_), view_(&pcp_) {}
+  pergensetup(const pergensetup& o) : n_(o.n_), pcp_(o.pcp_), view_(&pcp_), rec_(o.rec_) {}
+  // pergen.cpp:309-313: keeps the translation, replaces the rotation (eas = phi, theta, psi)
+  void set_rec_rotation(const double rec_eas[3]) { for (int k = 0; k < 3; k++) rec_.eas[k] = rec_eas[k]; rec_.flag = true; }
+  void copy_rec_transform(const pergensetup* pgs) { rec_ = pgs->rec_; }  // pergen.cpp:338-342
+  const rectransform& rec_transform() const { return rec_; }
   const periodicgenerator_view* get_pergen() const { return &view_; }
   int get_limb_number() const { return n_; }
   int get_config_dim() const { return 6 + 3 * n_; }
@@ -137,6 +151,7 @@ class pgssweeper {
     if (parami_ == 0) pcp.step_duration = val_; else pcp.TLh[parami_ - 1] = val_;
     pgs_ = new pergensetup(pgs0_->get_limb_number());
     pgs_->set_config_params(pcp);
+    pgs_->copy_rec_transform(pgs0_);  // pergen.cpp:446
     return true;
   }
   int number_of_values() const { return n_val_ + 1; }
@@ -183,6 +198,7 @@ class periodic {
   const kinematicmodel* model_;
   int n_t_, config_dim_, nmj_, n_, nf_;
   pgsconfigparams pcp_;
+  rectransform rec_;
   bool have_, pen_force_, pen_torque_;
   int flags_;
   double work_, cot_, min_cfz_, max_mu_;
@@ -198,6 +214,7 @@ class periodic {
     z_.assign((size_t)n_t_ * 3 * nf_, 0.0);
     tau_.assign((size_t)n_t_ * nmj_, 0.0);
     int32_t status = 0;
+    rec_.apply(model_->handle());
     check(hsl_eval_gaits_detail_host(model_->handle(), 1, n_t_, row, flags_, &cot_, &work_, &min_cfz_, &max_mu_, &status, traj_.data(),
                                      x_.data(), z_.data(), tau_.data(), nullptr));
     if (status & HSL_ST_UNREACHABLE) throw error("LIK ERROR: limb position is unreachable");
@@ -227,7 +244,7 @@ class periodic {
   int get_nfeet() const { return nf_; }
   int get_number_of_dynparts() const { return n_; }
   void set_ignore_reach_flag(bool v) { flags_ = v ? HSL_FLAG_IGNORE_REACH : 0; have_ = false; }
-  void record_trajectory(const pergensetup* pgs, int n_t) { pcp_ = pgs->params(); n_t_ = n_t; have_ = false; }
+  void record_trajectory(const pergensetup* pgs, int n_t) { pcp_ = pgs->params(); rec_ = pgs->rec_transform(); n_t_ = n_t; have_ = false; }
   void compute_dynrecs() {}
   void compute_dynrec_ders() {}
   void switch_torso_penalty(bool force, bool torque) { pen_force_ = force; pen_torque_ = torque; }
@@ -361,6 +378,7 @@ class modelplayer {
     }
     std::vector<double> cot(vals.size());
     std::vector<int32_t> status(vals.size());
+    pgs->rec_transform().apply(model_.handle());
     check(hsl_eval_gaits_host(model_.handle(), (int64_t)vals.size(), n_t, rows.data(), flags_, cot.data(), nullptr, nullptr, nullptr, status.data()));
     for (size_t i = 0; i < vals.size(); i++) std::cout << "val = " << vals[i] << " COT = " << cot[i] << std::endl;
     if (vals_out) *vals_out = vals;

@@ -34,7 +34,7 @@ def lib():
         _lib.orc_model_load.argtypes = [C.c_char_p]
         _lib.orc_model_rcap.restype = C.c_double
         for name in ("orc_model_free", "orc_model_dims", "orc_model_rcap", "orc_set_ignore_reach", "orc_model_constants",
-                     "orc_fk", "orc_ik", "orc_gait_setup", "orc_gait_rec", "orc_measure_cot", "orc_frame_fields",
+                     "orc_fk", "orc_ik", "orc_gait_setup", "orc_gait_rec", "orc_measure_cot", "orc_measure_cot_rect", "orc_frame_fields",
                      "orc_eval_trajectory", "orc_test_dynamics", "orc_measure_cot_sweep", "orc_eval_batch"):
             getattr(_lib, name).argtypes = None
     return _lib
@@ -134,14 +134,19 @@ class Model:
             raise ValueError("bad gait parameters")
         return rec
 
-    def measure_cot(self, params, n_t, detail=False):
+    def measure_cot(self, params, n_t, detail=False, rec_transform=None):
+        """rec_transform = (transl[3], eas[3]) switches pergensetup::rec_transform on (pergen.cpp:309-335)."""
         params = np.ascontiguousarray(params, np.float64)
         out = np.zeros(4)
         traj = x = z = tau = None
         if detail:
             traj = np.zeros((n_t + 5, self.config_dim)); x = np.zeros((n_t, 6 * self.n))
             z = np.zeros((n_t, 3 * self.nf)); tau = np.zeros((n_t, self.nmj))
-        rc = lib().orc_measure_cot(self.h, _p(params), C.c_int(n_t), _p(out), _p(traj), _p(x), _p(z), _p(tau))
+        if rec_transform is not None:
+            tr = np.ascontiguousarray(rec_transform[0], np.float64); ea = np.ascontiguousarray(rec_transform[1], np.float64)
+            rc = lib().orc_measure_cot_rect(self.h, _p(params), _p(tr), _p(ea), C.c_int(n_t), _p(out), _p(traj), _p(x), _p(z), _p(tau))
+        else:
+            rc = lib().orc_measure_cot(self.h, _p(params), C.c_int(n_t), _p(out), _p(traj), _p(x), _p(z), _p(tau))
         res = dict(status=rc, cot=out[0], work=out[1], min_cfz=out[2], max_mu=out[3])
         if detail:
             res.update(traj=traj, x=x, z=z, tau=tau)

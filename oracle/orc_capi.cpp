@@ -148,6 +148,20 @@ int orc_measure_cot(void* hv, const double* params, int n_t, double* out4, doubl
   } catch (const std::exception&) { return -1; }
 }
 
+// measure_cot with pergensetup::rec_transform active (pergen.cpp:309-335): rec_transl / rec_eas [3] each.
+int orc_measure_cot_rect(void* hv, const double* params, const double* rec_transl, const double* rec_eas, int n_t, double* out4,
+                         double* traj, double* x, double* z, double* tau) {
+  Model& m = *((Handle*)hv)->model;
+  try {
+    GaitSetup g(m.nlimbs());
+    setup_gait(g, m, params_from(params));
+    g.set_rec_transform(V4(rec_transl[0], rec_transl[1], rec_transl[2]), V4(rec_eas[0], rec_eas[1], rec_eas[2]));
+    CotResult r = measure_cot(m, g, n_t, traj, x, z, tau);
+    out4[0] = r.cot; out4[1] = r.work; out4[2] = r.min_cfz; out4[3] = r.max_mu;
+    return r.status;
+  } catch (const std::exception&) { return -1; }
+}
+
 // Per-frame dynrec fields of the solved frames 2..n_t+1 (inputs of the frame-solve entry).
 // Layout [frame][body][3] for pos,jpos,jzaxis,mom_rate,ang_mom_rate; fpos [frame][nf][3]; contacts [frame][nf].
 int orc_frame_fields(void* hv, const double* params, int n_t, double* pos, double* jpos, double* jzaxis,

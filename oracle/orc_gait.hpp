@@ -135,6 +135,11 @@ class GaitSetup {  // pergensetup
     rec_transform = m4_from_orientation(o);
     rec_transform_flag = true;
   }
+  void set_rec_transform(const V4& transl, const V4& eas) {  // pergen.cpp:316-320 (private in the reference)
+    V4 o[2] = {transl, eas};
+    rec_transform = m4_from_orientation(o);
+    rec_transform_flag = true;
+  }
   // pergen.cpp:225-239
   void set_rec(real* rec, real t) {
     V4 o[2] = {torso_pos0, euler};

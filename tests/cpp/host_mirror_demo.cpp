@@ -30,6 +30,15 @@ int main(int argc, char** argv) {
     for (int i = 0; i < nmj; i++) std::printf(" %.17g", torques[i]);
     std::printf("\n");
     if (argc > 4) player0.record_per_traj(pgs, argv[4]);
+    // main.cpp:38: extvec rec_eas (0,0,-1.571); pgs->set_rec_rotation(rec_eas);  -- sweep candidates inherit it (pergen.cpp:446)
+    const double rec_eas[3] = {0, 0, -1.571};
+    pgs->set_rec_rotation(rec_eas);
+    std::printf("rotated COT = %.17g\n", player0.measure_cot(pgs, 20));
+    std::vector<double> vals, cots;
+    player0.measure_cot_sweep(pgs, 20, "step_length", 0.3, 0.5, 2, &vals, &cots);
+    std::printf("rotated sweep:");
+    for (size_t i = 0; i < cots.size(); i++) std::printf(" %.17g", cots[i]);
+    std::printf("\n");
     delete pgs;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());

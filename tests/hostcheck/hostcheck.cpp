@@ -192,6 +192,25 @@ int hc_setup_candidate(const char* xml, const double* params, int n_t, HslCand* 
   return 0;
 }
 
+// test-side mirror of hsl_set_rec_transform (process-wide here; the library keeps it per handle)
+static bool g_rec_on = false;
+static double g_rec_R[9], g_rec_t[3];
+void hc_set_rec_transform(const double* transl, const double* eas) {
+  g_rec_on = (transl != nullptr) || (eas != nullptr);
+  if (!g_rec_on) return;
+  const double z3[3] = {0, 0, 0};
+  const double* e = eas ? eas : z3;
+  const double* t = transl ? transl : z3;
+  euler_to_R(e[0], e[1], e[2], g_rec_R);
+  for (int k = 0; k < 3; k++) g_rec_t[k] = t[k];
+}
+static void apply_rec(HslFrameArgs& A) {
+  if (!g_rec_on) return;
+  A.flags |= HSL_FLAG_REC_TRANSFORM;
+  memcpy(A.rec_R, g_rec_R, sizeof g_rec_R);
+  memcpy(A.rec_t, g_rec_t, sizeof g_rec_t);
+}
+
 int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int flags, double* cot, double* work, double* min_cfz,
                   double* max_mu, int32_t* status, double* traj, double* x, double* z, double* tau, uint8_t* contacts) {
   HslModelPod M;
@@ -211,6 +230,7 @@ int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int
   A.cand = cand.data(); A.ttab = ttab.data();
   A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
   A.x = dx.data(); A.z = dz.data(); A.tau = dtau.data(); A.q_out = dq.data(); A.contacts = dc.data();
+  apply_rec(A);
   run_any(M, A, HSL_MODE_GAIT);
   double tm = 0;
   for (int i = 0; i < M.n; i++) tm += 1.0;
@@ -242,6 +262,7 @@ int hc_eval_gaits_pipe(const char* xml, int64_t C, int n_t, const double* params
   A.n_cand = C; A.n_t = n_t; A.flags = flags; A.n_frames = nfr;
   A.cand = cand.data(); A.ttab = ttab.data();
   A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
+  apply_rec(A);
   if (M.nf == 6) { if (fb == 64) emulate_pipe<6, 64>(M, A, grid); else emulate_pipe<6, 32>(M, A, grid); }
   else { if (fb == 64) emulate_pipe<4, 64>(M, A, grid); else emulate_pipe<4, 32>(M, A, grid); }
   finish(C, n_t, (double)M.n, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);

@@ -43,6 +43,13 @@ def eval_gaits(xml, params, n_t, flags=0):
     return out
 
 
+def set_rec_transform(transl=None, eas=None):
+    """Process-wide mirror of hsl_set_rec_transform for the emulation; call with no arguments to switch it off."""
+    tr = None if transl is None else np.ascontiguousarray(transl, np.float64)
+    ea = None if eas is None else np.ascontiguousarray(eas, np.float64)
+    lib().hc_set_rec_transform(_p(tr), _p(ea))
+
+
 def eval_trajectories(xml, traj, dt, n_t):
     d = model_dims(xml)
     traj = np.ascontiguousarray(traj, np.float64).reshape(-1, n_t + 5, d["config_dim"])

@@ -31,18 +31,28 @@ def test_main_like_sequence(demo, orc, pid, tmp_path):
     params, name = orc.load_preset(PRESETS, pid)
     m = orc.Model(model_xml(name))
     vals, cots = m.measure_cot_sweep(params, 20, "period", 3, 18, 15)
-    got = re.findall(r"val = (\S+) COT = (\S+)", out.stdout)
+    got = re.findall(r"val = (\S+) COT = (\S+)", out.stdout)[:16]
     assert len(got) == 16
     assert np.allclose([float(v) for v, _ in got], vals, rtol=1e-5)
     assert np.allclose([float(c) for _, c in got], cots, rtol=1e-5)  # printed with 6 significant digits, like the reference
     ref = m.measure_cot(params, 20, detail=True)
-    cot = float(re.search(r"COT = (\S+)\n", out.stdout[out.stdout.rindex("COT = "):]).group(1))
+    cot = float(re.search(r"^COT = (\S+)$", out.stdout, re.M).group(1))
     work = float(re.search(r"work = (\S+)", out.stdout).group(1))
     assert abs(cot - ref["cot"]) <= 1e-9 * abs(ref["cot"]) and abs(work - ref["work"]) <= 1e-9 * abs(ref["work"])
     cfz = np.array([float(v) for v in re.search(r"cfz:(.*)", out.stdout).group(1).split()])
     tq = np.array([float(v) for v in re.search(r"torques:(.*)", out.stdout).group(1).split()])
     assert np.abs(cfz - ref["z"][0].reshape(-1, 3)[:, 2]).max() <= 1e-9 * np.abs(ref["z"]).max()
     assert np.abs(tq - ref["tau"][0]).max() <= 1e-9 * np.abs(ref["tau"]).max()
+    # set_rec_rotation (main.cpp:38, pergen.cpp:309-313) on the candidate and on the sweep built from it
+    rec = ((0, 0, 0), (0, 0, -1.571))
+    rot = float(re.search(r"rotated COT = (\S+)", out.stdout).group(1))
+    ref_rot = m.measure_cot(params, 20, rec_transform=rec)["cot"]
+    assert abs(rot - ref_rot) <= 1e-9 * abs(ref_rot)
+    sw = [float(v) for v in re.search(r"rotated sweep:(.*)", out.stdout).group(1).split()]
+    for sl, c in zip((0.3, 0.4, 0.5), sw):
+        p2 = np.array(params, np.float64); p2[8] = sl
+        r2 = m.measure_cot(p2, 20, rec_transform=rec)["cot"]
+        assert abs(c - r2) <= 1e-9 * abs(r2)
     # traj.txt wire format (periodic.cpp:408-426, core.cpp:47-61): n_t rows of [q, qdot, tau], n_t = T/play_dt
     rows = np.loadtxt(traj_file)
     n_t = int(params[7] / 0.02 + .5)

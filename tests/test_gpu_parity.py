@@ -265,3 +265,31 @@ def test_small_and_ragged_batches(hsl, orc):
     ref = om.eval_batch(batch, 6, nthreads=8)
     got = m.eval_gaits(batch, 6)      # 37 candidates x 10 slots: several candidates per block
     assert np.abs(got["cot"] - ref["cot"]).max() <= TOL * np.abs(ref["cot"]).max()
+
+
+@pytest.mark.parametrize("pid,transl,eas", [(8, (0, 0, 0), (0, 0, -1.571)), (1, (0, 0, 0), (0, 0, -1.571)), (12, (0.3, -0.2, 0), (0, 0, 0.7)),
+                                            (8, (0, 0, -0.05), (0, 0, 0.3)), (24, (0, 0, 0), (0.02, 0.03, 0)), (9, (0.1, 0.1, 0), (0, 0, 2.5))])
+def test_rec_transform(hsl, orc, pid, transl, eas):
+    """pergensetup::rec_transform (pergen.cpp:309-335) through hsl_set_rec_transform: detail entry against the oracle,
+    cost-only kernels (plain and pipelined) against the detail entry, and switching it off restores the plain result."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    ref = orc.Model(xml).measure_cot(params, n_t, detail=True, rec_transform=(transl, eas))
+    m = hsl.Model(xml)
+    plain = m.eval_gaits(params, n_t)["cot"][0]
+    m.set_rec_transform(transl, eas)
+    gpu = m.eval_gaits_detail(params, n_t)
+    assert ref["status"] == 0 and gpu["status"][0] == 0
+    assert _angle_err(gpu["traj"][0], ref["traj"][:n_t + 4]) < 1e-12
+    for key in ("x", "z", "tau"):
+        assert rel_err(gpu[key][0], ref[key]) < TOL, key
+    assert abs(gpu["cot"][0] - ref["cot"]) <= TOL * abs(ref["cot"])
+    batch = np.tile(np.asarray(params, np.float64), (70, 1))
+    for fb, mr in ((64, 128), (32, 128), (64, 1)):
+        m.set_tuning(fb, mr)
+        c = m.eval_gaits(batch, n_t)["cot"]
+        assert np.abs(c - ref["cot"]).max() <= TOL * abs(ref["cot"]), (fb, mr)
+    assert abs(plain - ref["cot"]) > 1e-6 * abs(ref["cot"])
+    m.set_rec_transform()
+    assert abs(m.eval_gaits(params, n_t)["cot"][0] - plain) <= 1e-12 * abs(plain)

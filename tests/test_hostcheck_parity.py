@@ -130,3 +130,38 @@ def test_pipelined_kernel_emulation(orc, model, fb, grid):
         assert np.isnan(pipe[k][~ok]).all()
     ref = orc.Model(xml).eval_batch(p, n_t, nthreads=4)
     assert np.abs(pipe["cot"][ok] - ref["cot"][ok]).max() <= TOL * np.abs(ref["cot"][ok]).max()
+
+
+REC_CASES = [  # (preset, rec_transl, rec_eas): maps that keep at least two feet on the ground in every frame
+    (8, (0, 0, 0), (0, 0, -1.571)),          # main.cpp:38 (commented-out call in the reference's main)
+    (1, (0, 0, 0), (0, 0, -1.571)),
+    (12, (0.3, -0.2, 0), (0, 0, 0.7)),
+    (8, (0, 0, -0.05), (0, 0, 0.3)),         # pushed down: every foot counts as a contact in every frame
+    (24, (0, 0, 0), (0.02, 0.03, 0)),        # slight tilt: contact pattern changes, gravity no longer along the legs' z
+    (9, (0.1, 0.1, 0), (0, 0, 2.5)),
+]
+
+
+@pytest.mark.parametrize("pid,transl,eas", REC_CASES)
+def test_rec_transform(orc, pid, transl, eas):
+    """pergensetup::rec_transform (pergen.cpp:309-335): torso pose and foot targets of every frame mapped rigidly."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    ref = orc.Model(xml).measure_cot(params, n_t, detail=True, rec_transform=(transl, eas))
+    hostlib.set_rec_transform(transl, eas)
+    try:
+        got = hostlib.eval_gaits(xml, params, n_t)
+        pipe = hostlib.eval_gaits_pipe(xml, params, n_t)
+    finally:
+        hostlib.set_rec_transform()
+    assert ref["status"] == 0 and got["status"][0] == 0
+    assert angle_err(got["traj"][0], ref["traj"][:n_t + 4]) < 1e-12
+    for key in ("x", "z", "tau"):
+        assert rel_err(got[key][0], ref[key]) < TOL, key
+    assert abs(got["cot"][0] - ref["cot"]) <= TOL * abs(ref["cot"])
+    assert abs(pipe["cot"][0] - ref["cot"]) <= TOL * abs(ref["cot"])
+    # the map changes the answer (the level-1 weights are axis components in the world frame, ftsolver.cpp:239-246),
+    # so this is not a vacuous check
+    plain = orc.Model(xml).measure_cot(params, n_t)
+    assert abs(plain["cot"] - ref["cot"]) > 1e-6 * abs(ref["cot"])
