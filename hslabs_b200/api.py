@@ -59,6 +59,8 @@ def _load():
     lib.hsl_eval_gaits_detail_host.argtypes = [vp, i64, i32, vp, i32] + [vp] * 10
     lib.hsl_eval_trajectories_host.argtypes = [vp, i64, i32] + [vp] * 9
     lib.hsl_solve_frames_host.argtypes = [vp, i64] + [vp] * 11
+    lib.hsl_solve_forces_host.argtypes = [vp, i64] + [vp] * 9
+    lib.hsl_solve_forces_gait_host.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
     lib.hsl_set_rec_transform.argtypes = [vp, vp, vp]
     lib.hsl_launch_count.argtypes = [vp]
@@ -73,7 +75,7 @@ def exported_symbols():
     """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
-            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_launch_count",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
 
 
@@ -200,6 +202,25 @@ class Model:
                    status=np.empty(f, np.int32))
         _check(_load().hsl_solve_frames_host(self._h, f, *[_p(a) for a in arrs], _p(contacts), _p(out["x"]), _p(out["z"]),
                                              _p(out["tau"]), _p(out["status"])))
+        return out
+
+    def solve_forces(self, pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos, torques):
+        """forcetorquesolver::solve_forces (ftsolver.cpp:331-378): contact forces of all feet for given motor torques."""
+        arrs = [np.ascontiguousarray(a, np.float64) for a in (pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos)]
+        f = arrs[0].shape[0]
+        torques = np.ascontiguousarray(torques, np.float64).reshape(f, self.nmj)
+        out = dict(z=np.empty((f, 3 * self.nf)), status=np.empty(f, np.int32))
+        _check(_load().hsl_solve_forces_host(self._h, f, *[_p(a) for a in arrs], _p(torques), _p(out["z"]), _p(out["status"])))
+        return out
+
+    def solve_forces_gait(self, params, n_t, torques, flags=0):
+        """periodic::solve_contforces_given_torques (periodic.cpp:369-374) on every solved frame of generated gaits:
+        torques [C][n_t][nmj] -> z [C][n_t][3nf]."""
+        params = np.ascontiguousarray(params, np.float64).reshape(-1, HSL_NPARAM)
+        c = params.shape[0]
+        torques = np.ascontiguousarray(torques, np.float64).reshape(c, n_t, self.nmj)
+        out = dict(z=np.empty((c, n_t, 3 * self.nf)), status=np.empty(c, np.int32))
+        _check(_load().hsl_solve_forces_gait_host(self._h, c, n_t, _p(params), flags, _p(torques), _p(out["z"]), _p(out["status"])))
         return out
 
     # ---- device-pointer entry (inputs already in HBM); arguments are integer device addresses

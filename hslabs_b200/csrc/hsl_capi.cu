@@ -394,6 +394,83 @@ int hsl_solve_frames_host(HslModel* m, int64_t F, const double* pos, const doubl
   return HSL_OK;
 }
 
+// ---------------------------------------------------------------- forces from torques (hsl_forces.h)
+int hsl_solve_forces_host(HslModel* m, int64_t F, const double* pos, const double* jpos, const double* jzaxis, const double* mom_rate,
+                          const double* ang_mom_rate, const double* fpos, const double* torques, double* z, int32_t* status) {
+  if (!m || F < 1 || !pos || !jpos || !jzaxis || !mom_rate || !ang_mom_rate || !fpos || !torques || !z)
+    return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const size_t nb = sizeof(double) * F * P.n * 3, fb = sizeof(double) * F * P.nf * 3, tb = sizeof(double) * F * P.nmj, cb = (size_t)F * P.nf;
+  HSL_CUDA(m->in_a.need(5 * nb + fb + tb + cb));
+  char* base = (char*)m->in_a.p;
+  const void* srcs[5] = {pos, jpos, jzaxis, mom_rate, ang_mom_rate};
+  for (int k = 0; k < 5; k++) HSL_CUDA(cudaMemcpyAsync(base + k * nb, srcs[k], nb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(base + 5 * nb, fpos, fb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(base + 5 * nb + fb, torques, tb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemsetAsync(base + 5 * nb + fb + tb, 1, cb, st));  // every foot takes part (ftsolver.cpp:343)
+  HSL_CUDA(m->status.need(sizeof(int32_t) * F));
+  HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * F, st));
+  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * F));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = F; A.n_t = 1; A.n_frames = F;
+  A.f_pos = (const double*)(base); A.f_jpos = (const double*)(base + nb); A.f_jz = (const double*)(base + 2 * nb);
+  A.f_momrate = (const double*)(base + 3 * nb); A.f_angrate = (const double*)(base + 4 * nb);
+  A.f_fpos = (const double*)(base + 5 * nb); A.tau_in = (const double*)(base + 5 * nb + fb);
+  A.f_contacts = (const uint8_t*)(base + 5 * nb + fb + tb);
+  A.status = (int32_t*)m->status.p;
+  A.z = (double*)m->dump_z.p;
+  HSL_CUDA(hsl_launch_forces(P, A, HSL_MODE_FIELDS, st));
+  m->launches += 1;
+  if (status) {
+    HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
+    HSL_CUDA(cudaStreamSynchronize(st));
+  }
+  return fetch_transposed(m, m->dump_z.p, 3 * P.nf, F, z, st);
+}
+
+int hsl_solve_forces_gait_host(HslModel* m, int64_t C, int n_t, const double* params, int flags, const double* torques, double* z,
+                               int32_t* status) {
+  if (!m || C < 1 || n_t < 1 || !params || !torques || !z) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const int64_t nfr = C * n_t;
+  const size_t pbytes = sizeof(double) * HSL_NPARAM * C, tb = sizeof(double) * nfr * P.nmj;
+  HSL_CUDA(m->params.need(pbytes));
+  HSL_CUDA(m->in_b.need(tb));
+  HSL_CUDA(cudaMemcpyAsync(m->params.p, params, pbytes, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(m->in_b.p, torques, tb, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(m->cand.need(sizeof(HslCand) * C));
+  HSL_CUDA(m->ttab.need(sizeof(double) * C * (n_t + 4)));
+  HSL_CUDA(m->status.need(sizeof(int32_t) * C));
+  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * nfr));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.flags = flags & ~HSL_FLAG_REC_TRANSFORM; A.n_frames = nfr;
+  A.cand = (const HslCand*)m->cand.p; A.ttab = (const double*)m->ttab.p;
+  A.status = (int32_t*)m->status.p;
+  A.tau_in = (const double*)m->in_b.p;
+  A.z = (double*)m->dump_z.p;
+  if (m->rec_on) {
+    A.flags |= HSL_FLAG_REC_TRANSFORM;
+    memcpy(A.rec_R, m->rec_R, sizeof A.rec_R);
+    memcpy(A.rec_t, m->rec_t, sizeof A.rec_t);
+  }
+  HSL_CUDA(hsl_launch_setup(P, C, n_t, (const double*)m->params.p, (HslCand*)m->cand.p, (double*)m->ttab.p, A.status, st));
+  HSL_CUDA(hsl_launch_forces(P, A, HSL_MODE_GAIT, st));
+  m->launches += 2;
+  if (status) {
+    HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+    HSL_CUDA(cudaStreamSynchronize(st));
+  }
+  return fetch_transposed(m, m->dump_z.p, 3 * P.nf, nfr, z, st);
+}
+
 // out: [10][n] = hsl_div, a/b, hsl_sqrt(|a|), sqrt(|a|), hsl_atan2(a,b), atan2(a,b), then sin, sin_ref, cos, cos_ref of |a| (|a| <= pi)
 int hsl_math_selftest(int n, const double* a, const double* b, double* out) {
   double *da = nullptr, *db = nullptr, *dout = nullptr;

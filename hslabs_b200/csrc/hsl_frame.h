@@ -72,6 +72,7 @@ struct HslFrameArgs {
   // FIELDS mode inputs, reference dynrecord layout [frame][body][3]
   const double *f_pos, *f_jpos, *f_jz, *f_momrate, *f_angrate, *f_fpos;
   const uint8_t* f_contacts;  // [frame][nf]
+  const double* tau_in;       // [solved frame][nmj] given motor torques (forces-from-torques kernel, hsl_forces.h)
   // per-frame outputs reduced by the finishing kernel
   double *wframe, *fmin_cfz, *fmax_mu;  // [C][n_t]
   int32_t* status;                      // [C], OR of HSL_ST_*

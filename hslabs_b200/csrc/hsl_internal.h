@@ -6,6 +6,7 @@
 #include "hsl_model.h"
 
 cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, int fb, int maxreg, cudaStream_t st);
+cudaError_t hsl_launch_forces(const HslModelPod& M, const HslFrameArgs& A, int mode, cudaStream_t st);
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
                              int32_t* status, cudaStream_t st);
 cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,

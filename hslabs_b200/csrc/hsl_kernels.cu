@@ -13,6 +13,7 @@
 
 #include <cstdio>
 
+#include "hsl_forces.h"
 #include "hsl_frame.h"
 #include "hsl_internal.h"
 #include "hsl_pipe.h"
@@ -95,6 +96,61 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
     for (int k = 0; k < 8; k++) dst[k] = clk[k];
   }
 #endif
+}
+
+// Contact forces of all feet from given motor torques (hsl_forces.h): phases A | B | F1 | F2 | F3, 32 frame slots.
+template <int NF, int MODE>
+__global__ void hsl_forces_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
+  constexpr int FB = 32;
+  extern __shared__ double hsl_smem_raw[];
+  HslSmem<NF, FB, HSL_FORCES_PART> sm;
+  sm.carve(hsl_smem_raw, M.ntrunk);
+  const int role = threadIdx.x / FB;
+  HslSlot sl;
+  sl.s = threadIdx.x % FB;
+  if (MODE == HSL_MODE_FIELDS) {
+    const int64_t g = (int64_t)blockIdx.x * FB + sl.s;
+    sl.valid = g < A.n_frames;
+    sl.i = (int32_t)(sl.valid ? g : A.n_frames - 1);
+    sl.c = sl.i;
+    sl.fo = sl.i;
+    sl.interior = sl.valid;
+  } else {
+    const int per = A.n_t + 4;
+    const int64_t g = (int64_t)blockIdx.x * (FB - 4) + sl.s;
+    sl.c = g / per;
+    sl.i = (int32_t)(g - sl.c * per);
+    sl.valid = sl.c < A.n_cand;
+    if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+    sl.interior = sl.valid && sl.s >= 2 && sl.s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+    sl.fo = sl.c * A.n_t + (sl.i - 2);
+  }
+  HslLegState<true> lst;
+  HslForcesLeg fst;
+  HslTrunkState tst;
+  int bad = 0;
+  if (role < NF) {
+    phase_a_leg<NF, FB, MODE, true>(M, A, sm, sl, role, lst);
+    bad = lst.bad;
+  } else {
+    phase_a_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+  }
+  __syncthreads();
+  if (sl.interior) {
+    if (role < NF) {
+      phase_b_leg<NF, FB, MODE, true>(M, A, sm, sl, role, lst);
+      lst.bad = 0;  // level-1 blocks of phase B are not used here
+      forces_f1_leg<NF, FB, MODE, true>(M, A, sm, sl, role, lst, fst);
+      bad |= lst.bad;
+    } else {
+      phase_b_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+    }
+  }
+  __syncthreads();
+  if (sl.interior && role == NF) bad |= forces_f2_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+  __syncthreads();
+  if (sl.interior && role < NF) forces_f3_leg<NF, FB, MODE, true>(M, A, sm, sl, role, lst, fst);
+  if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
 }
 
 // Persistent, software-pipelined cost-only kernel (schedule and buffer hand-offs in hsl_pipe.h).
@@ -397,6 +453,33 @@ cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int m
     if (mode == HSL_MODE_GAIT && !dump) return launch_gait_fast<4>(M, A, fb, maxreg, st);
     return launch_frames_nf<4, 32>(M, A, mode, dump, st);
   }
+  return cudaErrorInvalidValue;
+}
+
+namespace {
+template <int NF, int MODE>
+cudaError_t launch_forces_t(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
+  constexpr int FB = 32;
+  const size_t smem = (size_t)HslSmem<NF, FB, HSL_FORCES_PART>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
+  auto kern = hsl_forces_kernel<NF, MODE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  int64_t blocks;
+  if (MODE == HSL_MODE_FIELDS) blocks = (A.n_frames + FB - 1) / FB;
+  else {
+    blocks = (A.n_cand * (A.n_t + 4) - 4 + (FB - 4) - 1) / (FB - 4);
+    if (blocks < 1) blocks = 1;
+  }
+  if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  kern<<<(unsigned)blocks, (NF + 1) * FB, smem, st>>>(M, A);
+  return cudaGetLastError();
+}
+}  // namespace
+
+cudaError_t hsl_launch_forces(const HslModelPod& M, const HslFrameArgs& A, int mode, cudaStream_t st) {
+  if (mode != HSL_MODE_GAIT && mode != HSL_MODE_FIELDS) return cudaErrorInvalidValue;
+  if (M.nf == 6) return mode == HSL_MODE_GAIT ? launch_forces_t<6, HSL_MODE_GAIT>(M, A, st) : launch_forces_t<6, HSL_MODE_FIELDS>(M, A, st);
+  if (M.nf == 4) return mode == HSL_MODE_GAIT ? launch_forces_t<4, HSL_MODE_GAIT>(M, A, st) : launch_forces_t<4, HSL_MODE_FIELDS>(M, A, st);
   return cudaErrorInvalidValue;
 }
 

@@ -84,6 +84,18 @@ int hsl_solve_frames_host(HslModel* m, int64_t n_frames, const double* pos, cons
                           const double* mom_rate, const double* ang_mom_rate, const double* fpos, const uint8_t* contacts,
                           double* x, double* z, double* tau, int32_t* status);
 
+/* forcetorquesolver::solve_forces (ftsolver.cpp:331-378): least-squares contact forces of ALL feet for given motor
+ * torques, torso joint force/torque forced to zero, on populated dynrecords (layouts as hsl_solve_frames_host;
+ * torques [n_frames][nmj]; output z [n_frames][3nf]; status [n_frames], HSL_ST_SOLVER when a limb is singular). */
+int hsl_solve_forces_host(HslModel* m, int64_t n_frames, const double* pos, const double* jpos, const double* jzaxis,
+                          const double* mom_rate, const double* ang_mom_rate, const double* fpos, const double* torques,
+                          double* z, int32_t* status);
+/* periodic::solve_contforces_given_torques (periodic.cpp:369-374) for every solved frame of generated gaits:
+ * params [n_cand][13], torques [n_cand][n_t][nmj] (solve order, frames 2..n_t+1), z [n_cand][n_t][3nf],
+ * status [n_cand].  HOST pointers. */
+int hsl_solve_forces_gait_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, const double* torques,
+                               double* z, int32_t* status);
+
 /* pergensetup::set_rec_rotation / set_rec_transform (pergen.cpp:309-320): a rigid map [Rz(psi)Ry(theta)Rx(phi) | transl]
  * applied to every generated frame record (torso pose and foot targets, pergen.cpp:325-335) of the following
  * hsl_eval_gaits* calls on this handle -- the reference copies one rec_transform to every candidate of a sweep

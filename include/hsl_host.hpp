@@ -189,6 +189,16 @@ class forcetorquesolver {
                                 rec->ang_mom_rate.data(), rec->fpos.data(), rec->contacts.data(), x.data(), z.data(), tau_.data(), &status));
     fts_ = x;
   }
+  // ftsolver.cpp:331-378: z = given motor torques (nmj), y = contact forces of all feet (3 nf); the reference's argument names
+  void solve_forces(const dynrecord* rec, const std::vector<double>& z, std::vector<double>& y) {
+    const int nf = model_->number_of_limbs(), nmj = model_->number_of_motor_joints();
+    if ((int)z.size() != nmj) throw error("solve_forces: one torque per motor joint expected");
+    y.assign(3 * nf, 0.0);
+    int32_t status = 0;
+    check(hsl_solve_forces_host(model_->handle(), 1, rec->pos.data(), rec->jpos.data(), rec->jzaxis.data(), rec->mom_rate.data(),
+                                rec->ang_mom_rate.data(), rec->fpos.data(), z.data(), y.data(), &status));
+    if (status & HSL_ST_SOLVER) std::cout << "WARNING: singular limb in solve_forces" << std::endl;
+  }
   const std::vector<double>* get_fts() const { return &fts_; }
   const std::vector<double>& get_motor_torques() const { return tau_; }  // periodic::get_motor_torques
 };
@@ -260,6 +270,21 @@ class periodic {
     if (i < 2 || i > n_t_ + 1) throw error("frame index out of the solved range");
     for (int j = 0; j < nmj_; j++) torques[j] = tau_[(size_t)(i - 2) * nmj_ + j];
     for (int j = 0; j < 3 * nf_; j++) contforces[j] = z_[(size_t)(i - 2) * 3 * nf_ + j];
+  }
+  // periodic.cpp:369-374: contact forces of frame i (2 <= i <= n_t+1) for the given motor torques
+  void solve_contforces_given_torques(int i, double* contforces, double* torques) {
+    if (n_t_ <= 0) throw error("ERROR: no data");
+    if (i < 2 || i > n_t_ + 1) throw error("frame index out of the solved range");
+    double row[HSL_NPARAM];
+    pcp_.to_row(row);
+    // the entry solves every frame of the gait; the other frames get the torques of the forward solve
+    evaluate();
+    std::vector<double> tq(tau_), zz((size_t)n_t_ * 3 * nf_);
+    for (int j = 0; j < nmj_; j++) tq[(size_t)(i - 2) * nmj_ + j] = torques[j];
+    int32_t status = 0;
+    rec_.apply(model_->handle());
+    check(hsl_solve_forces_gait_host(model_->handle(), 1, n_t_, row, flags_, tq.data(), zz.data(), &status));
+    for (int j = 0; j < 3 * nf_; j++) contforces[j] = zz[(size_t)(i - 2) * 3 * nf_ + j];
   }
   const double* get_fts(int i) { evaluate(); return &x_[(size_t)(i - 2) * 6 * n_]; }  // forcetorquesolver::get_fts
   const double* get_traj(int i) { evaluate(); return &traj_[(size_t)i * config_dim_]; }

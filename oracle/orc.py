@@ -35,7 +35,7 @@ def lib():
         _lib.orc_model_rcap.restype = C.c_double
         for name in ("orc_model_free", "orc_model_dims", "orc_model_rcap", "orc_set_ignore_reach", "orc_model_constants",
                      "orc_fk", "orc_ik", "orc_gait_setup", "orc_gait_rec", "orc_measure_cot", "orc_measure_cot_rect", "orc_frame_fields",
-                     "orc_eval_trajectory", "orc_test_dynamics", "orc_measure_cot_sweep", "orc_eval_batch"):
+                     "orc_eval_trajectory", "orc_test_dynamics", "orc_solve_forces_frames", "orc_measure_cot_sweep", "orc_eval_batch"):
             getattr(_lib, name).argtypes = None
     return _lib
 
@@ -190,6 +190,16 @@ class Model:
         cf = np.zeros(3 * self.nf); cf1 = np.zeros(3 * self.nf); tau = np.zeros(self.nmj)
         rc = lib().orc_test_dynamics(self.h, _p(params), C.c_int(n_t), C.c_int(frame), _p(cf), _p(cf1), _p(tau))
         return rc, cf, cf1, tau
+
+    def solve_forces_frames(self, params, n_t, tau):
+        """forcetorquesolver::solve_forces on every solved frame: tau [n_t][nmj] -> contact forces [n_t][3nf]."""
+        params = np.ascontiguousarray(params, np.float64)
+        tau = np.ascontiguousarray(tau, np.float64).reshape(n_t, self.nmj)
+        cf = np.zeros((n_t, 3 * self.nf))
+        rc = lib().orc_solve_forces_frames(self.h, _p(params), C.c_int(n_t), _p(tau), _p(cf))
+        if rc:
+            raise ValueError("solve_forces_frames failed: %d" % rc)
+        return cf
 
     def measure_cot_sweep(self, params, n_t, name, v0, v1, n_val):
         params = np.ascontiguousarray(params, np.float64)

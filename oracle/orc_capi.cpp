@@ -231,6 +231,22 @@ int orc_test_dynamics(void* hv, const double* params, int n_t, int frame, double
   } catch (const std::exception&) { return -1; }
 }
 
+// periodic::solve_contforces_given_torques (periodic.cpp:369-374) on every solved frame 2..n_t+1 of a candidate:
+// tau [n_t][nmj] given motor torques (any values), cf [n_t][3nf] least-squares contact forces of all feet.
+int orc_solve_forces_frames(void* hv, const double* params, int n_t, const double* tau, double* cf) {
+  Model& m = *((Handle*)hv)->model;
+  try {
+    GaitSetup g(m.nlimbs());
+    setup_gait(g, m, params_from(params));
+    GaitEvaluator ev(&m);
+    if (!ev.record_trajectory(&g, n_t)) return 1;
+    ev.compute_dynrecs();
+    ev.compute_dynrec_ders();
+    for (int t = 0; t < n_t; t++) ev.solve_forces(ev.recs[t + 2], tau + (size_t)t * ev.nmj, cf + (size_t)t * 3 * ev.nf);
+    return 0;
+  } catch (const std::exception&) { return -1; }
+}
+
 // measure_cot_sweep (player.cpp:311-321): n_val+1 candidates; vals/cots: [n_val+1].
 int orc_measure_cot_sweep(void* hv, const double* params, int n_t, const char* name, double v0, double v1, int n_val,
                           double* vals, double* cots) {

@@ -29,6 +29,14 @@ int main(int argc, char** argv) {
     std::printf("\ntorques:");
     for (int i = 0; i < nmj; i++) std::printf(" %.17g", torques[i]);
     std::printf("\n");
+    // second half of test_dynamics (playerexperim.cpp:112-117): contact forces back from the motor torques
+    std::vector<double> cf1(3 * nf);
+    per.solve_contforces_given_torques(2, cf1.data(), torques.data());
+    double s = 0;
+    for (int i = 0; i < 3 * nf; i++) { const double d = cf[i] - cf1[i]; s += d * d; }
+    std::printf("s = %.3e\ncf1:", std::sqrt(s));
+    for (int i = 0; i < 3 * nf; i++) std::printf(" %.17g", cf1[i]);
+    std::printf("\n");
     if (argc > 4) player0.record_per_traj(pgs, argv[4]);
     // main.cpp:38: extvec rec_eas (0,0,-1.571); pgs->set_rec_rotation(rec_eas);  -- sweep candidates inherit it (pergen.cpp:446)
     const double rec_eas[3] = {0, 0, -1.571};

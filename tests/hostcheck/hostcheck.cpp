@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../hslabs_b200/csrc/hsl_frame.h"
+#include "../../hslabs_b200/csrc/hsl_forces.h"
 #include "../../hslabs_b200/csrc/hsl_model.h"
 #include "../../hslabs_b200/csrc/hsl_pipe.h"
 
@@ -76,6 +77,69 @@ void emulate(const HslModelPod& M, const HslFrameArgs& A) {
         if (bad[r * FB + s] && sls[s].valid && A.status) A.status[sls[s].c] |= bad[r * FB + s];
   }
 }
+// Serial emulation of hsl_forces_kernel (hsl_forces.h): phases A | B | F1 | F2 | F3.
+template <int NF, int MODE>
+void emulate_forces(const HslModelPod& M, const HslFrameArgs& A) {
+  constexpr int FB = 32;
+  typedef HslSmem<NF, FB, HSL_FORCES_PART> SM;
+  int64_t blocks;
+  if (MODE == HSL_MODE_FIELDS) blocks = (A.n_frames + FB - 1) / FB;
+  else {
+    const int64_t slots = A.n_cand * (A.n_t + 4);
+    blocks = (slots - 4 + (FB - 4) - 1) / (FB - 4);
+    if (blocks < 1) blocks = 1;
+  }
+  std::vector<double> smem((size_t)SM::doubles_per_slot(M.ntrunk) * FB);
+  std::vector<HslLegState<true> > lst((size_t)NF * FB);
+  std::vector<HslForcesLeg> fst((size_t)NF * FB);
+  std::vector<HslTrunkState> tst(FB);
+  std::vector<HslSlot> sls(FB);
+  for (int64_t b = 0; b < blocks; b++) {
+    SM sm;
+    sm.carve(smem.data(), M.ntrunk);
+    std::fill(smem.begin(), smem.end(), NAN);
+    for (int s = 0; s < FB; s++) {
+      HslSlot& sl = sls[s];
+      sl.s = s;
+      if (MODE == HSL_MODE_FIELDS) {
+        const int64_t g = b * FB + s;
+        sl.valid = g < A.n_frames;
+        sl.i = (int32_t)(sl.valid ? g : A.n_frames - 1);
+        sl.c = sl.i; sl.fo = sl.i; sl.interior = sl.valid;
+      } else {
+        const int per = A.n_t + 4;
+        const int64_t g = b * (FB - 4) + s;
+        sl.c = g / per;
+        sl.i = (int32_t)(g - sl.c * per);
+        sl.valid = sl.c < A.n_cand;
+        if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+        sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+        sl.fo = sl.c * A.n_t + (sl.i - 2);
+      }
+    }
+    auto flag = [&](const HslSlot& sl, int bad) { if (bad && sl.valid && A.status) A.status[sl.c] |= bad; };
+    for (int r = 0; r <= NF; r++)
+      for (int s = 0; s < FB; s++) {
+        if (r < NF) { phase_a_leg<NF, FB, MODE, true>(M, A, sm, sls[s], r, lst[r * FB + s]); flag(sls[s], lst[r * FB + s].bad); }
+        else phase_a_trunk<NF, FB, MODE>(M, A, sm, sls[s], tst[s]);
+      }
+    for (int r = 0; r <= NF; r++)
+      for (int s = 0; s < FB; s++) {
+        if (!sls[s].interior) continue;
+        if (r < NF) phase_b_leg<NF, FB, MODE, true>(M, A, sm, sls[s], r, lst[r * FB + s]);
+        else phase_b_trunk<NF, FB, MODE>(M, A, sm, sls[s], tst[s]);
+      }
+    for (int r = 0; r < NF; r++)
+      for (int s = 0; s < FB; s++)
+        if (sls[s].interior) { lst[r * FB + s].bad = 0; forces_f1_leg<NF, FB, MODE, true>(M, A, sm, sls[s], r, lst[r * FB + s], fst[r * FB + s]); flag(sls[s], lst[r * FB + s].bad); }
+    for (int s = 0; s < FB; s++)
+      if (sls[s].interior) flag(sls[s], forces_f2_trunk<NF, FB, MODE>(M, A, sm, sls[s], tst[s]));
+    for (int r = 0; r < NF; r++)
+      for (int s = 0; s < FB; s++)
+        if (sls[s].interior) forces_f3_leg<NF, FB, MODE, true>(M, A, sm, sls[s], r, lst[r * FB + s], fst[r * FB + s]);
+  }
+}
+
 // Serial emulation of hsl_gait_pipe_kernel with `grid` persistent blocks: the two halves of every iteration are run
 // role by role exactly in the order the device schedule allows (see hsl_pipe.h), so a wrong buffer hand-off shows up
 // here as a wrong result.
@@ -246,6 +310,29 @@ int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int
   return 0;
 }
 
+// forces from torques along a generated gait: tau [C][n_t][nmj] -> z [C][n_t][3nf]
+int hc_solve_forces_gait(const char* xml, int64_t C, int n_t, const double* params, int flags, const double* tau, double* z, int32_t* status) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  const int64_t nfr = C * n_t;
+  std::vector<HslCand> cand(C);
+  std::vector<double> ttab((size_t)C * (n_t + 4)), dz((size_t)3 * M.nf * nfr, NAN);
+  std::vector<int32_t> st(C, 0);
+  for (int64_t c = 0; c < C; c++) { setup_candidate(M, params + HSL_NPARAM * c, n_t, cand[c], &ttab[c * (n_t + 4)]); st[c] = cand[c].status; }
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.flags = flags; A.n_frames = nfr;
+  A.cand = cand.data(); A.ttab = ttab.data(); A.status = st.data();
+  A.tau_in = tau; A.z = dz.data();
+  apply_rec(A);
+  if (M.nf == 6) emulate_forces<6, HSL_MODE_GAIT>(M, A); else emulate_forces<4, HSL_MODE_GAIT>(M, A);
+  if (status) memcpy(status, st.data(), sizeof(int32_t) * C);
+  transpose_out(dz, 3 * M.nf, nfr, z);
+  return 0;
+}
+
 int hc_eval_gaits_pipe(const char* xml, int64_t C, int n_t, const double* params, int flags, int fb, int grid, double* cot, double* work,
                        double* min_cfz, double* max_mu, int32_t* status) {
   HslModelPod M;
@@ -312,6 +399,27 @@ int hc_solve_frames(const char* xml, int64_t F, const double* pos, const double*
   transpose_out(dx, 6 * M.n, F, x);
   transpose_out(dz, 3 * M.nf, F, z);
   transpose_out(dtau, M.nmj, F, tau);
+  return 0;
+}
+
+// forcetorquesolver::solve_forces on populated dynrecords: tau [F][nmj] -> z [F][3nf]
+int hc_solve_forces_fields(const char* xml, int64_t F, const double* pos, const double* jpos, const double* jz, const double* mom_rate,
+                           const double* ang_rate, const double* fpos, const double* tau, double* z, int32_t* status) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  std::vector<double> dz((size_t)3 * M.nf * F, NAN);
+  std::vector<uint8_t> con((size_t)M.nf * F, 1);
+  std::vector<int32_t> st(F, 0);
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = F; A.n_t = 1; A.n_frames = F;
+  A.f_pos = pos; A.f_jpos = jpos; A.f_jz = jz; A.f_momrate = mom_rate; A.f_angrate = ang_rate; A.f_fpos = fpos; A.f_contacts = con.data();
+  A.status = st.data(); A.z = dz.data(); A.tau_in = tau;
+  if (M.nf == 6) emulate_forces<6, HSL_MODE_FIELDS>(M, A); else emulate_forces<4, HSL_MODE_FIELDS>(M, A);
+  if (status) memcpy(status, st.data(), sizeof(int32_t) * F);
+  transpose_out(dz, 3 * M.nf, F, z);
   return 0;
 }
 }

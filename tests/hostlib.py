@@ -75,6 +75,29 @@ def solve_frames(xml, f):
     return out
 
 
+def solve_forces_gait(xml, params, n_t, tau, flags=0):
+    """Emulation of the forces-from-torques kernel along generated gaits: tau [C][n_t][nmj] -> z [C][n_t][3nf]."""
+    params = np.ascontiguousarray(params, np.float64).reshape(-1, 13)
+    c = params.shape[0]
+    d = model_dims(xml)
+    tau = np.ascontiguousarray(tau, np.float64).reshape(c, n_t, d["nmj"])
+    z = np.zeros((c, n_t, 3 * d["nf"])); status = np.zeros(c, np.int32)
+    rc = lib().hc_solve_forces_gait(xml.encode(), C.c_int64(c), C.c_int(n_t), _p(params), C.c_int(flags), _p(tau), _p(z), _p(status))
+    assert rc == 0, rc
+    return dict(z=z, status=status)
+
+
+def solve_forces_fields(xml, f, tau):
+    d = model_dims(xml)
+    nfr = f["pos"].shape[0]
+    arrs = [np.ascontiguousarray(f[k], np.float64) for k in ("pos", "jpos", "jzaxis", "mom_rate", "ang_mom_rate", "fpos")]
+    tau = np.ascontiguousarray(tau, np.float64).reshape(nfr, d["nmj"])
+    z = np.zeros((nfr, 3 * d["nf"])); status = np.zeros(nfr, np.int32)
+    rc = lib().hc_solve_forces_fields(xml.encode(), C.c_int64(nfr), *[_p(a) for a in arrs], _p(tau), _p(z), _p(status))
+    assert rc == 0, rc
+    return dict(z=z, status=status)
+
+
 def eval_gaits_pipe(xml, params, n_t, flags=0, fb=64, grid=3):
     """Serial emulation of the persistent pipelined cost-only kernel."""
     params = np.ascontiguousarray(params, np.float64).reshape(-1, 13)

@@ -81,8 +81,21 @@ def test_no_cpu_fallback(hsl):
     if torch.cuda.is_available():
         pytest.skip("CUDA device present")
     m = hsl.Model(hsl.model_path("hexapod"))
+    p = hsl.make_params(torso_pos=(0, 0, -.1))
     with pytest.raises(hsl.HslError, match="CUDA"):
-        m.eval_gaits(hsl.make_params(torso_pos=(0, 0, -.1)), 20)
+        m.eval_gaits(p, 20)
+    # every compute entry of the Python mirror: the wrapper code runs up to the C call, which must refuse
+    n, nf, nmj = m.n, m.nf, m.nmj
+    z3 = np.zeros((2, n, 3)); zf = np.zeros((2, nf, 3))
+    m.set_rec_transform((0, 0, 0), (0, 0, 0.1))
+    m.set_rec_transform()
+    for call in (lambda: m.eval_gaits_detail(p, 20),
+                 lambda: m.eval_trajectories(np.zeros((1, 25, m.config_dim)), 0.1, 20),
+                 lambda: m.solve_frames(z3, z3, z3, z3, z3, zf, np.ones((2, nf), np.uint8)),
+                 lambda: m.solve_forces(z3, z3, z3, z3, z3, zf, np.zeros((2, nmj))),
+                 lambda: m.solve_forces_gait(p, 20, np.zeros((1, 20, nmj)))):
+        with pytest.raises(hsl.HslError, match="CUDA"):
+            call()
 
 
 def test_preset_parser_matches_oracle(hsl, orc):

@@ -43,6 +43,12 @@ def test_main_like_sequence(demo, orc, pid, tmp_path):
     tq = np.array([float(v) for v in re.search(r"torques:(.*)", out.stdout).group(1).split()])
     assert np.abs(cfz - ref["z"][0].reshape(-1, 3)[:, 2]).max() <= 1e-9 * np.abs(ref["z"]).max()
     assert np.abs(tq - ref["tau"][0]).max() <= 1e-9 * np.abs(ref["tau"]).max()
+    # second half of test_dynamics: contact forces recovered from the torques (exact with >= 3 contacts, i.e. hexapod)
+    cf1 = np.array([float(v) for v in re.search(r"cf1:(.*)", out.stdout).group(1).split()])
+    ref_cf1 = m.solve_forces_frames(params, 20, ref["tau"])[0]
+    assert np.abs(cf1 - ref_cf1).max() <= 1e-9 * np.abs(ref["z"]).max()
+    if m.nf == 6:
+        assert float(re.search(r"s = (\S+)", out.stdout).group(1)) < 1e-9
     # set_rec_rotation (main.cpp:38, pergen.cpp:309-313) on the candidate and on the sweep built from it
     rec = ((0, 0, 0), (0, 0, -1.571))
     rot = float(re.search(r"rotated COT = (\S+)", out.stdout).group(1))

@@ -293,3 +293,36 @@ def test_rec_transform(hsl, orc, pid, transl, eas):
     assert abs(plain - ref["cot"]) > 1e-6 * abs(ref["cot"])
     m.set_rec_transform()
     assert abs(m.eval_gaits(params, n_t)["cot"][0] - plain) <= 1e-12 * abs(plain)
+
+
+@pytest.mark.parametrize("pid", [8, 1, 24, 12, 9, 26])
+def test_forces_from_torques(hsl, orc, pid):
+    """forcetorquesolver::solve_forces / periodic::solve_contforces_given_torques (ftsolver.cpp:331-378,
+    periodic.cpp:369-374) through the C ABI, gait and dynrecord entries, consistent and arbitrary torques."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 37
+    om = orc.Model(xml)
+    m = hsl.Model(xml)
+    fwd = om.measure_cot(params, n_t, detail=True)
+    fields = om.frame_fields(params, n_t)
+    rng = np.random.default_rng(pid)
+    for tau in (fwd["tau"], fwd["tau"] + rng.normal(0, 1.0, fwd["tau"].shape)):
+        ref = om.solve_forces_frames(params, n_t, tau)
+        got = m.solve_forces_gait(params, n_t, tau)
+        assert got["status"][0] == 0
+        assert rel_err(got["z"][0], ref) < TOL
+        got2 = m.solve_forces(fields["pos"], fields["jpos"], fields["jzaxis"], fields["mom_rate"], fields["ang_mom_rate"], fields["fpos"], tau)
+        assert (got2["status"] == 0).all()
+        assert rel_err(got2["z"], ref) < TOL
+    # round trip on the device alone (test_dynamics): forward solve -> torques -> contact forces, frames with >= 3 contacts
+    det = m.eval_gaits_detail(params, n_t)
+    back = m.solve_forces_gait(params, n_t, det["tau"][0])["z"][0]
+    sel = det["contacts"][0].sum(axis=1) >= 3
+    if sel.any():
+        assert np.abs(back[sel] - det["z"][0][sel]).max() < 1e-9 * np.abs(det["z"]).max()
+    # a batch of two candidates with different torques keeps them apart
+    p2 = np.stack([params, params]); t2 = np.stack([fwd["tau"], fwd["tau"] * 0.5])
+    zb = m.solve_forces_gait(p2, n_t, t2)["z"]
+    assert rel_err(zb[0], om.solve_forces_frames(params, n_t, t2[0])) < TOL
+    assert rel_err(zb[1], om.solve_forces_frames(params, n_t, t2[1])) < TOL

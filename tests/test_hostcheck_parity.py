@@ -165,3 +165,31 @@ def test_rec_transform(orc, pid, transl, eas):
     # so this is not a vacuous check
     plain = orc.Model(xml).measure_cot(params, n_t)
     assert abs(plain["cot"] - ref["cot"]) > 1e-6 * abs(ref["cot"])
+
+
+@pytest.mark.parametrize("pid", [8, 1, 24, 12, 9, 26])
+def test_forces_from_torques(orc, pid):
+    """forcetorquesolver::solve_forces (ftsolver.cpp:331-378): the 6-parameter pinned-feet residual space + one 3x3
+    solve per limb against the oracle's rectangular QR least squares -- for the torques of the forward solve
+    (test_dynamics, playerexperim.cpp:95-121) and for arbitrary (inconsistent) torques, gait and dynrecord entries."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    n_t = 20
+    om = orc.Model(xml)
+    fwd = om.measure_cot(params, n_t, detail=True)
+    rng = np.random.default_rng(pid)
+    fields = om.frame_fields(params, n_t)
+    for tau in (fwd["tau"], fwd["tau"] + rng.normal(0, 1.0, fwd["tau"].shape)):
+        ref = om.solve_forces_frames(params, n_t, tau)
+        got = hostlib.solve_forces_gait(xml, params, n_t, tau)
+        assert got["status"][0] == 0
+        assert rel_err(got["z"][0], ref) < TOL
+        got2 = hostlib.solve_forces_fields(xml, fields, tau)
+        assert (got2["status"] == 0).all()
+        assert rel_err(got2["z"], ref) < TOL
+    # test_dynamics property: with >= 3 feet on the ground the forward solve's torques give its contact forces back
+    k = fields["contacts"].sum(axis=1)
+    back = hostlib.solve_forces_gait(xml, params, n_t, fwd["tau"])["z"][0]
+    sel = k >= 3
+    if sel.any():
+        assert np.abs(back[sel] - fwd["z"][sel]).max() < 1e-9 * np.abs(fwd["z"]).max()
