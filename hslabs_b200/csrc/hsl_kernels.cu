@@ -18,6 +18,10 @@
 #include "hsl_internal.h"
 #include "hsl_pipe.h"
 
+// Block-wide barrier usable from role-divergent code: bar.sync counts arriving warps, it does not care which
+// instruction they arrive from (__syncthreads() may not be placed in divergent code).
+#define HSL_BLOCK_SYNC() asm volatile("bar.sync 0;" ::: "memory")
+
 template <int NF, int FB, int MODE, bool DUMP, int MAXREG>
 __global__ void __maxnreg__(MAXREG)
 hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
@@ -57,38 +61,46 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
 #else
 #define HSL_STAMP()
 #endif
-  HslLegState<DUMP> lst;
-  HslTrunkState tst;
   int bad = 0;
+  // The two kinds of role run separate instruction streams that meet at the same four block barriers.  Whole warps
+  // share a role (FB is a multiple of 32), so each warp executes every bar.sync exactly once per phase; keeping the
+  // streams apart keeps the limbs' phase B -> D state out of the register allocation of the trunk's phase C.
   HSL_STAMP();
   if (role < NF) {
+    HslLegState<DUMP> lst;
     phase_a_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
+    if (sl.interior) phase_b_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
     bad = lst.bad;
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
+    if (sl.interior) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
   } else {
+    HslTrunkState tst;
     phase_a_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
+    if (sl.interior) phase_b_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
+    if (sl.interior) bad |= phase_c_trunk<NF, FB, MODE, DUMP>(M, A, sm, sl, tst);
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    HSL_STAMP();
+    HSL_BLOCK_SYNC();
+    if (sl.interior) phase_e_trunk<NF, FB>(A, sm, sl);
+    HSL_STAMP();
   }
-  HSL_STAMP();
-  __syncthreads();
-  HSL_STAMP();
-  if (sl.interior) {
-    if (role < NF) {
-      phase_b_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
-      bad |= lst.bad;
-    } else {
-      phase_b_trunk<NF, FB, MODE>(M, A, sm, sl, tst);
-    }
-  }
-  HSL_STAMP();
-  __syncthreads();
-  HSL_STAMP();
-  if (sl.interior && role == NF) bad |= phase_c_trunk<NF, FB, MODE, DUMP>(M, A, sm, sl, tst);
-  HSL_STAMP();
-  __syncthreads();
-  HSL_STAMP();
-  if (sl.interior && role < NF) phase_d_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
-  __syncthreads();
-  if (sl.interior && role == NF) phase_e_trunk<NF, FB>(A, sm, sl);
-  HSL_STAMP();
   if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
 #ifdef HSL_PHASE_CLOCKS
   if (A.phase_clk && (threadIdx.x & 31) == 0) {
@@ -183,10 +195,7 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
   sm.carve(hsl_smem_raw, M.ntrunk);
   const int role = threadIdx.x / FB;
   const int s = threadIdx.x % FB;
-  // slots of the two previous tiles of this block (p1 = t-1, p2 = t-2)
-  bool p1_int = false, p2_int = false;
-  int64_t p1_fo = 0, p2_fo = 0, p1_c = 0;
-  HslTrunkState tst;
+  // p1 / p2 below: slots of the two previous tiles of this block (t-1, t-2)
 #ifdef HSL_PHASE_CLOCKS
   long long acc[4] = {0, 0, 0, 0};
   long long t0c = 0, t1c = 0;
@@ -198,15 +207,45 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
 #define HSL_T0()
 #define HSL_T1(k)
 #endif
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
-    HslLegState<false> lst;
-    int bad = 0;
-    HSL_T0();
-    if (role < NF) {
+  // Limb and trunk warps run separate loops that meet at the same two block barriers per tile (see
+  // HSL_BLOCK_SYNC): neither role's live state enters the other's register allocation.
+  if (role < NF) {
+    bool p1_int = false;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
+      HslLegState<false> lst;
+      HSL_T0();
       phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
-      bad = lst.bad;
-    } else {
+      int bad = lst.bad;
+      HSL_T1(0);
+      HSL_BLOCK_SYNC();
+      HSL_T1(1);
+      if (p1_int) pipe_d_leg<NF, FB>(sm, s, role);
+      if (sl.interior) {
+        phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
+        pipe_store_dstate<NF, FB>(sm, s, role, lst);
+        bad |= lst.bad;
+      }
+      if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
+      HSL_T1(2);
+      HSL_BLOCK_SYNC();
+      HSL_T1(3);
+#ifdef HSL_PHASE_CLOCKS
+      first_tile = false;
+#endif
+      p1_int = sl.interior;
+    }
+    // drain: [trunk E(T-1), C(T)] | D(T) | [trunk E(T)]
+    HSL_BLOCK_SYNC();
+    if (p1_int) pipe_d_leg<NF, FB>(sm, s, role);
+    HSL_BLOCK_SYNC();
+  } else {
+    bool p1_int = false, p2_int = false;
+    int64_t p1_fo = 0, p2_fo = 0, p1_c = 0;
+    HslTrunkState tst;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
+      HSL_T0();
       if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
       // C(t-1) needs the trunk wrench kept in tst.F0/T0 since B'(t-1); A'(t) only writes tst.R0/t0
       if (p1_int) {
@@ -216,29 +255,29 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
         if (tb && A.status) atomicOr(&A.status[p1_c], tb);
       }
       phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
-    }
-    HSL_T1(0);
-    __syncthreads();
-    HSL_T1(1);
-    if (role < NF) {
-      if (p1_int) pipe_d_leg<NF, FB>(sm, s, role);
-      if (sl.interior) {
-        phase_b_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
-        pipe_store_dstate<NF, FB>(sm, s, role, lst);
-        bad |= lst.bad;
-      }
-      if (bad && sl.valid && A.status) atomicOr(&A.status[sl.c], bad);
-    } else if (sl.interior) {
-      phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
-    }
-    HSL_T1(2);
-    __syncthreads();
-    HSL_T1(3);
+      HSL_T1(0);
+      HSL_BLOCK_SYNC();
+      HSL_T1(1);
+      if (sl.interior) phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
+      HSL_T1(2);
+      HSL_BLOCK_SYNC();
+      HSL_T1(3);
 #ifdef HSL_PHASE_CLOCKS
-    first_tile = false;
+      first_tile = false;
 #endif
-    p2_int = p1_int; p2_fo = p1_fo;
-    p1_int = sl.interior; p1_fo = sl.fo; p1_c = sl.c;
+      p2_int = p1_int; p2_fo = p1_fo;
+      p1_int = sl.interior; p1_fo = sl.fo; p1_c = sl.c;
+    }
+    if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
+    if (p1_int) {
+      HslSlot ps;
+      ps.s = s; ps.fo = p1_fo; ps.c = p1_c; ps.i = 2; ps.valid = true; ps.interior = true;
+      const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
+      if (tb && A.status) atomicOr(&A.status[p1_c], tb);
+    }
+    HSL_BLOCK_SYNC();
+    HSL_BLOCK_SYNC();
+    if (p1_int) pipe_e_trunk<NF, FB>(A, sm, s, p1_fo);
   }
 #ifdef HSL_PHASE_CLOCKS
   if (A.phase_clk && (threadIdx.x & 31) == 0) {
@@ -247,20 +286,6 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
     dst[4] = (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
   }
 #endif
-  // drain: E(T-1), C(T) | D(T) | E(T)
-  if (role == NF) {
-    if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
-    if (p1_int) {
-      HslSlot ps;
-      ps.s = s; ps.fo = p1_fo; ps.c = p1_c; ps.i = 2; ps.valid = true; ps.interior = true;
-      const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
-      if (tb && A.status) atomicOr(&A.status[p1_c], tb);
-    }
-  }
-  __syncthreads();
-  if (role < NF && p1_int) pipe_d_leg<NF, FB>(sm, s, role);
-  __syncthreads();
-  if (role == NF && p1_int) pipe_e_trunk<NF, FB>(A, sm, s, p1_fo);
 }
 
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
