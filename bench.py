@@ -212,8 +212,9 @@ def main():
     frames_per_step = world * n_cand * n_t
     value = frames_per_step * args.steps / (ms_total * 1e-3)
 
-    # kernel-only timing of the dominant kernel (hsl_frames_kernel) for the roofline: the three launches of a step
-    # are timed together here; the setup/finish kernels are < 1 % (profiles/).
+    # kernel-only timing of the dominant kernel (hsl_gait_pipe_kernel, the default cost-only variant for six-limbed
+    # models) for the roofline: the three launches of a step are timed together here; the setup/finish kernels are
+    # < 3 % (profiles/r01_launches.txt).
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     for a, b in kev:
         flush.fill_(2.0)
@@ -265,9 +266,9 @@ def main():
                     "d2h_bytes_per_step": int(n_cand * (4 * 8 + 4))},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / dfma_tf if dfma_tf else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of hsl_frames_kernel, one ncu --set full capture of
-                         # this configuration (profiles/r01_ncu_frames_kernel_summary.txt); null for other configurations
-                         "traffic": 13523200 if (n_cand, n_t, MODEL) == (4096, 256, "hexapod") else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of hsl_gait_pipe_kernel, one ncu --set full capture of
+                         # this configuration (profiles/r01_ncu_pipe_kernel_summary.txt); null for other configurations
+                         "traffic": 11816704 if (n_cand, n_t, MODEL) == (4096, 256, "hexapod") and not args.fb else None,
                          "peak_source": "measured live: register-resident DFMA probe kernel (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_frame": flops_per_frame, "kernel_ms": k_ms,
                          "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,

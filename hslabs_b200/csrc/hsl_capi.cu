@@ -98,10 +98,11 @@ int hsl_model_load_xml(const char* xml_path, HslModel** out) {
   for (int l = 0; l < m->pod.nf; l++)
     for (int h = 0; h < 3; h++) mass[m->pod.limb[l].h[h].body] = m->pod.limb[l].h[h].mass;
   for (int i = 0; i < m->pod.n; i++) m->total_mass += mass[i];
-  // default kernel variant (tools/tune.py): four-limbed models fit three 32-slot blocks per SM, six-limbed ones run
-  // best with one 64-slot block
+  // default kernel variant (tools/tune.py, profiles/r01_optimisation_log.md): four-limbed models fit three 32-slot
+  // blocks per SM with the plain kernel; six-limbed ones run best with the persistent pipelined kernel, one 64-slot
+  // block per SM
   m->fb = (m->pod.nf <= 4) ? 32 : 64;
-  m->maxreg = 128;
+  m->maxreg = (m->pod.nf <= 4) ? 128 : 1;
   *out = m;
   return HSL_OK;
 }
