@@ -149,6 +149,9 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; stdout must carry the one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     n_cand, n_t = args.candidates, args.frames
