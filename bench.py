@@ -98,6 +98,29 @@ def cpu_port_rate(params, n_t, nthreads, budget_s=15.0):
     return n * n_t / dt, n, dt, ok
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout must carry the one JSON line and nothing else, but native libraries (NCCL prints its version banner at
+    NCCL_DEBUG=VERSION/WARN) write to fd 1 directly: keep a private duplicate of fd 1 for the result line and point
+    fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -118,7 +141,7 @@ def run_reference(args):
             "config": {"workload": "hexapod.xml, %d candidates x %d frames per GPU (BASELINE configs[1]); CPU arm runs a bounded sample" % (N_CAND, N_T)},
             "cpu_baseline": {"value": v, "unit": "frame solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "frame solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def main():
@@ -133,6 +156,7 @@ def main():
     ap.add_argument("--maxreg", type=int, default=128, help="register cap per thread of the cost-only kernel variant")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -149,9 +173,6 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
-        # NCCL prints its version banner to stdout at NCCL_DEBUG=VERSION; stdout must carry the one JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     n_cand, n_t = args.candidates, args.frames
@@ -283,7 +304,7 @@ def main():
             rate, n, dt, ok = cpu_port_rate(params, n_t, cores, budget_s=15.0)
             line["cpu_baseline"] = {"value": rate, "unit": "frame solves/s", "cores": cores, "kind": "port",
                                     "sample": "%d candidates x %d frames on %d threads (%.1f s)" % (n, n_t, cores, dt)}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
