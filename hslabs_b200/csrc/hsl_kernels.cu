@@ -1,8 +1,12 @@
 // sm_100a kernels of the gait-evaluation hot path.
 //
-//   hsl_setup_kernel   one thread per candidate: candidate constants + frame-time table   (a1, a4)
-//   hsl_frames_kernel  one thread per (frame, role): phases A-E of hsl_frame.h             (a2-a14)
-//   hsl_finish_kernel  one warp per candidate: work = sum_f (power_f * dt), COT, statistics (a14)
+//   hsl_setup_kernel      one thread per candidate: candidate constants + frame-time table   (a1, a4)
+//   hsl_frames_kernel     one thread per (frame, role): phases A-E of hsl_frame.h             (a2-a14)
+//   hsl_gait_pipe_kernel  persistent, software-pipelined form of the cost-only path (hsl_pipe.h); default for
+//                         six-limbed models
+//   hsl_forces_kernel     contact forces of all feet from given motor torques (hsl_forces.h)  (a15)
+//   hsl_finish_kernel     one warp per candidate: work = sum_f (power_f * dt), COT, statistics (a14)
+//   hsl_argmin_kernel     selection after the all-gather of the costs
 //
 // Block layout of hsl_frames_kernel: FB frame slots x (NF+1) roles, thread = role*FB + slot, so a warp
 // is one role over 32 consecutive frames of (normally) one candidate.  Blocks overlap by 4 slots: the

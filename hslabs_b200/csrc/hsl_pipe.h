@@ -8,7 +8,7 @@
 //
 //               | first half of iteration t  (until barrier 1) | second half (until barrier 2)
 //   limb warps  | A(t): gait, IK, FK                            | D(t-1): contact force, torques, power ; B(t)
-//   trunk warps | E(t-2) ; A'(t) ; C(t-1): 6x6 solve            | B'(t)
+//   trunk warps | E(t-2) ; C(t-1): 6x6 solve ; A'(t)            | B'(t)
 //
 // Phase D needs 24 doubles of limb state from phase B of the same frame; instead of keeping them in registers across
 // a whole tile they are parked in shared memory: 12 in `dstate` (written at the end of B(t), read back in D(t) one
