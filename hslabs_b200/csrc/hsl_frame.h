@@ -59,6 +59,11 @@
 #define HSL_MODE_FIELDS 2  // per-frame dynrec fields -> x,z,tau (a8-a13)
 
 #define HSL_FLAG_IGNORE_REACH 1
+// Hinge-axis patterns a kernel can be specialised for (all limbs of the model alike, every hinge axis-aligned):
+// hip about the parent's y (yxx limbs: myant, hexapod) or z (zxx: spider), knee and ankle about x.
+#define HSL_AXP_GENERIC 0
+#define HSL_AXP_YXX 1
+#define HSL_AXP_ZXX 2
 #define HSL_FLAG_REC_TRANSFORM 2  // internal: set by the library when hsl_set_rec_transform is active
 
 struct HslFrameArgs {
@@ -255,10 +260,12 @@ HSL_HD void foot_target(const HslCandView& cd, double t, double* p) {
 // so the hot path needs no inverse trigonometry at all; the angles themselves (ang != nullptr) are only
 // evaluated when a trajectory dump is requested.
 //   q0 = -phi,  q1 = -theta + beta,  q2 = -(beta + gamma)                       (lik.cpp:181,220)
+// AXP: hinge-axis pattern of the model known at compile time (see HSL_AXP_* below), 0 = read L.kind at run time.
+template <int AXP = 0>
 HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, double* cq, double* sq, double* ang) {
   const double l0 = L.ls[0], l1 = L.ls[1], l2 = L.ls[2];
   const int s0 = L.ysign, s1 = 2 * (L.bend != 0) - 1;
-  const bool yxx = (L.kind == HSL_IK_YXX);
+  const bool yxx = (AXP == 0) ? (L.kind == HSL_IK_YXX) : (AXP == HSL_AXP_YXX);
   const double zoff = yxx ? pl[2] - s0 * l0 : pl[2] + l0;
   const double rho2 = pl[0] * pl[0] + pl[1] * pl[1];
   const double l2sq = rho2 + zoff * zoff;
@@ -381,6 +388,22 @@ HSL_HD void rot_about_axis(const double* Rp, double cs, double sn, double* Rb) {
     Rb[3 * C + i] = Rp[3 * C + i] * cs - Rp[3 * B + i] * sn;
   }
 }
+// Hinge known at compile time to turn about +-(coordinate axis AX of the parent frame) with the joint at the body
+// origin: same arithmetic as the aligned branch of hinge_fk below, without its run-time dispatch (the three-way
+// branch costs merge moves for the nine entries of Rb and keeps the scheduler from overlapping consecutive hinges).
+template <int AX>
+HSL_HD void hinge_fk_aligned(const HslHinge& H, double cs, double sn, const double* Rp, const double* tp, double* Rb, double* tb,
+                             double* jpos, double* axis, double* com, double* ust) {
+  m3_affine(Rp, H.tjp, tp, jpos);
+  const double sg = (H.aligned > 0) ? 1.0 : -1.0, s2 = sg * sn;
+  rot_about_axis<AX>(Rp, cs, s2, Rb);
+  axis[0] = sg * Rp[3 * AX]; axis[1] = sg * Rp[3 * AX + 1]; axis[2] = sg * Rp[3 * AX + 2];
+  tb[0] = jpos[0]; tb[1] = jpos[1]; tb[2] = jpos[2];
+  m3_affine(Rb, H.com, tb, com);
+  ust[0] = (Rb[5] - Rb[7]) / 2;
+  ust[1] = (Rb[6] - Rb[2]) / 2;
+  ust[2] = (Rb[1] - Rb[3]) / 2;
+}
 HSL_HD void hinge_fk(const HslHinge& H, double cs, double sn, const double* Rp, const double* tp, double* Rb, double* tb,
                      double* jpos, double* axis, double* com, double* ust) {
   m3_affine(Rp, H.tjp, tp, jpos);
@@ -415,7 +438,7 @@ HSL_HD void hinge_fk(const HslHinge& H, double cs, double sn, const double* Rp, 
   ust[2] = (Rb[1] - Rb[3]) / 2;
 }
 
-template <int NF, int FB, int MODE, bool DUMP, class SM>
+template <int NF, int FB, int MODE, bool DUMP, int AXP = 0, class SM>
 HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
                         HslLegState<DUMP>& st) {
   const HslLimb& L = M.limb[limb];
@@ -465,7 +488,7 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     for (int k = 0; k < 3; k++) pl[k] = Rj0[3 * k] * e[0] + Rj0[3 * k + 1] * e[1] + Rj0[3 * k + 2] * e[2];
     (void)Rh;
     const bool want_angles = DUMP && A.q_out != nullptr;
-    if (!limb_ik(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, cq, sq, want_angles ? qa : nullptr)) st.bad |= HSL_ST_UNREACHABLE;
+    if (!limb_ik<AXP>(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, cq, sq, want_angles ? qa : nullptr)) st.bad |= HSL_ST_UNREACHABLE;
   } else {  // HSL_MODE_TRAJ
     const double* qrow = A.traj + (sl.c * (A.n_t + 5) + sl.i) * M.config_dim;
 #pragma unroll
@@ -484,7 +507,10 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
 #pragma unroll
   for (int h = 0; h < 3; h++) {
     double ust[3];
-    hinge_fk(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    if (AXP == 0) hinge_fk(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else if (h > 0) hinge_fk_aligned<0>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else if (AXP == HSL_AXP_YXX) hinge_fk_aligned<1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else hinge_fk_aligned<2>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       sm.pos[((3 * limb + h) * 3 + k) * FB + sl.s] = st.pos[h][k];

@@ -26,7 +26,7 @@
 // instruction they arrive from (__syncthreads() may not be placed in divergent code).
 #define HSL_BLOCK_SYNC() asm volatile("bar.sync 0;" ::: "memory")
 
-template <int NF, int FB, int MODE, bool DUMP, int MAXREG>
+template <int NF, int FB, int MODE, bool DUMP, int MAXREG, int AXP = HSL_AXP_GENERIC>
 __global__ void __maxnreg__(MAXREG)
 hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
   extern __shared__ double hsl_smem_raw[];
@@ -72,7 +72,7 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
   HSL_STAMP();
   if (role < NF) {
     HslLegState<DUMP> lst;
-    phase_a_leg<NF, FB, MODE, DUMP>(M, A, sm, sl, role, lst);
+    phase_a_leg<NF, FB, MODE, DUMP, AXP>(M, A, sm, sl, role, lst);
     HSL_STAMP();
     HSL_BLOCK_SYNC();
     HSL_STAMP();
@@ -191,7 +191,7 @@ HSL_HD HslSlot hsl_pipe_slot(const HslFrameArgs& A, int64_t tile, int s) {
   return sl;
 }
 
-template <int NF, int FB>
+template <int NF, int FB, int AXP = HSL_AXP_GENERIC>
 __global__ void __maxnreg__(128)
 hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A, const int64_t n_tiles) {
   extern __shared__ double hsl_smem_raw[];
@@ -219,7 +219,7 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
       const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
       HslLegState<false> lst;
       HSL_T0();
-      phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, sl, role, lst);
+      phase_a_leg<NF, FB, HSL_MODE_GAIT, false, AXP>(M, A, sm, sl, role, lst);
       int bad = lst.bad;
       HSL_T1(0);
       HSL_BLOCK_SYNC();
@@ -405,10 +405,28 @@ __global__ void hsl_math_selftest_kernel(int n, const double* __restrict__ a, co
 
 // ------------------------------------------------------------------ launchers
 namespace {
-template <int NF, int FB, int MODE, bool DUMP, int MAXREG = 255>
+// Hinge-axis pattern shared by every limb of the model, or HSL_AXP_GENERIC (kernels specialised for a pattern skip
+// the run-time dispatch on the hinge axes; hsl_frame.h).
+int axis_pattern(const HslModelPod& M) {
+  int pat = -1;
+  for (int l = 0; l < M.nf; l++) {
+    const HslLimb& L = M.limb[l];
+    const int a0 = L.h[0].aligned < 0 ? -L.h[0].aligned : L.h[0].aligned;
+    const int a1 = L.h[1].aligned < 0 ? -L.h[1].aligned : L.h[1].aligned;
+    const int a2 = L.h[2].aligned < 0 ? -L.h[2].aligned : L.h[2].aligned;
+    int p = HSL_AXP_GENERIC;
+    if (a1 == 1 && a2 == 1 && a0 == 2 && L.kind == HSL_IK_YXX) p = HSL_AXP_YXX;
+    if (a1 == 1 && a2 == 1 && a0 == 3 && L.kind == HSL_IK_ZXX) p = HSL_AXP_ZXX;
+    if (pat < 0) pat = p;
+    if (p != pat) return HSL_AXP_GENERIC;
+  }
+  return pat < 0 ? HSL_AXP_GENERIC : pat;
+}
+
+template <int NF, int FB, int MODE, bool DUMP, int MAXREG = 255, int AXP = HSL_AXP_GENERIC>
 cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
   const size_t smem = (size_t)HslSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
-  auto kern = hsl_frames_kernel<NF, FB, MODE, DUMP, MAXREG>;
+  auto kern = hsl_frames_kernel<NF, FB, MODE, DUMP, MAXREG, AXP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   int64_t blocks;
@@ -431,10 +449,10 @@ cudaError_t launch_frames_nf(const HslModelPod& M, const HslFrameArgs& A, int mo
 }
 }  // namespace
 
-template <int NF, int FB>
+template <int NF, int FB, int AXP = HSL_AXP_GENERIC>
 cudaError_t launch_gait_pipe(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
   const size_t smem = (size_t)HslPipeSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
-  auto kern = hsl_gait_pipe_kernel<NF, FB>;
+  auto kern = hsl_gait_pipe_kernel<NF, FB, AXP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int64_t slots = A.n_cand * (A.n_t + 4);
@@ -463,11 +481,23 @@ cudaError_t launch_gait_pipe(const HslModelPod& M, const HslFrameArgs& A, cudaSt
 // 4 warps per sub-partition -> 128 registers, 3 -> 168, 2 -> 255.
 template <int NF>
 cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int maxreg, cudaStream_t st) {
+  // the default variants (six limbs: pipelined, 64 slots; four limbs: plain, 32 slots, 128 registers) also exist
+  // specialised for the model's hinge-axis pattern
+  const int axp = axis_pattern(M);
   if (maxreg == 1) {  // software-pipelined persistent kernel
-    if (fb == 64) return launch_gait_pipe<NF, 64>(M, A, st);
+    if (fb == 64) {
+      if (NF == 6 && axp == HSL_AXP_YXX) return launch_gait_pipe<NF, 64, (NF == 6 ? HSL_AXP_YXX : HSL_AXP_GENERIC)>(M, A, st);
+      if (NF == 6 && axp == HSL_AXP_ZXX) return launch_gait_pipe<NF, 64, (NF == 6 ? HSL_AXP_ZXX : HSL_AXP_GENERIC)>(M, A, st);
+      return launch_gait_pipe<NF, 64>(M, A, st);
+    }
     return launch_gait_pipe<NF, 32>(M, A, st);
   }
-  if (fb == 64) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128>(M, A, st);  // 14 warps (nf=6): 4 per sub-partition
+  if (fb == 64) {  // 14 warps (nf=6): 4 per sub-partition
+    if (NF == 6 && axp == HSL_AXP_YXX) return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128, (NF == 6 ? HSL_AXP_YXX : HSL_AXP_GENERIC)>(M, A, st);
+    return launch_frames_t<NF, 64, HSL_MODE_GAIT, false, 128>(M, A, st);
+  }
+  if (NF == 4 && maxreg > 96 && maxreg <= 128 && axp == HSL_AXP_YXX)
+    return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 128, (NF == 4 ? HSL_AXP_YXX : HSL_AXP_GENERIC)>(M, A, st);
   if (maxreg <= 96) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 80>(M, A, st);   // 3 blocks x 7 warps
   if (maxreg <= 128) return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 128>(M, A, st); // 2 blocks x 7 warps
   return launch_frames_t<NF, 32, HSL_MODE_GAIT, false, 255>(M, A, st);                    // 1 block x 7 warps

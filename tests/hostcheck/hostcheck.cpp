@@ -4,6 +4,7 @@
 // This lets the CPU-only test tier check the exact arithmetic the CUDA kernels run (same source) against
 // the oracle.  It is never used by the product: hslabs_b200/ has no CPU path.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -15,7 +16,21 @@
 int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int errlen);
 
 namespace {
-template <int NF, int FB, int MODE, bool DUMP>
+bool g_axis_special = true;  // emulate the kernels specialised for the model's hinge-axis pattern when there is one
+int axis_pattern(const HslModelPod& M) {  // same rule as the launcher in hsl_kernels.cu
+  int pat = -1;
+  for (int l = 0; l < M.nf; l++) {
+    const HslLimb& L = M.limb[l];
+    const int a0 = std::abs(L.h[0].aligned), a1 = std::abs(L.h[1].aligned), a2 = std::abs(L.h[2].aligned);
+    int p = HSL_AXP_GENERIC;
+    if (a1 == 1 && a2 == 1 && a0 == 2 && L.kind == HSL_IK_YXX) p = HSL_AXP_YXX;
+    if (a1 == 1 && a2 == 1 && a0 == 3 && L.kind == HSL_IK_ZXX) p = HSL_AXP_ZXX;
+    if (pat < 0) pat = p;
+    if (p != pat) return HSL_AXP_GENERIC;
+  }
+  return pat < 0 ? HSL_AXP_GENERIC : pat;
+}
+template <int NF, int FB, int MODE, bool DUMP, int AXP = HSL_AXP_GENERIC>
 void emulate(const HslModelPod& M, const HslFrameArgs& A) {
   const int roles = NF + 1;
   int64_t blocks;
@@ -56,7 +71,7 @@ void emulate(const HslModelPod& M, const HslFrameArgs& A) {
     }
     for (int r = 0; r < roles; r++)
       for (int s = 0; s < FB; s++) {
-        if (r < NF) { phase_a_leg<NF, FB, MODE, DUMP>(M, A, sm, sls[s], r, lst[r * FB + s]); bad[r * FB + s] = lst[r * FB + s].bad; }
+        if (r < NF) { phase_a_leg<NF, FB, MODE, DUMP, AXP>(M, A, sm, sls[s], r, lst[r * FB + s]); bad[r * FB + s] = lst[r * FB + s].bad; }
         else phase_a_trunk<NF, FB, MODE>(M, A, sm, sls[s], tst[s]);
       }
     for (int r = 0; r < roles; r++)
@@ -143,7 +158,7 @@ void emulate_forces(const HslModelPod& M, const HslFrameArgs& A) {
 // Serial emulation of hsl_gait_pipe_kernel with `grid` persistent blocks: the two halves of every iteration are run
 // role by role exactly in the order the device schedule allows (see hsl_pipe.h), so a wrong buffer hand-off shows up
 // here as a wrong result.
-template <int NF, int FB>
+template <int NF, int FB, int AXP = HSL_AXP_GENERIC>
 void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
   const int64_t slots = A.n_cand * (A.n_t + 4);
   int64_t n_tiles = (slots - 4 + (FB - 4) - 1) / (FB - 4);
@@ -184,7 +199,7 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
       }
       // first half: trunk E(t-2), C(t-1), A'(t) ; limbs A(t)   (any interleaving is legal on the device; limbs first here)
       for (int r = 0; r < NF; r++)
-        for (int s = 0; s < FB; s++) phase_a_leg<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, cur[s], r, lst[r * FB + s]);
+        for (int s = 0; s < FB; s++) phase_a_leg<NF, FB, HSL_MODE_GAIT, false, AXP>(M, A, sm, cur[s], r, lst[r * FB + s]);
       trunk_e(p2);
       trunk_c(p1);
       for (int s = 0; s < FB; s++) phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, cur[s], tst[s]);
@@ -212,7 +227,10 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
 
 template <int NF>
 void run(const HslModelPod& M, const HslFrameArgs& A, int mode) {
-  if (mode == HSL_MODE_GAIT) emulate<NF, 32, HSL_MODE_GAIT, true>(M, A);
+  const int axp = g_axis_special ? axis_pattern(M) : HSL_AXP_GENERIC;
+  if (mode == HSL_MODE_GAIT && axp == HSL_AXP_YXX) emulate<NF, 32, HSL_MODE_GAIT, true, HSL_AXP_YXX>(M, A);
+  else if (mode == HSL_MODE_GAIT && axp == HSL_AXP_ZXX) emulate<NF, 32, HSL_MODE_GAIT, true, HSL_AXP_ZXX>(M, A);
+  else if (mode == HSL_MODE_GAIT) emulate<NF, 32, HSL_MODE_GAIT, true>(M, A);
   else if (mode == HSL_MODE_TRAJ) emulate<NF, 32, HSL_MODE_TRAJ, true>(M, A);
   else emulate<NF, 32, HSL_MODE_FIELDS, true>(M, A);
 }
@@ -254,6 +272,15 @@ int hc_setup_candidate(const char* xml, const double* params, int n_t, HslCand* 
   if (rc) return rc;
   setup_candidate(M, params, n_t, *cd, ttab);
   return 0;
+}
+
+// 1 (default): emulate the kernels specialised for the model's hinge-axis pattern; 0: the generic ones
+void hc_set_axis_specialisation(int on) { g_axis_special = (on != 0); }
+int hc_axis_pattern(const char* xml) {
+  HslModelPod M;
+  char err[256];
+  if (hsl_build_model_pod(xml, &M, err, sizeof err)) return -1;
+  return axis_pattern(M);
 }
 
 // test-side mirror of hsl_set_rec_transform (process-wide here; the library keeps it per handle)
@@ -350,7 +377,10 @@ int hc_eval_gaits_pipe(const char* xml, int64_t C, int n_t, const double* params
   A.cand = cand.data(); A.ttab = ttab.data();
   A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
   apply_rec(A);
-  if (M.nf == 6) { if (fb == 64) emulate_pipe<6, 64>(M, A, grid); else emulate_pipe<6, 32>(M, A, grid); }
+  const int axp = g_axis_special ? axis_pattern(M) : HSL_AXP_GENERIC;
+  if (M.nf == 6 && fb == 64 && axp == HSL_AXP_YXX) emulate_pipe<6, 64, HSL_AXP_YXX>(M, A, grid);
+  else if (M.nf == 6 && fb == 64 && axp == HSL_AXP_ZXX) emulate_pipe<6, 64, HSL_AXP_ZXX>(M, A, grid);
+  else if (M.nf == 6) { if (fb == 64) emulate_pipe<6, 64>(M, A, grid); else emulate_pipe<6, 32>(M, A, grid); }
   else { if (fb == 64) emulate_pipe<4, 64>(M, A, grid); else emulate_pipe<4, 32>(M, A, grid); }
   finish(C, n_t, (double)M.n, cand.data(), nullptr, wf, fmn, fmx, st.data(), cot, work, min_cfz, max_mu);
   if (status) memcpy(status, st.data(), sizeof(int32_t) * C);

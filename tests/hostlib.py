@@ -50,6 +50,15 @@ def set_rec_transform(transl=None, eas=None):
     lib().hc_set_rec_transform(_p(tr), _p(ea))
 
 
+def set_axis_specialisation(on=True):
+    """Emulate the kernels specialised for the model's hinge-axis pattern (default) or the generic ones."""
+    lib().hc_set_axis_specialisation(C.c_int(1 if on else 0))
+
+
+def axis_pattern(xml):
+    return lib().hc_axis_pattern(xml.encode())
+
+
 def eval_trajectories(xml, traj, dt, n_t):
     d = model_dims(xml)
     traj = np.ascontiguousarray(traj, np.float64).reshape(-1, n_t + 5, d["config_dim"])

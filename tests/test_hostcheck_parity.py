@@ -193,3 +193,25 @@ def test_forces_from_torques(orc, pid):
     sel = k >= 3
     if sel.any():
         assert np.abs(back[sel] - fwd["z"][sel]).max() < 1e-9 * np.abs(fwd["z"]).max()
+
+
+@pytest.mark.parametrize("model,pattern", [("hexapod", 1), ("myant", 1), ("spider", 2)])
+def test_axis_specialised_kernels_equal_generic(model, pattern):
+    """The kernels specialised for the model's hinge-axis pattern (compile-time hinge axes, hsl_frame.h) run the same
+    arithmetic as the generic ones: bit-identical results, detail and pipelined paths."""
+    from test_gpu_parity import _random_candidates
+    xml = model_xml(model)
+    assert hostlib.axis_pattern(xml) == pattern
+    p = _random_candidates(model, 6, 7)
+    try:
+        hostlib.set_axis_specialisation(True)
+        a = hostlib.eval_gaits(xml, p, 24)
+        ap = hostlib.eval_gaits_pipe(xml, p, 24)
+        hostlib.set_axis_specialisation(False)
+        b = hostlib.eval_gaits(xml, p, 24)
+        bp = hostlib.eval_gaits_pipe(xml, p, 24)
+    finally:
+        hostlib.set_axis_specialisation(True)
+    for k in ("cot", "work", "x", "z", "tau", "traj"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert np.array_equal(ap["cot"], bp["cot"], equal_nan=True)
