@@ -61,6 +61,9 @@
 #define HSL_FLAG_IGNORE_REACH 1
 // Hinge-axis patterns a kernel can be specialised for (all limbs of the model alike, every hinge axis-aligned):
 // hip about the parent's y (yxx limbs: myant, hexapod) or z (zxx: spider), knee and ankle about x.
+// The patterns also fix which body axis the link offsets lie on (all other components exactly zero):
+//   YXX: hip COM, knee / ankle joint offsets and COMs, foot point on y ; ZXX: hip COM and knee joint offset on z,
+//   knee COM, ankle joint offset and COM, foot point on y ; the hip joint offset is a general vector in both.
 #define HSL_AXP_GENERIC 0
 #define HSL_AXP_YXX 1
 #define HSL_AXP_ZXX 2
@@ -128,6 +131,29 @@ HSL_HD void euler_to_R(double phi, double theta, double psi, double* R) {
 HSL_HD void wrap_pm_pi(double& a) {  // visualization.cpp:73-79
   if (a < -M_PI) { while (a < -M_PI) a += 2 * M_PI; }
   else if (a > M_PI) { while (a > M_PI) a -= 2 * M_PI; }
+}
+
+// Pattern shared by every limb of the model, or HSL_AXP_GENERIC.  Used by the launchers (and the host emulation) to
+// pick a kernel specialised for it.
+HSL_HD bool hsl_on_axis(const double* v, int ax) {
+  return v[(ax + 1) % 3] == 0.0 && v[(ax + 2) % 3] == 0.0;
+}
+HSL_HD int hsl_axis_pattern(const HslModelPod& M) {
+  int pat = -1;
+  for (int l = 0; l < M.nf; l++) {
+    const HslLimb& L = M.limb[l];
+    const int a0 = L.h[0].aligned < 0 ? -L.h[0].aligned : L.h[0].aligned;
+    const int a1 = L.h[1].aligned < 0 ? -L.h[1].aligned : L.h[1].aligned;
+    const int a2 = L.h[2].aligned < 0 ? -L.h[2].aligned : L.h[2].aligned;
+    int p = HSL_AXP_GENERIC;
+    const bool tail = a1 == 1 && a2 == 1 && hsl_on_axis(L.h[1].com, 1) && hsl_on_axis(L.h[2].tjp, 1) && hsl_on_axis(L.h[2].com, 1) &&
+                      hsl_on_axis(L.foot, 1);
+    if (tail && a0 == 2 && L.kind == HSL_IK_YXX && hsl_on_axis(L.h[0].com, 1) && hsl_on_axis(L.h[1].tjp, 1)) p = HSL_AXP_YXX;
+    if (tail && a0 == 3 && L.kind == HSL_IK_ZXX && hsl_on_axis(L.h[0].com, 2) && hsl_on_axis(L.h[1].tjp, 2)) p = HSL_AXP_ZXX;
+    if (pat < 0) pat = p;
+    if (p != pat) return HSL_AXP_GENERIC;
+  }
+  return pat < 0 ? HSL_AXP_GENERIC : pat;
 }
 
 // ------------------------------------------------------------------ gait generator (a2)
@@ -388,18 +414,27 @@ HSL_HD void rot_about_axis(const double* Rp, double cs, double sn, double* Rb) {
     Rb[3 * C + i] = Rp[3 * C + i] * cs - Rp[3 * B + i] * sn;
   }
 }
+// y = t + R[:, AXV] * v[AXV] when the vector v is known to lie on body axis AXV (AXV < 0: general vector)
+template <int AXV>
+HSL_HD void m3_affine_ax(const double* R, const double* v, const double* t, double* y) {
+  if (AXV < 0) { m3_affine(R, v, t, y); return; }
+#pragma unroll
+  for (int i = 0; i < 3; i++) y[i] = R[3 * (AXV < 0 ? 0 : AXV) + i] * v[AXV < 0 ? 0 : AXV] + t[i];
+}
 // Hinge known at compile time to turn about +-(coordinate axis AX of the parent frame) with the joint at the body
-// origin: same arithmetic as the aligned branch of hinge_fk below, without its run-time dispatch (the three-way
-// branch costs merge moves for the nine entries of Rb and keeps the scheduler from overlapping consecutive hinges).
-template <int AX>
+// origin, joint offset along parent axis TAX and COM offset along body axis CAX (negative = general vector): same
+// arithmetic as the aligned branch of hinge_fk below without its run-time dispatch (the three-way branch costs merge
+// moves for the nine entries of Rb and keeps the scheduler from overlapping consecutive hinges) and without the
+// products with the structural zeros of the offsets.
+template <int AX, int TAX, int CAX>
 HSL_HD void hinge_fk_aligned(const HslHinge& H, double cs, double sn, const double* Rp, const double* tp, double* Rb, double* tb,
                              double* jpos, double* axis, double* com, double* ust) {
-  m3_affine(Rp, H.tjp, tp, jpos);
+  m3_affine_ax<TAX>(Rp, H.tjp, tp, jpos);
   const double sg = (H.aligned > 0) ? 1.0 : -1.0, s2 = sg * sn;
   rot_about_axis<AX>(Rp, cs, s2, Rb);
   axis[0] = sg * Rp[3 * AX]; axis[1] = sg * Rp[3 * AX + 1]; axis[2] = sg * Rp[3 * AX + 2];
   tb[0] = jpos[0]; tb[1] = jpos[1]; tb[2] = jpos[2];
-  m3_affine(Rb, H.com, tb, com);
+  m3_affine_ax<CAX>(Rb, H.com, tb, com);
   ust[0] = (Rb[5] - Rb[7]) / 2;
   ust[1] = (Rb[6] - Rb[2]) / 2;
   ust[2] = (Rb[1] - Rb[3]) / 2;
@@ -507,10 +542,13 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
 #pragma unroll
   for (int h = 0; h < 3; h++) {
     double ust[3];
+    // per-pattern (hinge axis, joint-offset axis, COM-offset axis) of the three hinges: see hsl_axis_pattern()
     if (AXP == 0) hinge_fk(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
-    else if (h > 0) hinge_fk_aligned<0>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
-    else if (AXP == HSL_AXP_YXX) hinge_fk_aligned<1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
-    else hinge_fk_aligned<2>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else if (h == 2) hinge_fk_aligned<0, 1, 1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else if (AXP == HSL_AXP_YXX && h == 0) hinge_fk_aligned<1, -1, 1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else if (AXP == HSL_AXP_YXX) hinge_fk_aligned<0, 1, 1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else if (h == 0) hinge_fk_aligned<2, -1, 2>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
+    else hinge_fk_aligned<0, 2, 1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       sm.pos[((3 * limb + h) * 3 + k) * FB + sl.s] = st.pos[h][k];
@@ -523,7 +561,8 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
 #pragma unroll
     for (int k = 0; k < 3; k++) tp[k] = tb[k];
   }
-  m3_affine(Rb, L.foot, tb, st.fpos);                 // odepart::get_foot_pos, visualization.cpp:565
+  if (AXP == 0) m3_affine(Rb, L.foot, tb, st.fpos);   // odepart::get_foot_pos, visualization.cpp:565
+  else m3_affine_ax<1>(Rb, L.foot, tb, st.fpos);
   st.contact = (st.fpos[2] < M.rcap + 1e-4);          // dynrec.cpp:149
   if (DUMP && MODE == HSL_MODE_GAIT && A.q_out && sl.valid) {
     const int64_t tot = A.n_cand * (A.n_t + 4), g = sl.c * (A.n_t + 4) + sl.i;

@@ -405,24 +405,6 @@ __global__ void hsl_math_selftest_kernel(int n, const double* __restrict__ a, co
 
 // ------------------------------------------------------------------ launchers
 namespace {
-// Hinge-axis pattern shared by every limb of the model, or HSL_AXP_GENERIC (kernels specialised for a pattern skip
-// the run-time dispatch on the hinge axes; hsl_frame.h).
-int axis_pattern(const HslModelPod& M) {
-  int pat = -1;
-  for (int l = 0; l < M.nf; l++) {
-    const HslLimb& L = M.limb[l];
-    const int a0 = L.h[0].aligned < 0 ? -L.h[0].aligned : L.h[0].aligned;
-    const int a1 = L.h[1].aligned < 0 ? -L.h[1].aligned : L.h[1].aligned;
-    const int a2 = L.h[2].aligned < 0 ? -L.h[2].aligned : L.h[2].aligned;
-    int p = HSL_AXP_GENERIC;
-    if (a1 == 1 && a2 == 1 && a0 == 2 && L.kind == HSL_IK_YXX) p = HSL_AXP_YXX;
-    if (a1 == 1 && a2 == 1 && a0 == 3 && L.kind == HSL_IK_ZXX) p = HSL_AXP_ZXX;
-    if (pat < 0) pat = p;
-    if (p != pat) return HSL_AXP_GENERIC;
-  }
-  return pat < 0 ? HSL_AXP_GENERIC : pat;
-}
-
 template <int NF, int FB, int MODE, bool DUMP, int MAXREG = 255, int AXP = HSL_AXP_GENERIC>
 cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
   const size_t smem = (size_t)HslSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
@@ -483,7 +465,7 @@ template <int NF>
 cudaError_t launch_gait_fast(const HslModelPod& M, const HslFrameArgs& A, int fb, int maxreg, cudaStream_t st) {
   // the default variants (six limbs: pipelined, 64 slots; four limbs: plain, 32 slots, 128 registers) also exist
   // specialised for the model's hinge-axis pattern
-  const int axp = axis_pattern(M);
+  const int axp = hsl_axis_pattern(M);
   if (maxreg == 1) {  // software-pipelined persistent kernel
     if (fb == 64) {
       if (NF == 6 && axp == HSL_AXP_YXX) return launch_gait_pipe<NF, 64, (NF == 6 ? HSL_AXP_YXX : HSL_AXP_GENERIC)>(M, A, st);

@@ -17,19 +17,6 @@ int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int e
 
 namespace {
 bool g_axis_special = true;  // emulate the kernels specialised for the model's hinge-axis pattern when there is one
-int axis_pattern(const HslModelPod& M) {  // same rule as the launcher in hsl_kernels.cu
-  int pat = -1;
-  for (int l = 0; l < M.nf; l++) {
-    const HslLimb& L = M.limb[l];
-    const int a0 = std::abs(L.h[0].aligned), a1 = std::abs(L.h[1].aligned), a2 = std::abs(L.h[2].aligned);
-    int p = HSL_AXP_GENERIC;
-    if (a1 == 1 && a2 == 1 && a0 == 2 && L.kind == HSL_IK_YXX) p = HSL_AXP_YXX;
-    if (a1 == 1 && a2 == 1 && a0 == 3 && L.kind == HSL_IK_ZXX) p = HSL_AXP_ZXX;
-    if (pat < 0) pat = p;
-    if (p != pat) return HSL_AXP_GENERIC;
-  }
-  return pat < 0 ? HSL_AXP_GENERIC : pat;
-}
 template <int NF, int FB, int MODE, bool DUMP, int AXP = HSL_AXP_GENERIC>
 void emulate(const HslModelPod& M, const HslFrameArgs& A) {
   const int roles = NF + 1;
@@ -227,7 +214,7 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
 
 template <int NF>
 void run(const HslModelPod& M, const HslFrameArgs& A, int mode) {
-  const int axp = g_axis_special ? axis_pattern(M) : HSL_AXP_GENERIC;
+  const int axp = g_axis_special ? hsl_axis_pattern(M) : HSL_AXP_GENERIC;
   if (mode == HSL_MODE_GAIT && axp == HSL_AXP_YXX) emulate<NF, 32, HSL_MODE_GAIT, true, HSL_AXP_YXX>(M, A);
   else if (mode == HSL_MODE_GAIT && axp == HSL_AXP_ZXX) emulate<NF, 32, HSL_MODE_GAIT, true, HSL_AXP_ZXX>(M, A);
   else if (mode == HSL_MODE_GAIT) emulate<NF, 32, HSL_MODE_GAIT, true>(M, A);
@@ -280,7 +267,7 @@ int hc_axis_pattern(const char* xml) {
   HslModelPod M;
   char err[256];
   if (hsl_build_model_pod(xml, &M, err, sizeof err)) return -1;
-  return axis_pattern(M);
+  return hsl_axis_pattern(M);
 }
 
 // test-side mirror of hsl_set_rec_transform (process-wide here; the library keeps it per handle)
@@ -377,7 +364,7 @@ int hc_eval_gaits_pipe(const char* xml, int64_t C, int n_t, const double* params
   A.cand = cand.data(); A.ttab = ttab.data();
   A.wframe = wf.data(); A.fmin_cfz = fmn.data(); A.fmax_mu = fmx.data(); A.status = st.data();
   apply_rec(A);
-  const int axp = g_axis_special ? axis_pattern(M) : HSL_AXP_GENERIC;
+  const int axp = g_axis_special ? hsl_axis_pattern(M) : HSL_AXP_GENERIC;
   if (M.nf == 6 && fb == 64 && axp == HSL_AXP_YXX) emulate_pipe<6, 64, HSL_AXP_YXX>(M, A, grid);
   else if (M.nf == 6 && fb == 64 && axp == HSL_AXP_ZXX) emulate_pipe<6, 64, HSL_AXP_ZXX>(M, A, grid);
   else if (M.nf == 6) { if (fb == 64) emulate_pipe<6, 64>(M, A, grid); else emulate_pipe<6, 32>(M, A, grid); }

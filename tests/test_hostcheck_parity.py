@@ -198,7 +198,8 @@ def test_forces_from_torques(orc, pid):
 @pytest.mark.parametrize("model,pattern", [("hexapod", 1), ("myant", 1), ("spider", 2)])
 def test_axis_specialised_kernels_equal_generic(model, pattern):
     """The kernels specialised for the model's hinge-axis pattern (compile-time hinge axes, hsl_frame.h) run the same
-    arithmetic as the generic ones: bit-identical results, detail and pipelined paths."""
+    arithmetic as the generic ones up to the order of a few fused multiply-adds (offsets with structural zeros):
+    results equal to 1e-13, detail and pipelined paths."""
     from test_gpu_parity import _random_candidates
     xml = model_xml(model)
     assert hostlib.axis_pattern(xml) == pattern
@@ -213,5 +214,5 @@ def test_axis_specialised_kernels_equal_generic(model, pattern):
     finally:
         hostlib.set_axis_specialisation(True)
     for k in ("cot", "work", "x", "z", "tau", "traj"):
-        assert np.array_equal(a[k], b[k], equal_nan=True), k
-    assert np.array_equal(ap["cot"], bp["cot"], equal_nan=True)
+        assert rel_err(a[k], b[k]) < 1e-13, k
+    assert rel_err(ap["cot"], bp["cot"]) < 1e-13
