@@ -172,7 +172,7 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
     A.q_out = (double*)m->dump_q.p; A.contacts = (uint8_t*)m->dump_c.p;
   }
 #ifdef HSL_PHASE_CLOCKS
-  const int fbp = (dump ? 32 : m->fb), warps = (m->pod.nf + 1) * fbp / 32;
+  const int fbp = (dump ? 32 : m->fb), nroles = m->pod.nf + ((m->maxreg == 1 && !dump) ? 2 : 1), warps = nroles * fbp / 32;
   const int64_t nblk = (C * (n_t + 4) - 4 + (fbp - 4) - 1) / (fbp - 4);
   static DevBuf clkbuf;
   HSL_CUDA(clkbuf.need(sizeof(long long) * nblk * warps * 8));
@@ -185,7 +185,7 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
     HSL_CUDA(cudaStreamSynchronize(st));
     std::vector<long long> h((size_t)nblk * warps * 8);
     HSL_CUDA(cudaMemcpy(h.data(), clkbuf.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-    const int roles = m->pod.nf + 1, wpr = fbp / 32;
+    const int roles = nroles, wpr = fbp / 32;
     if (m->maxreg == 1 && !dump) {  // pipelined kernel: per-tile averages of [work before barrier 1 | wait | phase B | wait]
       const int64_t grid = nblk < 148 * (fbp == 64 ? 1 : 2) ? nblk : 148 * (fbp == 64 ? 1 : 2);
       fprintf(stderr, "[pipe clocks] tiles=%lld grid=%lld\n", (long long)nblk, (long long)grid);

@@ -243,26 +243,55 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
     HSL_BLOCK_SYNC();
     if (p1_int) pipe_d_leg<NF, FB>(sm, s, role);
     HSL_BLOCK_SYNC();
+  } else if (role == NF) {
+    // solver warps: phase C of the previous tile in the first half, nothing in the second
+    bool p1_int = false;
+    int64_t p1_fo = 0, p1_c = 0;
+    auto solve = [&]() {
+      HslTrunkState tst;
+#pragma unroll
+      for (int k = 0; k < 3; k++) { tst.F0[k] = sm.twr[k * FB + s]; tst.T0[k] = sm.twr[(3 + k) * FB + s]; }
+      HslSlot ps;
+      ps.s = s; ps.fo = p1_fo; ps.c = p1_c; ps.i = 2; ps.valid = true; ps.interior = true;
+      const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
+      if (tb && A.status) atomicOr(&A.status[p1_c], tb);
+    };
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
+      HSL_T0();
+      if (p1_int) solve();
+      HSL_T1(0);
+      HSL_BLOCK_SYNC();
+      HSL_T1(1);
+      HSL_T1(2);
+      HSL_BLOCK_SYNC();
+      HSL_T1(3);
+#ifdef HSL_PHASE_CLOCKS
+      first_tile = false;
+#endif
+      p1_int = sl.interior; p1_fo = sl.fo; p1_c = sl.c;
+    }
+    if (p1_int) solve();
+    HSL_BLOCK_SYNC();
+    HSL_BLOCK_SYNC();
   } else {
+    // trunk warps: output pass of tile t-2 and kinematics of tile t in the first half, derivatives in the second
     bool p1_int = false, p2_int = false;
-    int64_t p1_fo = 0, p2_fo = 0, p1_c = 0;
+    int64_t p1_fo = 0, p2_fo = 0;
     HslTrunkState tst;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
       HSL_T0();
       if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
-      // C(t-1) needs the trunk wrench kept in tst.F0/T0 since B'(t-1); A'(t) only writes tst.R0/t0
-      if (p1_int) {
-        HslSlot ps = sl;
-        ps.fo = p1_fo; ps.c = p1_c;
-        const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
-        if (tb && A.status) atomicOr(&A.status[p1_c], tb);
-      }
       phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
       HSL_T1(0);
       HSL_BLOCK_SYNC();
       HSL_T1(1);
-      if (sl.interior) phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
+      if (sl.interior) {
+        phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
+#pragma unroll
+        for (int k = 0; k < 3; k++) { sm.twr[k * FB + s] = tst.F0[k]; sm.twr[(3 + k) * FB + s] = tst.T0[k]; }
+      }
       HSL_T1(2);
       HSL_BLOCK_SYNC();
       HSL_T1(3);
@@ -270,15 +299,9 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
       first_tile = false;
 #endif
       p2_int = p1_int; p2_fo = p1_fo;
-      p1_int = sl.interior; p1_fo = sl.fo; p1_c = sl.c;
+      p1_int = sl.interior; p1_fo = sl.fo;
     }
     if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
-    if (p1_int) {
-      HslSlot ps;
-      ps.s = s; ps.fo = p1_fo; ps.c = p1_c; ps.i = 2; ps.valid = true; ps.interior = true;
-      const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
-      if (tb && A.status) atomicOr(&A.status[p1_c], tb);
-    }
     HSL_BLOCK_SYNC();
     HSL_BLOCK_SYNC();
     if (p1_int) pipe_e_trunk<NF, FB>(A, sm, s, p1_fo);
@@ -448,12 +471,12 @@ cudaError_t launch_gait_pipe(const HslModelPod& M, const HslFrameArgs& A, cudaSt
     if (sms <= 0) sms = 148;
   }
   int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (NF + 1) * FB, smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HSL_PIPE_ROLES(NF) * FB, smem);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) return cudaErrorInvalidConfiguration;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<(unsigned)grid, (NF + 1) * FB, smem, st>>>(M, A, n_tiles);
+  kern<<<(unsigned)grid, HSL_PIPE_ROLES(NF) * FB, smem, st>>>(M, A, n_tiles);
   return cudaGetLastError();
 }
 

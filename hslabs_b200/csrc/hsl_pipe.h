@@ -8,7 +8,13 @@
 //
 //               | first half of iteration t  (until barrier 1) | second half (until barrier 2)
 //   limb warps  | A(t): gait, IK, FK                            | D(t-1): contact force, torques, power ; B(t)
-//   trunk warps | E(t-2) ; C(t-1): 6x6 solve ; A'(t)            | B'(t)
+//   solver warps| C(t-1): 6x6 solve                             | -
+//   trunk warps | E(t-2) ; A'(t)                                | B'(t)
+//
+// The trunk's work is split over two roles (solver: phase C; trunk: kinematics, derivatives and the output pass) so
+// that the block has 16 warps, four per scheduler: with 14 warps two schedulers hosted a trunk warp next to three limb
+// warps (6300 instructions per tile against 4600 on the other two) and their limb warps set the pace of both halves.
+// The trunk wrench F0/T0 goes from B'(t) to C(t) through `twr`.
 //
 // Phase D needs 24 doubles of limb state from phase B of the same frame; instead of keeping them in registers across
 // a whole tile they are parked in shared memory: 12 in `dstate` (written at the end of B(t), read back in D(t) one
@@ -26,12 +32,15 @@
 template <int NF, int FB>
 struct HslPipeSmem : HslSmem<NF, FB, 19> {
   double* dstate;  // [NF*HSL_DSTATE][FB]
-  HSL_HD static int doubles_per_slot(int ntrunk) { return HslSmem<NF, FB, 19>::doubles_per_slot(ntrunk) + NF * HSL_DSTATE; }
+  double* twr;     // [6][FB]  trunk bodies' own share of the root wrench: w B'(t) (second half) | r C(t) (next first half)
+  HSL_HD static int doubles_per_slot(int ntrunk) { return HslSmem<NF, FB, 19>::doubles_per_slot(ntrunk) + NF * HSL_DSTATE + 6; }
   HSL_HD void carve(double* base, int ntrunk) {
     HslSmem<NF, FB, 19>::carve(base, ntrunk);
     dstate = this->mu + 7 * FB;
+    twr = dstate + NF * HSL_DSTATE * FB;
   }
 };
+#define HSL_PIPE_ROLES(NF) ((NF) + 2)  // limbs, solver, trunk
 
 // Limb thread, end of phase B: park what phase D needs besides W, W g, r.
 template <int NF, int FB, class SM>

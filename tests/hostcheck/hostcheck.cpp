@@ -160,10 +160,12 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
     std::fill(smem.begin(), smem.end(), NAN);
     std::vector<HslSlot> cur(FB), p1(FB), p2(FB);
     for (int s = 0; s < FB; s++) { p1[s].interior = p2[s].interior = false; p1[s].s = p2[s].s = s; }
-    auto trunk_c = [&](std::vector<HslSlot>& ps) {
+    auto trunk_c = [&](std::vector<HslSlot>& ps) {  // solver role: own trunk state, wrench from `twr`
       for (int s = 0; s < FB; s++)
         if (ps[s].interior) {
-          int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps[s], tst[s]);
+          HslTrunkState sv;
+          for (int k = 0; k < 3; k++) { sv.F0[k] = sm.twr[k * FB + s]; sv.T0[k] = sm.twr[(3 + k) * FB + s]; }
+          int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps[s], sv);
           if (tb && A.status) A.status[ps[s].c] |= tb;
         }
     };
@@ -201,7 +203,12 @@ void emulate_pipe(const HslModelPod& M, const HslFrameArgs& A, int grid) {
           }
           if (st.bad && cur[s].valid && A.status) A.status[cur[s].c] |= st.bad;
         }
-      for (int s = 0; s < FB; s++) if (cur[s].interior) phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, cur[s], tst[s]);
+      for (int s = 0; s < FB; s++)
+        if (cur[s].interior) {
+          phase_b_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, cur[s], tst[s]);
+          for (int k = 0; k < 3; k++) { sm.twr[k * FB + s] = tst[s].F0[k]; sm.twr[(3 + k) * FB + s] = tst[s].T0[k]; }
+          tst[s].F0[0] = tst[s].T0[0] = NAN;  // the solver role must not see the trunk role's registers
+        }
       p2 = p1;
       p1 = cur;
     }
