@@ -796,13 +796,14 @@ HSL_HD void phase_b_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM&
 
 // ------------------------------------------------------------------ phase C (trunk)
 // LDL^T solve of a symmetric positive definite 6x6 (lower triangle in S[i][j], i>=j). Returns false on breakdown.
-HSL_HD bool spd6_solve(double S[6][6], double* b) {
+// *ill (optional) is set when a pivot falls below HSL_ILLCOND_PIVOT of the trace (nearly rank deficient).
+HSL_HD bool spd6_solve(double S[6][6], double* b, bool* ill = nullptr) {
   double dinv[6], dd[6];
   double tr = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) tr += S[i][i];
-  const double tol = 1e-13 * tr;
-  bool ok = true;
+  const double tol = 1e-13 * tr, tol_ill = HSL_ILLCOND_PIVOT * tr;
+  bool ok = true, weak = false;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     // column j: u_i = S_ij - sum_k L_ik (L_jk d_k) for i >= j ; d_j = u_j ; L_ij = u_i / d_j
@@ -813,6 +814,7 @@ HSL_HD bool spd6_solve(double S[6][6], double* b) {
 #pragma unroll
     for (int k = 0; k < j; k++) d -= S[j][k] * ld[k];
     ok = ok && (d > tol);
+    weak = weak || (d < tol_ill);
     dd[j] = d;
     dinv[j] = hsl_rcp(d);
 #pragma unroll
@@ -833,6 +835,7 @@ HSL_HD bool spd6_solve(double S[6][6], double* b) {
   for (int i = 5; i >= 0; i--)
 #pragma unroll
     for (int k = i + 1; k < 6; k++) b[i] -= S[k][i] * b[k];
+  if (ill) *ill = weak;
   return ok;
 }
 
@@ -916,7 +919,9 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& 
 #pragma unroll
       for (int k = 0; k < 6; k++) mu[k] = -(b[k] + v[k]);
     }
-    if (!spd6_solve(S, mu)) bad |= HSL_ST_SOLVER;
+    bool ill = false;
+    if (!spd6_solve(S, mu, &ill)) bad |= HSL_ST_SOLVER;
+    if (ill) bad |= HSL_ST_ILLCOND;
   } else {
     bad |= HSL_ST_FEW_CONTACTS;
   }

@@ -229,6 +229,8 @@ class periodic {
                                      x_.data(), z_.data(), tau_.data(), nullptr));
     if (status & HSL_ST_UNREACHABLE) throw error("LIK ERROR: limb position is unreachable");
     if (status & HSL_ST_BAD_PARAMS) throw error("ERROR: step_duration out of bounds");
+    // the reference prints this when its retry loop lowers the rank (ftsolver.cpp:219); here it marks the same regime
+    if (status & HSL_ST_ILLCOND) std::cout << "WARNING: decomposition threshold increased" << std::endl;
     // periodic::compute_vel_traj (periodic.cpp:261-282) on the host, frames 1..n_t+2
     const double dt = pcp_.TLh[0] / n_t_;
     vel_.assign((size_t)(n_t_ + 4) * config_dim_, 0.0);

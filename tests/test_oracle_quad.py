@@ -77,3 +77,29 @@ def test_reference_stats_over_swing_feet_are_roundoff(orc):
     zc = d["z"].reshape(20, m.nf, 3)
     swing = np.abs(zc).max(axis=2) <= 1e-9 * np.abs(zc).max()
     assert swing.any() and np.abs(zc[swing]).max() < 1e-12
+
+
+def test_illconditioned_candidates_follow_the_exact_algorithm(orc):
+    """Almost collinear contact points make level 0 nearly rank deficient.  The reference's FP64 arithmetic then trips
+    its rank-threshold retry loop (ftsolver.cpp:208-232) in some frames and returns something else than its own
+    algorithm does in exact arithmetic; the kernel math agrees with the __float128 evaluation of the reference
+    algorithm, not with the FP64 one, and flags the candidate (HSL_ST_ILLCOND: a level-0 LDL^T pivot below 1e-5 of
+    the trace)."""
+    from test_gpu_parity import _random_candidates
+    n, n_t = 512, 48
+    p = _random_candidates("myant", n, 20261018 + n_t)
+    rng = np.random.default_rng(5)
+    p[:, 10] = rng.uniform(-0.1, 0.1, n); p[:, 11] = 0; p[:, 12] = rng.uniform(0, 0.3, n)
+    xml = model_xml("myant")
+    m = orc.Model(xml)
+    for c, deviates in ((91, True), (113, False), (114, True)):
+        d = m.measure_cot(p[c], n_t)
+        q = m.measure_cot_quad(p[c], n_t)
+        h = hostlib.eval_gaits(xml, p[c], n_t)
+        assert d["status"] == 0 and q["status"] == 0
+        assert h["status"][0] == 16                                       # informational flag only
+        assert abs(h["cot"][0] - q["cot"]) <= 1e-9 * abs(q["cot"])        # the exact algorithm's value
+        assert (abs(d["cot"] - q["cot"]) > 1e-3 * abs(q["cot"])) == deviates
+    # a benign neighbour: all three agree, no flag
+    d = m.measure_cot(p[0], n_t); q = m.measure_cot_quad(p[0], n_t); h = hostlib.eval_gaits(xml, p[0], n_t)
+    assert h["status"][0] == 0 and abs(h["cot"][0] - q["cot"]) <= 1e-12 * abs(q["cot"]) and abs(d["cot"] - q["cot"]) <= 1e-12 * abs(q["cot"])
