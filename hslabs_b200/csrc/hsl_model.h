@@ -86,4 +86,4 @@ typedef struct HslCand {
 #define HSL_ST_SOLVER 4          // contact blocks not positive definite (reference: threshold retry loop, ftsolver.cpp:208-232)
 #define HSL_ST_FEW_CONTACTS 8    // fewer than 2 feet on the ground in some frame (cannot occur for valid step_duration)
 #define HSL_ST_ILLCOND 16        // informational: level 0 nearly rank deficient (contact points almost collinear) in some frame
-#define HSL_ILLCOND_PIVOT 1e-5   // ... = an LDL^T pivot of the 6x6 level-0 matrix below this fraction of its trace
+#define HSL_ILLCOND_PIVOT 1e-4   // ... = an LDL^T pivot of the 6x6 level-0 matrix below this fraction of its trace

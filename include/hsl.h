@@ -36,7 +36,7 @@ extern "C" {
 #define HSL_ST_SOLVER 4       /* contact system not positive definite (ftsolver.cpp:208-232) */
 #define HSL_ST_FEW_CONTACTS 8 /* fewer than two feet on the ground */
 #define HSL_ST_ILLCOND 16     /* informational: in some frame the feet on the ground are almost collinear (an LDL^T pivot
-                                 of the 6x6 level-0 matrix below 1e-5 of its trace).  The reference's FP64 result then
+                                 of the 6x6 level-0 matrix below 1e-4 of its trace).  The reference's FP64 result then
                                  depends on its rank-threshold retry loop (ftsolver.cpp:208-232) and is not
                                  reproducible; the value returned here is the one its algorithm gives in exact
                                  arithmetic.  Results are still written. */

@@ -83,7 +83,7 @@ def test_illconditioned_candidates_follow_the_exact_algorithm(orc):
     """Almost collinear contact points make level 0 nearly rank deficient.  The reference's FP64 arithmetic then trips
     its rank-threshold retry loop (ftsolver.cpp:208-232) in some frames and returns something else than its own
     algorithm does in exact arithmetic; the kernel math agrees with the __float128 evaluation of the reference
-    algorithm, not with the FP64 one, and flags the candidate (HSL_ST_ILLCOND: a level-0 LDL^T pivot below 1e-5 of
+    algorithm, not with the FP64 one, and flags the candidate (HSL_ST_ILLCOND: a level-0 LDL^T pivot below 1e-4 of
     the trace)."""
     from test_gpu_parity import _random_candidates
     n, n_t = 512, 48
