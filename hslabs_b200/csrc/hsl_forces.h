@@ -151,7 +151,7 @@ HSL_HD int forces_f2_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM
 #pragma unroll
     for (int k = 0; k < 3; k++)
       r[k] = ((MODE == HSL_MODE_FIELDS) ? A.f_pos[((int64_t)sl.i * M.n + M.trunk[tb].body) * 3 + k]
-                                        : sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s]) - ref[k];
+                                        : sm.tpos[(tb * 3 + k) * FB + sl.s]) - ref[k];
     // ph = v0 + w0 x r, th = w0 for the six unit twists
     double mot[6][6];
 #pragma unroll

@@ -357,19 +357,25 @@ HSL_HD bool limb_ik(const HslLimb& L, const double* pl, bool ignore_reach, doubl
 // ------------------------------------------------------------------ shared-memory view
 // All exchange arrays are [field][slot] so that consecutive lanes (= consecutive frames) hit
 // consecutive 8-byte words: conflict-free LDS.64 / STS.64.
+struct alignas(16) HslD2 { double x, y; };
 template <int NF, int FB, int PARTN = 19>
 struct HslSmem {
   static constexpr int PART = PARTN;  // doubles per limb in `part`
-  double* pos;   // [(3*NF + ntrunk)*3][FB]   COM positions
-  double* ust;   // [(3*NF + 1)*3][FB]        u*sin(theta) of body rotations (one entry for all trunk bodies)
+  HslD2* pu;     // [9*NF][FB]      limb bodies: (COM position component, u*sin(theta) component of the body rotation)
+                 //                 as one 16-byte entry -- both get the same +-2 frame stencil, so phase B reads them
+                 //                 with one LDS.128 per stencil point instead of two LDS.64 (pairing the cos/sin and
+                 //                 the parked phase-D entries the same way measured no gain)
+  double* tpos;  // [ntrunk*3][FB]  trunk bodies' COM positions
+  double* tust;  // [3][FB]         u*sin(theta) of the trunk rotation (one entry for all trunk bodies)
   double* cs;    // [6*NF][FB]                cos, sin of the hinge angles
   double* part;  // [NF*PART][FB]             limb -> trunk partials ; reused for limb -> trunk results after phase D
   double* mu;    // [7][FB]                   trunk -> limb multiplier (+ validity)
   HSL_HD static int doubles_per_slot(int ntrunk) { return (3 * NF + ntrunk) * 3 + (3 * NF + 1) * 3 + 6 * NF + NF * PARTN + 7; }
-  HSL_HD void carve(double* base, int ntrunk) {
-    pos = base;
-    ust = pos + (3 * NF + ntrunk) * 3 * FB;
-    cs = ust + (3 * NF + 1) * 3 * FB;
+  HSL_HD void carve(double* base, int ntrunk) {  // base must be 16-byte aligned
+    pu = reinterpret_cast<HslD2*>(base);
+    tpos = base + 18 * NF * FB;
+    tust = tpos + ntrunk * 3 * FB;
+    cs = tust + 3 * FB;
     part = cs + 6 * NF * FB;
     mu = part + NF * PARTN * FB;
   }
@@ -551,8 +557,9 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     else hinge_fk_aligned<0, 2, 1>(L.h[h], cq[h], sq[h], Rp, tp, Rb, tb, st.jpos[h], st.axis[h], st.pos[h], ust);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      sm.pos[((3 * limb + h) * 3 + k) * FB + sl.s] = st.pos[h][k];
-      sm.ust[((3 * limb + h) * 3 + k) * FB + sl.s] = ust[k];
+      HslD2 e;
+      e.x = st.pos[h][k]; e.y = ust[k];
+      sm.pu[((3 * limb + h) * 3 + k) * FB + sl.s] = e;
     }
     sm.cs[(6 * limb + 2 * h) * FB + sl.s] = cq[h];
     sm.cs[(6 * limb + 2 * h + 1) * FB + sl.s] = sq[h];
@@ -598,11 +605,11 @@ HSL_HD void phase_a_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM&
     m3_affine(st.R0, M.trunk[tb].off, st.t0, ob);
     m3_affine(st.R0, M.trunk[tb].com, ob, pb);
 #pragma unroll
-    for (int k = 0; k < 3; k++) sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s] = pb[k];
+    for (int k = 0; k < 3; k++) sm.tpos[(tb * 3 + k) * FB + sl.s] = pb[k];
   }
-  sm.ust[((3 * NF) * 3 + 0) * FB + sl.s] = (st.R0[5] - st.R0[7]) / 2;
-  sm.ust[((3 * NF) * 3 + 1) * FB + sl.s] = (st.R0[6] - st.R0[2]) / 2;
-  sm.ust[((3 * NF) * 3 + 2) * FB + sl.s] = (st.R0[1] - st.R0[3]) / 2;
+  sm.tust[0 * FB + sl.s] = (st.R0[5] - st.R0[7]) / 2;
+  sm.tust[1 * FB + sl.s] = (st.R0[6] - st.R0[2]) / 2;
+  sm.tust[2 * FB + sl.s] = (st.R0[1] - st.R0[3]) / 2;
 }
 
 // ------------------------------------------------------------------ phase B
@@ -614,7 +621,7 @@ HSL_HD void root_ref(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, 
 #pragma unroll
   for (int k = 0; k < 3; k++)
     ref[k] = (MODE == HSL_MODE_FIELDS) ? A.f_pos[((int64_t)sl.i * M.n + M.trunk[0].body) * 3 + k]
-                                       : sm.pos[((3 * NF + 0) * 3 + k) * FB + sl.s];
+                                       : sm.tpos[k * FB + sl.s];
 }
 // Second central difference over +-2 frames.  The reference stages it (dynrec.cpp:175-224): first differences
 // (f(s+1)-f(s-1))*hh at frames s+-1, scaled by the mass / inertia, then their difference times hh again
@@ -625,6 +632,12 @@ HSL_HD double fd2(const double* a, int s, int FB_, double hh, double scale) {
   const double m2 = a[s - 2], c0 = a[s], p2 = a[s + 2];
   (void)FB_;
   return ((p2 - c0) + (m2 - c0)) * (hh * hh * scale);
+}
+// The same for a (position, u sin theta) pair stored as one 16-byte entry: three 128-bit loads.
+HSL_HD void fd2_pair(const HslD2* a, int s, double hh, double scale_x, double scale_y, double* dx, double* dy) {
+  const HslD2 m2 = a[s - 2], c0 = a[s], p2 = a[s + 2];
+  *dx = ((p2.x - c0.x) + (m2.x - c0.x)) * (hh * hh * scale_x);
+  *dy = ((p2.y - c0.y) + (m2.y - c0.y)) * (hh * hh * scale_y);
 }
 // Inverse of a symmetric positive definite 3x3 stored as (00,01,02,11,12,22): adjugate over determinant (one
 // reciprocal, all cofactors independent of each other -- a short dependency chain).  Returns false unless the
@@ -673,8 +686,7 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     for (int h = 0; h < 3; h++) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        f[h][k] = fd2(sm.pos + ((3 * limb + h) * 3 + k) * FB, sl.s, FB, hh, L.h[h].mass);
-        nn[h][k] = fd2(sm.ust + ((3 * limb + h) * 3 + k) * FB, sl.s, FB, hh, L.h[h].inertia);
+        fd2_pair(sm.pu + ((3 * limb + h) * 3 + k) * FB, sl.s, hh, L.h[h].mass, L.h[h].inertia, &f[h][k], &nn[h][k]);
       }
       f[h][2] += L.h[h].mass * M.g;  // dynrec.cpp:293-297
       // joint rate, periodic.cpp:261-282: (q(s+1) - q(s-1)) wrapped to (-pi, pi], over 2 dt.  The wrapped
@@ -782,9 +794,9 @@ HSL_HD void phase_b_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM&
     } else {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        f[k] = fd2(sm.pos + ((3 * NF + tb) * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].mass);
-        nn[k] = fd2(sm.ust + ((3 * NF) * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].inertia);
-        pb[k] = sm.pos[((3 * NF + tb) * 3 + k) * FB + sl.s];
+        f[k] = fd2(sm.tpos + (tb * 3 + k) * FB, sl.s, FB, hh, M.trunk[tb].mass);
+        nn[k] = fd2(sm.tust + k * FB, sl.s, FB, hh, M.trunk[tb].inertia);
+        pb[k] = sm.tpos[(tb * 3 + k) * FB + sl.s];
       }
     }
     f[2] += M.trunk[tb].mass * M.g;
@@ -983,9 +995,9 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& 
         } else {
 #pragma unroll
           for (int k = 0; k < 3; k++) {
-            f[k] = fd2(sm.pos + ((3 * NF + t2) * 3 + k) * FB, sl.s, FB, hh, M.trunk[t2].mass);
-            nn[k] = fd2(sm.ust + ((3 * NF) * 3 + k) * FB, sl.s, FB, hh, M.trunk[t2].inertia);
-            pb[k] = sm.pos[((3 * NF + t2) * 3 + k) * FB + sl.s];
+            f[k] = fd2(sm.tpos + (t2 * 3 + k) * FB, sl.s, FB, hh, M.trunk[t2].mass);
+            nn[k] = fd2(sm.tust + k * FB, sl.s, FB, hh, M.trunk[t2].inertia);
+            pb[k] = sm.tpos[(t2 * 3 + k) * FB + sl.s];
           }
         }
         f[2] += M.trunk[t2].mass * M.g;

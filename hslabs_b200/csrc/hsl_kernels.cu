@@ -29,7 +29,7 @@
 template <int NF, int FB, int MODE, bool DUMP, int MAXREG, int AXP = HSL_AXP_GENERIC>
 __global__ void __maxnreg__(MAXREG)
 hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
-  extern __shared__ double hsl_smem_raw[];
+  extern __shared__ __align__(16) double hsl_smem_raw[];
   HslSmem<NF, FB> sm;
   sm.carve(hsl_smem_raw, M.ntrunk);
   const int role = threadIdx.x / FB;
@@ -118,7 +118,7 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
 template <int NF, int MODE>
 __global__ void hsl_forces_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A) {
   constexpr int FB = 32;
-  extern __shared__ double hsl_smem_raw[];
+  extern __shared__ __align__(16) double hsl_smem_raw[];
   HslSmem<NF, FB, HSL_FORCES_PART> sm;
   sm.carve(hsl_smem_raw, M.ntrunk);
   const int role = threadIdx.x / FB;
@@ -194,7 +194,7 @@ HSL_HD HslSlot hsl_pipe_slot(const HslFrameArgs& A, int64_t tile, int s) {
 template <int NF, int FB, int AXP = HSL_AXP_GENERIC>
 __global__ void __maxnreg__(128)
 hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A, const int64_t n_tiles) {
-  extern __shared__ double hsl_smem_raw[];
+  extern __shared__ __align__(16) double hsl_smem_raw[];
   HslPipeSmem<NF, FB> sm;
   sm.carve(hsl_smem_raw, M.ntrunk);
   const int role = threadIdx.x / FB;
