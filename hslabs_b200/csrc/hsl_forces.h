@@ -136,7 +136,7 @@ HSL_HD int forces_f2_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM
   for (int l = 0; l < NF; l++) {
     const double* P = sm.part + (l * SM::PART) * FB + sl.s;
 #pragma unroll
-    for (int k = 0; k < 6; k++) d[k] += P[k * FB] - P[(40 + k) * FB];
+    for (int k = 0; k < 6; k++) d[k] += part_get<FB>(sm.part + (l * SM::PART) * FB, sl.s, k) - P[(40 + k) * FB];
     int e = 19;
 #pragma unroll
     for (int i = 0; i < 6; i++)

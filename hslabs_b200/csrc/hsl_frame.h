@@ -380,7 +380,23 @@ struct HslSmem {
     mu = part + NF * PARTN * FB;
   }
 };
-// part layout per limb: [0..2] Fl  [3..5] Tl  [6..11] W  [12..14] Wg  [15..17] r  [18] contact flag
+// part fields per limb: [0..2] Fl  [3..5] Tl  [6..11] W  [12..14] Wg  [15..17] r  [18] contact flag.  Fields 0..17 are
+// stored as nine 16-byte pairs (field 2j, 2j+1 of a slot together: [j][slot][2]) so that the solver reads a limb with
+// 9 LDS.128 + 1 LDS.64 instead of 19 LDS.64; fields >= 18 are single doubles at [field][slot] as before.
+template <int FB>
+HSL_HD HslD2 part_pair_load(const double* limb_base, int s, int j) {
+  return reinterpret_cast<const HslD2*>(limb_base)[j * FB + s];
+}
+template <int FB>
+HSL_HD void part_pair_store(double* limb_base, int s, int j, double a, double b) {
+  HslD2 e;
+  e.x = a; e.y = b;
+  reinterpret_cast<HslD2*>(limb_base)[j * FB + s] = e;
+}
+template <int FB>
+HSL_HD double part_get(const double* limb_base, int s, int k) {  // one field 0..17 (dump paths)
+  return limb_base[2 * ((k >> 1) * FB + s) + (k & 1)];
+}
 // (pipelined kernel, PART = 34: + [19..21] tau_p  [22..30] w  [31..33] qdot)
 
 // Where a thread sits.
@@ -729,9 +745,11 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
 #pragma unroll
   for (int k = 0; k < 3; k++) d[k] = st.jpos[0][k] - ref[k];
   v3_cross_add(d, F, T);
-  double* P = sm.part + (limb * SM::PART) * FB + sl.s;
-#pragma unroll
-  for (int k = 0; k < 3; k++) { P[k * FB] = F[k]; P[(3 + k) * FB] = T[k]; }
+  double* Pl = sm.part + (limb * SM::PART) * FB;
+  double* P = Pl + sl.s;
+  part_pair_store<FB>(Pl, sl.s, 0, F[0], F[1]);
+  part_pair_store<FB>(Pl, sl.s, 1, F[2], T[0]);
+  part_pair_store<FB>(Pl, sl.s, 2, T[1], T[2]);
   P[18 * FB] = st.contact ? 1.0 : 0.0;
   // motor torque of the particular solution and its sensitivity to the contact force:
   // tau_h = a_h . T_h - (a_h x rho_h) . lambda ,  rho_h = fpos - jpos_h     (periodic.cpp:328-343)
@@ -764,10 +782,12 @@ HSL_HD void phase_b_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     sym3_mul(st.W, g, st.Wg);
 #pragma unroll
     for (int k = 0; k < 3; k++) st.r[k] = st.fpos[k] - ref[k];
-#pragma unroll
-    for (int k = 0; k < 6; k++) P[(6 + k) * FB] = st.W[k];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { P[(12 + k) * FB] = st.Wg[k]; P[(15 + k) * FB] = st.r[k]; }
+    part_pair_store<FB>(Pl, sl.s, 3, st.W[0], st.W[1]);
+    part_pair_store<FB>(Pl, sl.s, 4, st.W[2], st.W[3]);
+    part_pair_store<FB>(Pl, sl.s, 5, st.W[4], st.W[5]);
+    part_pair_store<FB>(Pl, sl.s, 6, st.Wg[0], st.Wg[1]);
+    part_pair_store<FB>(Pl, sl.s, 7, st.Wg[2], st.r[0]);
+    part_pair_store<FB>(Pl, sl.s, 8, st.r[1], st.r[2]);
   }
 }
 
@@ -866,15 +886,20 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& 
   double rA[3] = {0, 0, 0}, rB[3] = {0, 0, 0};
 #pragma unroll
   for (int l = 0; l < NF; l++) {
-    const double* P = sm.part + (l * SM::PART) * FB + sl.s;
-#pragma unroll
-    for (int k = 0; k < 6; k++) b[k] += P[k * FB];
+    const double* Pl = sm.part + (l * SM::PART) * FB;
+    const double* P = Pl + sl.s;
+    {
+      const HslD2 e0 = part_pair_load<FB>(Pl, sl.s, 0), e1 = part_pair_load<FB>(Pl, sl.s, 1), e2 = part_pair_load<FB>(Pl, sl.s, 2);
+      b[0] += e0.x; b[1] += e0.y; b[2] += e1.x; b[3] += e1.y; b[4] += e2.x; b[5] += e2.y;
+    }
     if (P[18 * FB] != 0.0) {
       double W[6], Wg[3], r[3];
-#pragma unroll
-      for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
-#pragma unroll
-      for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
+      {
+        const HslD2 e3 = part_pair_load<FB>(Pl, sl.s, 3), e4 = part_pair_load<FB>(Pl, sl.s, 4), e5 = part_pair_load<FB>(Pl, sl.s, 5);
+        const HslD2 e6 = part_pair_load<FB>(Pl, sl.s, 6), e7 = part_pair_load<FB>(Pl, sl.s, 7), e8 = part_pair_load<FB>(Pl, sl.s, 8);
+        W[0] = e3.x; W[1] = e3.y; W[2] = e4.x; W[3] = e4.y; W[4] = e5.x; W[5] = e5.y;
+        Wg[0] = e6.x; Wg[1] = e6.y; Wg[2] = e7.x; r[0] = e7.y; r[1] = e8.x; r[2] = e8.y;
+      }
       if (nc == 0) { rA[0] = r[0]; rA[1] = r[1]; rA[2] = r[2]; }
       if (nc == 1) { rB[0] = r[0]; rB[1] = r[1]; rB[2] = r[2]; }
       nc++;
@@ -948,21 +973,22 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& 
     bool con[NF];
 #pragma unroll
     for (int l = 0; l < NF; l++) {
-      const double* P = sm.part + (l * SM::PART) * FB + sl.s;
+      const double* Pl = sm.part + (l * SM::PART) * FB;
+      const double* P = Pl + sl.s;
       con[l] = (P[18 * FB] != 0.0) && (nc >= 2);
       lam[l][0] = lam[l][1] = lam[l][2] = 0;
       if (con[l]) {
         double W[6], y[3], r[3], Wy[3];
 #pragma unroll
-        for (int k = 0; k < 6; k++) W[k] = P[(6 + k) * FB];
+        for (int k = 0; k < 6; k++) W[k] = part_get<FB>(Pl, sl.s, 6 + k);
 #pragma unroll
-        for (int k = 0; k < 3; k++) r[k] = P[(15 + k) * FB];
+        for (int k = 0; k < 3; k++) r[k] = part_get<FB>(Pl, sl.s, 15 + k);
         v3_cross(mu + 3, r, y);
 #pragma unroll
         for (int k = 0; k < 3; k++) y[k] += mu[k];
         sym3_mul(W, y, Wy);
 #pragma unroll
-        for (int k = 0; k < 3; k++) lam[l][k] = -(P[(12 + k) * FB] + Wy[k]);
+        for (int k = 0; k < 3; k++) lam[l][k] = -(part_get<FB>(Pl, sl.s, 12 + k) + Wy[k]);
       }
     }
     double hh = 0;
@@ -1010,15 +1036,15 @@ HSL_HD int phase_c_trunk(const HslModelPod& M, const HslFrameArgs& A, const SM& 
         int a = M.limb[l].attach;
         while (a > tb) a = M.trunk[a].parent_trunk;
         if (a != tb) continue;
-        const double* P = sm.part + (l * SM::PART) * FB + sl.s;
+        const double* Pl = sm.part + (l * SM::PART) * FB;
         double Fl[3], d[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++) { Fl[k] = P[k * FB]; Fb[k] += Fl[k]; Tb[k] += P[(3 + k) * FB]; d[k] = ref[k] - jp[k]; }
+        for (int k = 0; k < 3; k++) { Fl[k] = part_get<FB>(Pl, sl.s, k); Fb[k] += Fl[k]; Tb[k] += part_get<FB>(Pl, sl.s, 3 + k); d[k] = ref[k] - jp[k]; }
         v3_cross_add(d, Fl, Tb);  // move the limb wrench from the root reference point to jp
         if (con[l]) {
           double rr[3];
 #pragma unroll
-          for (int k = 0; k < 3; k++) { rr[k] = P[(15 + k) * FB] + ref[k] - jp[k]; Fb[k] -= lam[l][k]; }
+          for (int k = 0; k < 3; k++) { rr[k] = part_get<FB>(Pl, sl.s, 15 + k) + ref[k] - jp[k]; Fb[k] -= lam[l][k]; }
           double cr[3];
           v3_cross(rr, lam[l], cr);
 #pragma unroll

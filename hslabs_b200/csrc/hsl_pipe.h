@@ -59,15 +59,20 @@ HSL_HD void pipe_store_dstate(const SM& sm, int s, int limb, const HslLegState<f
 template <int NF, int FB, class SM>
 HSL_HD void pipe_d_leg(const SM& sm, int s, int limb) {
   double* D = sm.dstate + (limb * HSL_DSTATE) * FB + s;
-  const double* P = sm.part + (limb * SM::PART) * FB + s;
+  const double* Pl = sm.part + (limb * SM::PART) * FB;
+  const double* P = Pl + s;
   const bool con = (P[18 * FB] != 0.0) && (sm.mu[6 * FB + s] != 0.0);
   double lam[3] = {0, 0, 0};
   if (con) {
     double W[6], Wg[3], r[3], mu[6], y[3], Wy[3];
 #pragma unroll
-    for (int k = 0; k < 6; k++) { W[k] = P[(6 + k) * FB]; mu[k] = sm.mu[k * FB + s]; }
-#pragma unroll
-    for (int k = 0; k < 3; k++) { Wg[k] = P[(12 + k) * FB]; r[k] = P[(15 + k) * FB]; }
+    for (int k = 0; k < 6; k++) mu[k] = sm.mu[k * FB + s];
+    {
+      const HslD2 e3 = part_pair_load<FB>(Pl, s, 3), e4 = part_pair_load<FB>(Pl, s, 4), e5 = part_pair_load<FB>(Pl, s, 5);
+      const HslD2 e6 = part_pair_load<FB>(Pl, s, 6), e7 = part_pair_load<FB>(Pl, s, 7), e8 = part_pair_load<FB>(Pl, s, 8);
+      W[0] = e3.x; W[1] = e3.y; W[2] = e4.x; W[3] = e4.y; W[4] = e5.x; W[5] = e5.y;
+      Wg[0] = e6.x; Wg[1] = e6.y; Wg[2] = e7.x; r[0] = e7.y; r[1] = e8.x; r[2] = e8.y;
+    }
     v3_cross(mu + 3, r, y);
 #pragma unroll
     for (int k = 0; k < 3; k++) y[k] += mu[k];
