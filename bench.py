@@ -135,7 +135,7 @@ def run_reference(args):
             rates.append(rate)
         sample = "%d candidates x %d frames per step on %d threads (%.1f s)" % (n, N_T, cores, dt)
     v = float(np.mean(rates))
-    line = {"impl": "reference", "metric": "frame_solves_per_sec", "value": v, "unit": "frame solves/s", "n_gpus": args.gpus,
+    line = {"impl": "reference", "metric": "frame solves/sec (IK+ID+contact QP)", "value": v, "unit": "frame solves/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (n * N_T) / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "hexapod.xml, %d candidates x %d frames per GPU (BASELINE configs[1]); CPU arm runs a bounded sample" % (N_CAND, N_T)},
@@ -278,7 +278,7 @@ def main():
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = n_cand * (13 * 8 + 4 * 8 + 4) + n_cand * n_t * 0  # cost-only mode: candidates in, costs out
         line = {
-            "metric": "frame_solves_per_sec", "value": value, "unit": "frame solves/s", "n_gpus": world, "steps": args.steps,
+            "metric": "frame solves/sec (IK+ID+contact QP)", "value": value, "unit": "frame solves/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "hexapod.xml, %d candidates x %d frames per GPU (BASELINE configs[1])" % (n_cand, n_t),
