@@ -191,6 +191,35 @@ HSL_HD HslSlot hsl_pipe_slot(const HslFrameArgs& A, int64_t tile, int s) {
   return sl;
 }
 
+// The same slot walked incrementally: a block's tiles are gridDim.x tiles apart, so (candidate, frame) advance by a
+// fixed quotient / remainder per iteration -- two additions and a compare instead of a division at the head of the
+// dependency chain of every phase A.
+template <int NF, int FB>
+struct HslPipeSlotIter {
+  int64_t c, dq;
+  int32_t i, dr, per, s;
+  __device__ __forceinline__ void init(const HslFrameArgs& A, int s_) {
+    s = s_;
+    per = A.n_t + 4;
+    const int64_t g = (int64_t)blockIdx.x * (FB - 4) + s, step = (int64_t)gridDim.x * (FB - 4);
+    c = g / per; i = (int32_t)(g - c * per);
+    dq = step / per; dr = (int32_t)(step - dq * per);
+  }
+  __device__ __forceinline__ HslSlot get(const HslFrameArgs& A) const {
+    HslSlot sl;
+    sl.s = s; sl.c = c; sl.i = i;
+    sl.valid = c < A.n_cand;
+    if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
+    sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
+    sl.fo = sl.c * A.n_t + (sl.i - 2);
+    return sl;
+  }
+  __device__ __forceinline__ void next() {
+    i += dr; c += dq;
+    if (i >= per) { i -= per; c += 1; }
+  }
+};
+
 template <int NF, int FB, int AXP = HSL_AXP_GENERIC>
 __global__ void __maxnreg__(128)
 hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A, const int64_t n_tiles) {
@@ -215,8 +244,10 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
   // HSL_BLOCK_SYNC): neither role's live state enters the other's register allocation.
   if (role < NF) {
     bool p1_int = false;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
+    HslPipeSlotIter<NF, FB> it;
+    it.init(A, s);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it.next()) {
+      const HslSlot sl = it.get(A);
       HslLegState<false> lst;
       HSL_T0();
       phase_a_leg<NF, FB, HSL_MODE_GAIT, false, AXP>(M, A, sm, sl, role, lst);
@@ -256,8 +287,10 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
       const int tb = phase_c_trunk<NF, FB, HSL_MODE_GAIT, false>(M, A, sm, ps, tst);
       if (tb && A.status) atomicOr(&A.status[p1_c], tb);
     };
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
+    HslPipeSlotIter<NF, FB> it;
+    it.init(A, s);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it.next()) {
+      const HslSlot sl = it.get(A);
       HSL_T0();
       if (p1_int) solve();
       HSL_T1(0);
@@ -279,8 +312,10 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
     bool p1_int = false, p2_int = false;
     int64_t p1_fo = 0, p2_fo = 0;
     HslTrunkState tst;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const HslSlot sl = hsl_pipe_slot<NF, FB>(A, tile, s);
+    HslPipeSlotIter<NF, FB> it;
+    it.init(A, s);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it.next()) {
+      const HslSlot sl = it.get(A);
       HSL_T0();
       if (p2_int) pipe_e_trunk<NF, FB>(A, sm, s, p2_fo);
       phase_a_trunk<NF, FB, HSL_MODE_GAIT>(M, A, sm, sl, tst);
