@@ -72,6 +72,8 @@
 struct HslFrameArgs {
   int64_t n_cand;
   int32_t n_t, flags;
+  uint32_t div_magic;  // floor(g / (n_t + 4)) = (g * div_magic) >> div_shift for 0 <= g < 2^31 (set by the launchers):
+  int32_t div_shift;   // a multiply-shift instead of a division at the head of every block's dependency chain
   int64_t n_frames;         // n_cand * n_t solved frames (FIELDS mode: number of frames)
   const HslCand* cand;      // [C]            (GAIT)
   const double* ttab;       // [C][n_t+4]     (GAIT) accumulated frame times, periodic.cpp:87-91

@@ -45,8 +45,8 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
   } else {
     const int per = A.n_t + 4;
     const int64_t g = (int64_t)blockIdx.x * (FB - 4) + sl.s;
-    if (g < 0x7fffffffLL) {  // 32-bit division: the 64-bit one is a ~100-instruction software routine
-      const uint32_t c32 = (uint32_t)g / (uint32_t)per;
+    if (g < 0x7fffffffLL) {  // multiply-shift (exact for g < 2^31, see hsl_set_divider); the 64-bit division is a
+      const uint32_t c32 = (uint32_t)(((uint64_t)(uint32_t)g * A.div_magic) >> A.div_shift);  // ~100-instruction routine
       sl.c = c32;
       sl.i = (int32_t)((uint32_t)g - c32 * (uint32_t)per);
     } else {
@@ -170,30 +170,10 @@ __global__ void hsl_forces_kernel(const __grid_constant__ HslModelPod M, const _
 }
 
 // Persistent, software-pipelined cost-only kernel (schedule and buffer hand-offs in hsl_pipe.h).
-template <int NF, int FB>
-HSL_HD HslSlot hsl_pipe_slot(const HslFrameArgs& A, int64_t tile, int s) {
-  HslSlot sl;
-  sl.s = s;
-  const int per = A.n_t + 4;
-  const int64_t g = tile * (FB - 4) + s;
-  if (g < 0x7fffffffLL) {
-    const uint32_t c32 = (uint32_t)g / (uint32_t)per;
-    sl.c = c32;
-    sl.i = (int32_t)((uint32_t)g - c32 * (uint32_t)per);
-  } else {
-    sl.c = g / per;
-    sl.i = (int32_t)(g - sl.c * per);
-  }
-  sl.valid = sl.c < A.n_cand;
-  if (!sl.valid) { sl.c = A.n_cand - 1; sl.i = 0; }
-  sl.interior = sl.valid && s >= 2 && s < FB - 2 && sl.i >= 2 && sl.i <= A.n_t + 1;
-  sl.fo = sl.c * A.n_t + (sl.i - 2);
-  return sl;
-}
-
-// The same slot walked incrementally: a block's tiles are gridDim.x tiles apart, so (candidate, frame) advance by a
-// fixed quotient / remainder per iteration -- two additions and a compare instead of a division at the head of the
-// dependency chain of every phase A.
+// Slot of a thread: tile t covers the linearised (candidate, frame) indices t (FB-4) + s.  Walked incrementally: a
+// block's tiles are gridDim.x tiles apart, so (candidate, frame) advance by a fixed quotient / remainder per
+// iteration -- two additions and a compare instead of a division at the head of the dependency chain of every
+// phase A.
 template <int NF, int FB>
 struct HslPipeSlotIter {
   int64_t c, dq;
@@ -463,8 +443,19 @@ __global__ void hsl_math_selftest_kernel(int n, const double* __restrict__ a, co
 
 // ------------------------------------------------------------------ launchers
 namespace {
+// floor(g / d) = (g * magic) >> shift for all 0 <= g < 2^31: shift = 31 + ceil(log2 d), magic = ceil(2^shift / d) < 2^32
+void hsl_set_divider(HslFrameArgs& A) {
+  const uint32_t d = (uint32_t)(A.n_t + 4);
+  int l = 0;
+  while ((1u << l) < d) l++;
+  A.div_shift = 31 + l;
+  A.div_magic = (uint32_t)((((uint64_t)1 << A.div_shift) + d - 1) / d);
+}
+
 template <int NF, int FB, int MODE, bool DUMP, int MAXREG = 255, int AXP = HSL_AXP_GENERIC>
-cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
+cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A_in, cudaStream_t st) {
+  HslFrameArgs A = A_in;
+  hsl_set_divider(A);
   const size_t smem = (size_t)HslSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
   auto kern = hsl_frames_kernel<NF, FB, MODE, DUMP, MAXREG, AXP>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
