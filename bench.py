@@ -292,7 +292,7 @@ def main():
                          "frac": achieved_tf / dfma_tf if dfma_tf else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of hsl_gait_pipe_kernel, one ncu --set full capture of
                          # this configuration (profiles/r01_ncu_pipe_kernel_summary.txt); null for other configurations
-                         "traffic": 11567360 if (n_cand, n_t, MODEL) == (4096, 256, "hexapod") and not args.fb else None,
+                         "traffic": 11584000 if (n_cand, n_t, MODEL) == (4096, 256, "hexapod") and not args.fb else None,
                          "peak_source": "measured live: register-resident DFMA probe kernel (MEASURED_PEAKS.json has no FP64 figure)",
                          "flops_per_frame": flops_per_frame, "kernel_ms": k_ms,
                          "hbm": {"achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
