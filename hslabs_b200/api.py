@@ -60,6 +60,8 @@ def _load():
     lib.hsl_eval_trajectories_host.argtypes = [vp, i64, i32] + [vp] * 9
     lib.hsl_solve_frames_host.argtypes = [vp, i64] + [vp] * 11
     lib.hsl_solve_forces_host.argtypes = [vp, i64] + [vp] * 9
+    lib.hsl_gait_records_host.argtypes = [vp, i64, vp, i32, vp, i32, vp, vp]
+    lib.hsl_ik_records_host.argtypes = [vp, i64, vp, i32, vp, vp]
     lib.hsl_solve_forces_gait_host.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
     lib.hsl_set_rec_transform.argtypes = [vp, vp, vp]
@@ -75,7 +77,7 @@ def exported_symbols():
     """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
-            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_launch_count",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
 
 
@@ -203,6 +205,23 @@ class Model:
         _check(_load().hsl_solve_frames_host(self._h, f, *[_p(a) for a in arrs], _p(contacts), _p(out["x"]), _p(out["z"]),
                                              _p(out["tau"]), _p(out["status"])))
         return out
+
+    def gait_records(self, params, times, flags=0):
+        """pergensetup::set_rec (pergen.cpp:225-239): records [C][len(times)][6+3nf] of the candidates at the given times."""
+        params = np.ascontiguousarray(params, np.float64).reshape(-1, HSL_NPARAM)
+        times = np.ascontiguousarray(times, np.float64).reshape(-1)
+        c = params.shape[0]
+        rec = np.empty((c, times.shape[0], 6 + 3 * self.nf)); status = np.empty(c, np.int32)
+        _check(_load().hsl_gait_records_host(self._h, c, _p(params), times.shape[0], _p(times), flags, _p(rec), _p(status)))
+        return dict(rec=rec, status=status)
+
+    def ik_records(self, rec, flags=0):
+        """kinematicmodel::set_jvalues_with_lik + get_jvalues: joint values [n][config_dim] of records [n][6+3nf]."""
+        rec = np.ascontiguousarray(rec, np.float64).reshape(-1, 6 + 3 * self.nf)
+        n = rec.shape[0]
+        q = np.empty((n, self.config_dim)); status = np.empty(n, np.int32)
+        _check(_load().hsl_ik_records_host(self._h, n, _p(rec), flags, _p(q), _p(status)))
+        return dict(q=q, status=status)
 
     def solve_forces(self, pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos, torques):
         """forcetorquesolver::solve_forces (ftsolver.cpp:331-378): contact forces of all feet for given motor torques."""

@@ -395,6 +395,63 @@ int hsl_solve_frames_host(HslModel* m, int64_t F, const double* pos, const doubl
   return HSL_OK;
 }
 
+// ---------------------------------------------------------------- record-level entries (a2, a3)
+int hsl_gait_records_host(HslModel* m, int64_t C, const double* params, int n_times, const double* times, int flags, double* rec,
+                          int32_t* status) {
+  if (!m || C < 1 || n_times < 1 || !params || !times || !rec) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const int rl = 6 + 3 * P.nf;
+  const size_t pbytes = sizeof(double) * HSL_NPARAM * C, tbytes = sizeof(double) * n_times, rbytes = sizeof(double) * rl * C * n_times;
+  HSL_CUDA(m->params.need(pbytes));
+  HSL_CUDA(m->in_b.need(tbytes));
+  HSL_CUDA(m->in_a.need(rbytes));
+  HSL_CUDA(m->cand.need(sizeof(HslCand) * C));
+  HSL_CUDA(m->ttab.need(sizeof(double) * C * 5));
+  HSL_CUDA(m->status.need(sizeof(int32_t) * C));
+  HSL_CUDA(cudaMemcpyAsync(m->params.p, params, pbytes, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemcpyAsync(m->in_b.p, times, tbytes, cudaMemcpyHostToDevice, st));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = 1; A.flags = flags & ~HSL_FLAG_REC_TRANSFORM;
+  A.cand = (const HslCand*)m->cand.p;
+  if (m->rec_on) {
+    A.flags |= HSL_FLAG_REC_TRANSFORM;
+    memcpy(A.rec_R, m->rec_R, sizeof A.rec_R);
+    memcpy(A.rec_t, m->rec_t, sizeof A.rec_t);
+  }
+  // the candidate constants do not depend on n_t except for dt / the time table, which this entry does not use
+  HSL_CUDA(hsl_launch_setup(P, C, 1, (const double*)m->params.p, (HslCand*)m->cand.p, (double*)m->ttab.p, (int32_t*)m->status.p, st));
+  HSL_CUDA(hsl_launch_gait_records(P, A, n_times, (const double*)m->in_b.p, (double*)m->in_a.p, st));
+  m->launches += 2;
+  HSL_CUDA(cudaMemcpyAsync(rec, m->in_a.p, rbytes, cudaMemcpyDeviceToHost, st));
+  if (status) HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * C, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
+  return HSL_OK;
+}
+
+int hsl_ik_records_host(HslModel* m, int64_t n, const double* rec, int flags, double* q, int32_t* status) {
+  if (!m || n < 1 || !rec || !q) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const size_t rbytes = sizeof(double) * (6 + 3 * P.nf) * n, qbytes = sizeof(double) * P.config_dim * n;
+  HSL_CUDA(m->in_a.need(rbytes));
+  HSL_CUDA(m->in_b.need(qbytes));
+  HSL_CUDA(m->status.need(sizeof(int32_t) * n));
+  HSL_CUDA(cudaMemcpyAsync(m->in_a.p, rec, rbytes, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * n, st));
+  HSL_CUDA(hsl_launch_ik_records(P, n, flags, (const double*)m->in_a.p, (double*)m->in_b.p, (int32_t*)m->status.p, st));
+  m->launches += 1;
+  HSL_CUDA(cudaMemcpyAsync(q, m->in_b.p, qbytes, cudaMemcpyDeviceToHost, st));
+  if (status) HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
+  return HSL_OK;
+}
+
 // ---------------------------------------------------------------- forces from torques (hsl_forces.h)
 int hsl_solve_forces_host(HslModel* m, int64_t F, const double* pos, const double* jpos, const double* jzaxis, const double* mom_rate,
                           const double* ang_mom_rate, const double* fpos, const double* torques, double* z, int32_t* status) {

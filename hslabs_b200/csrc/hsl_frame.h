@@ -497,6 +497,21 @@ HSL_HD void hinge_fk(const HslHinge& H, double cs, double sn, const double* Rp, 
   ust[2] = (Rb[1] - Rb[3]) / 2;
 }
 
+// Foot target p (world) into the hip joint frame of limb L (lik.cpp:341-347): R0, t0 = torso rotation / body origin.
+HSL_HD void foot_into_hip_frame(const HslLimb& L, const double* R0, const double* t0, const double* p, double* pl) {
+  double ta[3], th[3], d[3], e[3];
+  m3_affine(R0, L.oatt, t0, ta);       // frame of the trunk body the limb hangs from
+  m3_affine(R0, L.h[0].tjp, ta, th);   // hip joint origin
+#pragma unroll
+  for (int k = 0; k < 3; k++) d[k] = p[k] - th[k];
+  // (R0 Rjp)^T d = Rjp^T (R0^T d): two matrix-vector products instead of a matrix-matrix product
+#pragma unroll
+  for (int k = 0; k < 3; k++) e[k] = R0[3 * k] * d[0] + R0[3 * k + 1] * d[1] + R0[3 * k + 2] * d[2];
+  const double* Rj0 = L.h[0].Rjp;
+#pragma unroll
+  for (int k = 0; k < 3; k++) pl[k] = Rj0[3 * k] * e[0] + Rj0[3 * k + 1] * e[1] + Rj0[3 * k + 2] * e[2];
+}
+
 template <int NF, int FB, int MODE, bool DUMP, int AXP = 0, class SM>
 HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& sm, const HslSlot& sl, int limb,
                         HslLegState<DUMP>& st) {
@@ -534,18 +549,8 @@ HSL_HD void phase_a_leg(const HslModelPod& M, const HslFrameArgs& A, const SM& s
     if (A.flags & HSL_FLAG_REC_TRANSFORM) rec_transform_point(A, p);
 #pragma unroll
     for (int k = 0; k < 3; k++) oj[k] = L.oatt[k];
-    double ta[3], e[3];
-    m3_affine(R0, oj, t0, ta);           // frame of the trunk body the limb hangs from
-    m3_affine(R0, L.h[0].tjp, ta, th);   // hip joint origin
-#pragma unroll
-    for (int k = 0; k < 3; k++) d[k] = p[k] - th[k];
-    // (R0 Rjp)^T d = Rjp^T (R0^T d): two matrix-vector products instead of a matrix-matrix product
-#pragma unroll
-    for (int k = 0; k < 3; k++) e[k] = R0[3 * k] * d[0] + R0[3 * k + 1] * d[1] + R0[3 * k + 2] * d[2];
-    const double* Rj0 = L.h[0].Rjp;
-#pragma unroll
-    for (int k = 0; k < 3; k++) pl[k] = Rj0[3 * k] * e[0] + Rj0[3 * k + 1] * e[1] + Rj0[3 * k + 2] * e[2];
-    (void)Rh;
+    foot_into_hip_frame(L, R0, t0, p, pl);
+    (void)Rh; (void)th; (void)oj; (void)d;
     const bool want_angles = DUMP && A.q_out != nullptr;
     if (!limb_ik<AXP>(L, pl, (A.flags & HSL_FLAG_IGNORE_REACH) != 0, cq, sq, want_angles ? qa : nullptr)) st.bad |= HSL_ST_UNREACHABLE;
   } else {  // HSL_MODE_TRAJ
@@ -1145,6 +1150,47 @@ HSL_HD void phase_e_trunk(const HslFrameArgs& A, const SM& sm, const HslSlot& sl
 
 // ------------------------------------------------------------------ candidate setup (a1)
 // pgssweeper::setup_pergen / partial_setup_pergen / setup_foot_shift / shift_pos0 (pergen.cpp:453-507),
+// ------------------------------------------------------------------ record-level entries (a2, a3 on their own)
+// pergensetup::set_rec (pergen.cpp:225-239): frame record of candidate cd at time t -- torso position and Euler
+// angles, then the foot targets in LIK order.  One call per (record, role): role < nf writes that limb's target,
+// role == nf the torso entries.
+HSL_HD void gait_record(const HslFrameArgs& A, const HslCand& c, int nf, int role, double t, double* rec) {
+  HslCandView cd;
+  load_cand(c, role < nf ? role : -1, cd);
+  if (role < nf) {
+    double p[3];
+    foot_target(cd, t, p);
+    if (A.flags & HSL_FLAG_REC_TRANSFORM) rec_transform_point(A, p);
+#pragma unroll
+    for (int k = 0; k < 3; k++) rec[6 + 3 * role + k] = p[k];
+  } else {
+    double qt[3], R0[9], eul[3];
+    torso_pose(cd, t, qt, R0, eul);
+    if (A.flags & HSL_FLAG_REC_TRANSFORM) rec_transform_pose(A, qt, R0, eul);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { rec[k] = qt[k]; rec[3 + k] = eul[k]; }
+  }
+}
+// kinematicmodel::set_jvalues_with_lik / liksolver::place_limbs (model.cpp:354-359, lik.cpp:89-99,316-354): joint
+// values of a record.  role < nf: the three hinge angles of that limb (false when out of reach); role == nf: the
+// torso's six values.
+HSL_HD bool ik_record(const HslModelPod& M, int role, const double* rec, bool ignore_reach, double* q) {
+  if (role >= M.nf) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) q[k] = rec[k];
+    return true;
+  }
+  const HslLimb& L = M.limb[role];
+  double R0[9], t0[3], pl[3], cq[3], sq[3], ang[3];
+  euler_to_R(rec[3], rec[4], rec[5], R0);
+  torso_frame(M, rec, R0, t0);
+  foot_into_hip_frame(L, R0, t0, rec + 6 + 3 * role, pl);
+  const bool ok = limb_ik<0>(L, pl, ignore_reach, cq, sq, ang);
+#pragma unroll
+  for (int h = 0; h < 3; h++) q[6 + 3 * role + h] = ang[h];
+  return ok;
+}
+
 // periodicgenerator::set_step_duration / compute_max_radius (pergen.cpp:30-51,144-154),
 // periodic::record_trajectory time base (periodic.cpp:84-91).  p = 13 candidate scalars (include/hsl.h).
 HSL_HD void setup_candidate(const HslModelPod& M, const double* p, int n_t, HslCand& cd, double* ttab) {

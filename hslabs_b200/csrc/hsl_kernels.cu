@@ -330,6 +330,29 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
 #endif
 }
 
+// Record-level entries: one thread per (record, role), role = limb 0..nf-1 | torso.
+// rec [C][n_times][6+3nf] for candidates cand[C] at times[n_times]               (pergensetup::set_rec)
+__global__ void hsl_gait_records_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__ HslFrameArgs A, int n_times,
+                                        const double* __restrict__ times, double* __restrict__ rec) {
+  const int roles = M.nf + 1, rl = 6 + 3 * M.nf;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = g / roles;
+  if (r >= A.n_cand * n_times) return;
+  const int role = (int)(g - r * roles);
+  const int64_t c = r / n_times;
+  gait_record(A, A.cand[c], M.nf, role, times[r - c * n_times], rec + r * rl);
+}
+// q [n][config_dim] for records rec [n][6+3nf]; status [n] gets HSL_ST_UNREACHABLE    (kinematicmodel::set_jvalues_with_lik)
+__global__ void hsl_ik_records_kernel(const __grid_constant__ HslModelPod M, int64_t n, int flags, const double* __restrict__ rec,
+                                      double* __restrict__ q, int32_t* __restrict__ status) {
+  const int roles = M.nf + 1, rl = 6 + 3 * M.nf;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = g / roles;
+  if (r >= n) return;
+  const int role = (int)(g - r * roles);
+  if (!ik_record(M, role, rec + r * rl, (flags & HSL_FLAG_IGNORE_REACH) != 0, q + r * M.config_dim)) atomicOr(&status[r], HSL_ST_UNREACHABLE);
+}
+
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
                                  HslCand* __restrict__ cand, double* __restrict__ ttab, int32_t* __restrict__ status) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -571,6 +594,19 @@ cudaError_t hsl_launch_forces(const HslModelPod& M, const HslFrameArgs& A, int m
   if (M.nf == 6) return mode == HSL_MODE_GAIT ? launch_forces_t<6, HSL_MODE_GAIT>(M, A, st) : launch_forces_t<6, HSL_MODE_FIELDS>(M, A, st);
   if (M.nf == 4) return mode == HSL_MODE_GAIT ? launch_forces_t<4, HSL_MODE_GAIT>(M, A, st) : launch_forces_t<4, HSL_MODE_FIELDS>(M, A, st);
   return cudaErrorInvalidValue;
+}
+
+cudaError_t hsl_launch_gait_records(const HslModelPod& M, const HslFrameArgs& A, int n_times, const double* times, double* rec,
+                                    cudaStream_t st) {
+  const int64_t threads = A.n_cand * n_times * (M.nf + 1);
+  hsl_gait_records_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(M, A, n_times, times, rec);
+  return cudaGetLastError();
+}
+cudaError_t hsl_launch_ik_records(const HslModelPod& M, int64_t n, int flags, const double* rec, double* q, int32_t* status,
+                                  cudaStream_t st) {
+  const int64_t threads = n * (M.nf + 1);
+  hsl_ik_records_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(M, n, flags, rec, q, status);
+  return cudaGetLastError();
 }
 
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,

@@ -89,6 +89,16 @@ int hsl_solve_frames_host(HslModel* m, int64_t n_frames, const double* pos, cons
                           const double* mom_rate, const double* ang_mom_rate, const double* fpos, const uint8_t* contacts,
                           double* x, double* z, double* tau, int32_t* status);
 
+/* pergensetup::set_rec (pergen.cpp:225-239): frame records rec [n_cand][n_times][6+3nf] (torso position, Euler angles,
+ * foot targets in LIK order) of the candidates params [n_cand][13] at the times [n_times]; honours
+ * hsl_set_rec_transform.  status [n_cand] (HSL_ST_BAD_PARAMS).  HOST pointers. */
+int hsl_gait_records_host(HslModel* m, int64_t n_cand, const double* params, int n_times, const double* times, int flags,
+                          double* rec, int32_t* status);
+/* kinematicmodel::set_jvalues_with_lik + get_jvalues / liksolver::place_limbs (model.cpp:354-359,369-372,
+ * lik.cpp:89-99,316-354): joint values q [n][config_dim] of the records rec [n][6+3nf]; status [n] gets
+ * HSL_ST_UNREACHABLE where the reference prints "LIK ERROR" and exits (unless HSL_FLAG_IGNORE_REACH).  HOST pointers. */
+int hsl_ik_records_host(HslModel* m, int64_t n, const double* rec, int flags, double* q, int32_t* status);
+
 /* forcetorquesolver::solve_forces (ftsolver.cpp:331-378): least-squares contact forces of ALL feet for given motor
  * torques, torso joint force/torque forced to zero, on populated dynrecords (layouts as hsl_solve_frames_host;
  * torques [n_frames][nmj]; output z [n_frames][3nf]; status [n_frames], HSL_ST_SOLVER when a limb is singular). */

@@ -74,6 +74,19 @@ class kinematicmodel {
   int number_of_limbs() const { return dims_[1]; }
   double get_rcap() const { return hsl_model_rcap(h_); }  // liksolver::get_rcap
   HslModel* handle() const { return h_; }
+  // model.cpp:354-372: joint values from a record (closed-form limb IK on the GPU), plain setter / getter
+  void set_jvalues_with_lik(const double* rec) {
+    jvalues_.assign(dims_[3], 0.0);
+    int32_t status = 0;
+    check(hsl_ik_records_host(h_, 1, rec, ignore_reach_ ? HSL_FLAG_IGNORE_REACH : 0, jvalues_.data(), &status));
+    if (status & HSL_ST_UNREACHABLE) throw error("LIK ERROR: limb position is unreachable");  // lik.cpp:161-164
+  }
+  void set_jvalues(const double* values) { jvalues_.assign(values, values + dims_[3]); }
+  void get_jvalues(double* values) const { for (size_t i = 0; i < jvalues_.size(); i++) values[i] = jvalues_[i]; }
+  void set_ignore_reach_flag(bool v) { ignore_reach_ = v; }  // liksolver::set_ignore_reach_flag, lik.cpp:142-146
+ private:
+  std::vector<double> jvalues_;
+  bool ignore_reach_ = false;
 };
 
 // periodicgenerator accessors used by callers (pergen.h:38-41)
@@ -102,9 +115,22 @@ class pergensetup {
   pgsconfigparams pcp_;
   periodicgenerator_view view_;
   rectransform rec_;
+  const kinematicmodel* model_;  // set by make_pergensu / pgssweeper: the reference bakes the model's default foot
+                                 // positions into the pergensetup at that point (pergen.cpp:453-507)
  public:
-  explicit pergensetup(int n) : n_(n), view_(&pcp_) {}
-  pergensetup(const pergensetup& o) : n_(o.n_), pcp_(o.pcp_), view_(&pcp_), rec_(o.rec_) {}
+  explicit pergensetup(int n, const kinematicmodel* model = nullptr) : n_(n), view_(&pcp_), model_(model) {}
+  pergensetup(const pergensetup& o) : n_(o.n_), pcp_(o.pcp_), view_(&pcp_), rec_(o.rec_), model_(o.model_) {}
+  const kinematicmodel* get_model() const { return model_; }
+  // pergen.cpp:225-239: frame record (torso position, Euler angles, foot targets in LIK order) at time t
+  void set_rec(double* rec, double t) const {
+    if (!model_) throw error("pergensetup::set_rec needs the model the setup was made for");
+    double row[HSL_NPARAM];
+    pcp_.to_row(row);
+    int32_t status = 0;
+    rec_.apply(model_->handle());
+    check(hsl_gait_records_host(model_->handle(), 1, row, 1, &t, 0, rec, &status));
+    if (status & HSL_ST_BAD_PARAMS) throw error("ERROR: step_duration out of bounds");
+  }
   // pergen.cpp:309-313: keeps the translation, replaces the rotation (eas = phi, theta, psi)
   void set_rec_rotation(const double rec_eas[3]) { for (int k = 0; k < 3; k++) rec_.eas[k] = rec_eas[k]; rec_.flag = true; }
   void copy_rec_transform(const pergensetup* pgs) { rec_ = pgs->rec_; }  // pergen.cpp:338-342
@@ -149,7 +175,7 @@ class pgssweeper {
     pgsconfigparams pcp;
     pgs0_->get_config_params(&pcp);
     if (parami_ == 0) pcp.step_duration = val_; else pcp.TLh[parami_ - 1] = val_;
-    pgs_ = new pergensetup(pgs0_->get_limb_number());
+    pgs_ = new pergensetup(pgs0_->get_limb_number(), pgs0_->get_model());
     pgs_->set_config_params(pcp);
     pgs_->copy_rec_transform(pgs0_);  // pergen.cpp:446
     return true;
@@ -368,7 +394,7 @@ class modelplayer {
     const std::string path = model_dir + "/" + pcp.fname;
     if (!model_.if_loaded()) load_model(path);
     else if (model_.get_xmlfname() != path) throw error("ERROR: model not from " + pcp.fname);
-    pergensetup* pgs = new pergensetup(model_.number_of_limbs());
+    pergensetup* pgs = new pergensetup(model_.number_of_limbs(), &model_);
     pgs->set_config_params(pcp);
     return pgs;
   }

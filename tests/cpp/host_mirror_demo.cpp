@@ -38,6 +38,20 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 3 * nf; i++) std::printf(" %.17g", cf1[i]);
     std::printf("\n");
     if (argc > 4) player0.record_per_traj(pgs, argv[4]);
+    // the two kinematic seams on their own: pergensetup::set_rec and kinematicmodel::set_jvalues_with_lik
+    {
+      const int cd = player0.get_model()->get_config_dim();
+      std::vector<double> rec(6 + 3 * nf), q(cd);
+      pgs->set_rec(rec.data(), 0.7);
+      hsl::kinematicmodel* km = const_cast<hsl::kinematicmodel*>(player0.get_model());
+      km->set_jvalues_with_lik(rec.data());
+      km->get_jvalues(q.data());
+      std::printf("rec:");
+      for (size_t i = 0; i < rec.size(); i++) std::printf(" %.17g", rec[i]);
+      std::printf("\njvalues:");
+      for (int i = 0; i < cd; i++) std::printf(" %.17g", q[i]);
+      std::printf("\n");
+    }
     // main.cpp:38: extvec rec_eas (0,0,-1.571); pgs->set_rec_rotation(rec_eas);  -- sweep candidates inherit it (pergen.cpp:446)
     const double rec_eas[3] = {0, 0, -1.571};
     pgs->set_rec_rotation(rec_eas);

@@ -446,4 +446,41 @@ int hc_solve_forces_fields(const char* xml, int64_t F, const double* pos, const 
   transpose_out(dz, 3 * M.nf, F, z);
   return 0;
 }
+
+// record-level entries (serial mirror of hsl_gait_records_kernel / hsl_ik_records_kernel)
+int hc_gait_records(const char* xml, int64_t C, const double* params, int n_times, const double* times, int flags, double* rec,
+                    int32_t* status) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  const int rl = 6 + 3 * M.nf;
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = 1; A.flags = flags;
+  apply_rec(A);
+  for (int64_t c = 0; c < C; c++) {
+    HslCand cd;
+    double ttab[5];
+    setup_candidate(M, params + HSL_NPARAM * c, 1, cd, ttab);
+    if (status) status[c] = cd.status;
+    for (int k = 0; k < n_times; k++)
+      for (int role = 0; role <= M.nf; role++) gait_record(A, cd, M.nf, role, times[k], rec + (c * n_times + k) * rl);
+  }
+  return 0;
+}
+int hc_ik_records(const char* xml, int64_t n, const double* rec, int flags, double* q, int32_t* status) {
+  HslModelPod M;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  const int rl = 6 + 3 * M.nf;
+  for (int64_t r = 0; r < n; r++) {
+    int st = 0;
+    for (int role = 0; role <= M.nf; role++)
+      if (!ik_record(M, role, rec + r * rl, (flags & HSL_FLAG_IGNORE_REACH) != 0, q + r * M.config_dim)) st |= HSL_ST_UNREACHABLE;
+    if (status) status[r] = st;
+  }
+  return 0;
+}
 }

@@ -107,6 +107,27 @@ def solve_forces_fields(xml, f, tau):
     return dict(z=z, status=status)
 
 
+def gait_records(xml, params, times, flags=0):
+    params = np.ascontiguousarray(params, np.float64).reshape(-1, 13)
+    times = np.ascontiguousarray(times, np.float64).reshape(-1)
+    d = model_dims(xml)
+    c = params.shape[0]
+    rec = np.zeros((c, times.shape[0], 6 + 3 * d["nf"])); status = np.zeros(c, np.int32)
+    rc = lib().hc_gait_records(xml.encode(), C.c_int64(c), _p(params), C.c_int(times.shape[0]), _p(times), C.c_int(flags), _p(rec), _p(status))
+    assert rc == 0, rc
+    return dict(rec=rec, status=status)
+
+
+def ik_records(xml, rec, flags=0):
+    d = model_dims(xml)
+    rec = np.ascontiguousarray(rec, np.float64).reshape(-1, 6 + 3 * d["nf"])
+    n = rec.shape[0]
+    q = np.zeros((n, d["config_dim"])); status = np.zeros(n, np.int32)
+    rc = lib().hc_ik_records(xml.encode(), C.c_int64(n), _p(rec), C.c_int(flags), _p(q), _p(status))
+    assert rc == 0, rc
+    return dict(q=q, status=status)
+
+
 def eval_gaits_pipe(xml, params, n_t, flags=0, fb=64, grid=3):
     """Serial emulation of the persistent pipelined cost-only kernel."""
     params = np.ascontiguousarray(params, np.float64).reshape(-1, 13)

@@ -93,7 +93,9 @@ def test_no_cpu_fallback(hsl):
                  lambda: m.eval_trajectories(np.zeros((1, 25, m.config_dim)), 0.1, 20),
                  lambda: m.solve_frames(z3, z3, z3, z3, z3, zf, np.ones((2, nf), np.uint8)),
                  lambda: m.solve_forces(z3, z3, z3, z3, z3, zf, np.zeros((2, nmj))),
-                 lambda: m.solve_forces_gait(p, 20, np.zeros((1, 20, nmj)))):
+                 lambda: m.solve_forces_gait(p, 20, np.zeros((1, 20, nmj))),
+                 lambda: m.gait_records(p, [0.0, 0.5]),
+                 lambda: m.ik_records(np.zeros((2, 6 + 3 * nf)))):
         with pytest.raises(hsl.HslError, match="CUDA"):
             call()
 

@@ -49,6 +49,15 @@ def test_main_like_sequence(demo, orc, pid, tmp_path):
     assert np.abs(cf1 - ref_cf1).max() <= 1e-9 * np.abs(ref["z"]).max()
     if m.nf == 6:
         assert float(re.search(r"s = (\S+)", out.stdout).group(1)) < 1e-9
+    # pergensetup::set_rec / kinematicmodel::set_jvalues_with_lik on their own
+    rec = np.array([float(v) for v in re.search(r"^rec:(.*)$", out.stdout, re.M).group(1).split()])
+    jv = np.array([float(v) for v in re.search(r"^jvalues:(.*)$", out.stdout, re.M).group(1).split()])
+    ref_rec = m.gait_rec(params, 0.7)
+    assert np.abs(rec - ref_rec).max() < 1e-12
+    rc, ref_q = m.ik(ref_rec)
+    assert rc == 0
+    dq = np.abs(jv - ref_q); dq[6:] = np.minimum(dq[6:], np.abs(dq[6:] - 2 * np.pi))
+    assert dq.max() < 1e-12
     # set_rec_rotation (main.cpp:38, pergen.cpp:309-313) on the candidate and on the sweep built from it
     rec = ((0, 0, 0), (0, 0, -1.571))
     rot = float(re.search(r"rotated COT = (\S+)", out.stdout).group(1))

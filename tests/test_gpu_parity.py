@@ -326,3 +326,31 @@ def test_forces_from_torques(hsl, orc, pid):
     zb = m.solve_forces_gait(p2, n_t, t2)["z"]
     assert rel_err(zb[0], om.solve_forces_frames(params, n_t, t2[0])) < TOL
     assert rel_err(zb[1], om.solve_forces_frames(params, n_t, t2[1])) < TOL
+
+
+@pytest.mark.parametrize("pid", [8, 9, 12, 24, 20])
+def test_record_level_entries(hsl, orc, pid):
+    """pergensetup::set_rec and kinematicmodel::set_jvalues_with_lik through the C ABI (hsl_gait_records_host,
+    hsl_ik_records_host) against the oracle: records at arbitrary times, joint values of arbitrary records."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    om = orc.Model(xml)
+    m = hsl.Model(xml)
+    times = np.array([0.0, 0.137, 1.0, 2.75, 7.3, 19.9])
+    p2 = np.stack([params, params]); p2[1, 8] *= 0.5
+    got = m.gait_records(p2, times)
+    assert (got["status"] == 0).all()
+    for c in range(2):
+        for k, t in enumerate(times):
+            assert np.abs(got["rec"][c, k] - om.gait_rec(p2[c], float(t))).max() < 1e-12, (c, k)
+    recs = got["rec"].reshape(-1, got["rec"].shape[-1])
+    far = recs[0].copy(); far[6:9] += 5.0
+    ik = m.ik_records(np.vstack([recs, far[None]]))
+    for k in range(recs.shape[0]):
+        rc, q = om.ik(recs[k])
+        assert (ik["status"][k] == 2) == (rc != 0)
+        if rc == 0:
+            d = np.abs(ik["q"][k] - q); d[6:] = np.minimum(d[6:], np.abs(d[6:] - 2 * np.pi))
+            assert d.max() < 1e-12
+    assert ik["status"][-1] == 2
+    assert m.ik_records(far, flags=hsl.HSL_FLAG_IGNORE_REACH)["status"][0] == 0

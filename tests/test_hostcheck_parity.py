@@ -216,3 +216,36 @@ def test_axis_specialised_kernels_equal_generic(model, pattern):
     for k in ("cot", "work", "x", "z", "tau", "traj"):
         assert rel_err(a[k], b[k]) < 1e-13, k
     assert rel_err(ap["cot"], bp["cot"]) < 1e-13
+
+
+@pytest.mark.parametrize("pid", [8, 9, 12, 24, 20])
+def test_record_level_entries(orc, pid):
+    """pergensetup::set_rec (pergen.cpp:225-239) and kinematicmodel::set_jvalues_with_lik (model.cpp:354-359) on their
+    own: frame records of a candidate at arbitrary times, and the joint values of arbitrary records."""
+    params, name = orc.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    om = orc.Model(xml)
+    times = np.array([0.0, 0.137, 1.0, 2.75, 7.3, 19.9])
+    got = hostlib.gait_records(xml, params, times)
+    assert got["status"][0] == 0
+    for k, t in enumerate(times):
+        ref = om.gait_rec(params, float(t))
+        assert np.abs(got["rec"][0, k] - ref).max() < 1e-12, (k, t)
+    # with a rec_transform
+    hostlib.set_rec_transform((0.1, -0.2, 0.0), (0, 0, 0.6))
+    try:
+        tr = hostlib.gait_records(xml, params, times[:2])["rec"][0]
+    finally:
+        hostlib.set_rec_transform()
+    assert np.abs(tr - got["rec"][0, :2]).max() > 1e-3
+    # IK of those records: the oracle's joint values (mod 2 pi), unreachable records flagged
+    ik = hostlib.ik_records(xml, got["rec"][0])
+    for k in range(len(times)):
+        rc, q = om.ik(got["rec"][0, k])
+        if rc:
+            assert ik["status"][k] == 2
+        else:
+            assert ik["status"][k] == 0
+            assert angle_err(ik["q"][k][None, :], q[None, :]) < 1e-12
+    far = got["rec"][0, 0].copy(); far[6:9] += 5.0           # a foot five metres away
+    assert hostlib.ik_records(xml, far)["status"][0] == 2
