@@ -157,3 +157,44 @@ def test_random_candidates_equal_lapack(orc, model, zlo, zhi, shift):
             checked += 1
             seen.add(int(fr["contacts"].sum()))
     assert checked >= 64 and len(seen) >= 2, (checked, seen)
+
+
+@pytest.mark.parametrize("pid", [0, 8, 24])
+def test_oracle_frame_fields_equal_numpy(orc, pid):
+    """The per-frame inputs of the solve (a6, a7), recomputed in numpy from the oracle's own trajectory and body
+    frames: COM / foot positions (visualization.cpp:541-568), u sin(theta) = vee(A - A^T)/2 and the contact flags
+    (dynrecord::initialize, dynrec.cpp:134-155), hinge axes (dynpart::get_joint_zaxis, dynrec.cpp:84-93), and the
+    two central-difference stages with unit mass / unit inertia (dynrecord::compute_ders, dynrec.cpp:175-224):
+    mom_rate[i] = (pos[i+2] - 2 pos[i] + pos[i-2]) / (2 dt)^2, likewise ang_mom_rate from u sin(theta)."""
+    params, name = orc.load_preset(PRESETS, pid)
+    m = orc.Model(model_xml(name))
+    n_t = 20
+    ref = m.measure_cot(params, n_t, detail=True)
+    fields = m.frame_fields(params, n_t)
+    k = m.constants()
+    dt = params[7] / n_t  # periodic::record_trajectory, periodic.cpp:77-96
+    n, nf = m.n, m.nf
+    pos = np.zeros((n_t + 5, n, 3)); ust = np.zeros((n_t + 5, n, 3))
+    for i in range(n_t + 5):
+        A, J = m.fk(ref["traj"][i])
+        M = A.reshape(n, 4, 4).transpose(0, 2, 1)  # affine data is column-major (matrix.cpp:144-146)
+        com = np.concatenate([k["A_body_geom"][:, 12:15], np.ones((n, 1))], axis=1)
+        pos[i] = np.einsum("bij,bj->bi", M, com)[:, :3]
+        R = M[:, :3, :3]
+        ust[i] = 0.5 * np.stack([R[:, 2, 1] - R[:, 1, 2], R[:, 0, 2] - R[:, 2, 0], R[:, 1, 0] - R[:, 0, 1]], axis=1)
+        t = i - 2
+        if 0 <= t < n_t:
+            assert np.abs(pos[i] - fields["pos"][t]).max() < 1e-13
+            jz = J.reshape(n, 16)[:, 8:11] * (k["jkind"] != 0)[:, None]  # zero for bodies without a joint
+            assert np.abs(jz - fields["jzaxis"][t]).max() < 1e-13
+            for fi, b in enumerate(k["limb_foot"]):
+                fp = M[b] @ np.append(k["capsule_to_pos"][b], 1.0)
+                assert np.abs(fp[:3] - fields["fpos"][t][fi]).max() < 1e-13
+                assert bool(fields["contacts"][t][fi]) == (fp[2] < m.rcap + 1e-4)
+    for t in range(n_t):
+        i = t + 2
+        mr = (pos[i + 2] - 2 * pos[i] + pos[i - 2]) / (2 * dt) ** 2
+        ar = (ust[i + 2] - 2 * ust[i] + ust[i - 2]) / (2 * dt) ** 2
+        scale = max(np.abs(mr).max(), np.abs(ar).max(), 1e-3)
+        assert np.abs(mr - fields["mom_rate"][t]).max() < 1e-10 * scale, t
+        assert np.abs(ar - fields["ang_mom_rate"][t]).max() < 1e-10 * scale, t
