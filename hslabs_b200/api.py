@@ -64,6 +64,7 @@ def _load():
     lib.hsl_ik_records_host.argtypes = [vp, i64, vp, i32, vp, vp]
     lib.hsl_solve_forces_gait_host.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
+    lib.hsl_set_max_slots.argtypes = [vp, i64]
     lib.hsl_set_rec_transform.argtypes = [vp, vp, vp]
     lib.hsl_launch_count.argtypes = [vp]
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
@@ -77,7 +78,7 @@ def exported_symbols():
     """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
-            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_launch_count",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_set_max_slots", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
 
 
@@ -155,6 +156,10 @@ class Model:
     # ---- measurement helpers
     def set_tuning(self, fb=64, maxreg=128):
         _check(_load().hsl_set_tuning(self._h, fb, maxreg))
+
+    def set_max_slots(self, max_slots):
+        """Frame slots per launch: larger batches run as consecutive chunks (bounded workspace, same results)."""
+        _check(_load().hsl_set_max_slots(self._h, int(max_slots)))
 
     def launch_count(self):
         return int(_load().hsl_launch_count(self._h))

@@ -57,6 +57,7 @@ struct HslModel {
   HslModelPod pod;
   double total_mass;
   int fb = 64, maxreg = 128;
+  int64_t max_slots = (int64_t)1 << 26;  // frame slots per launch (hsl_set_max_slots)
   int64_t launches = 0;
   bool rec_on = false;           // pergensetup::rec_transform_flag
   double rec_R[9], rec_t[3];
@@ -123,6 +124,11 @@ int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
   m->maxreg = maxreg;
   return HSL_OK;
 }
+int hsl_set_max_slots(HslModel* m, int64_t max_slots) {
+  if (!m || max_slots < 5 || max_slots > 0x7fffffff) return set_err(HSL_ERR_ARG, "frame slots per launch must be in 5 .. 2^31 - 1");
+  m->max_slots = max_slots;
+  return HSL_OK;
+}
 int64_t hsl_launch_count(const HslModel* m) { return m ? m->launches : 0; }
 int hsl_set_rec_transform(HslModel* m, const double* transl, const double* eas) {
   if (!m) return set_err(HSL_ERR_ARG, "null model");
@@ -137,9 +143,10 @@ int hsl_set_rec_transform(HslModel* m, const double* transl, const double* eas) 
 }
 
 // ---------------------------------------------------------------- device-pointer entry
-static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
-                          double* d_min, double* d_max, int32_t* d_status, bool dump, cudaStream_t st) {
-  if (!m || C < 1 || n_t < 1 || !d_params) return set_err(HSL_ERR_ARG, "bad argument");
+// One launch sequence (setup, frames, finish) over C candidates whose C * (n_t + 4) frame slots fit the kernels'
+// 32-bit slot arithmetic and the workspace bound; eval_gaits_dev below splits larger batches.
+static int eval_gaits_chunk(HslModel* m, int64_t C, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                            double* d_min, double* d_max, int32_t* d_status, bool dump, cudaStream_t st) {
   const int64_t nfr = C * n_t;
   HSL_CUDA(m->cand.need(sizeof(HslCand) * C));
   HSL_CUDA(m->ttab.need(sizeof(double) * C * (n_t + 4)));
@@ -220,6 +227,39 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
   return HSL_OK;
 }
 
+// Candidates are independent, so a batch of any size is evaluated as consecutive chunks of at most max_slots frame
+// slots: the per-frame workspace (3 doubles per solved frame + the time table) stays bounded however many candidates
+// the caller hands over, and slot indices stay below 2^31.  Per-frame dumps are sized by the caller's own output
+// arrays and are not split.
+// Candidates per launch; argument errors only (no CUDA call), so the host entries can run it first.
+static int gait_chunk_candidates(const HslModel* m, int64_t C, int n_t, bool dump, int64_t* cmax) {
+  if (!m || C < 1 || n_t < 1) return set_err(HSL_ERR_ARG, "bad argument");
+  const int64_t per_cand = (int64_t)n_t + 4, limit = dump ? (int64_t)0x7fffffff : m->max_slots;
+  *cmax = limit / per_cand;
+  if (*cmax < 1) return set_err(HSL_ERR_ARG, "n_t + 4 frame slots of one candidate exceed the launch bound (hsl_set_max_slots)");
+  if (dump && C > *cmax) return set_err(HSL_ERR_ARG, "per-frame dump of more than 2^31 frame slots: split the batch");
+  return HSL_OK;
+}
+
+static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                          double* d_min, double* d_max, int32_t* d_status, bool dump, cudaStream_t st) {
+  if (!d_params) return set_err(HSL_ERR_ARG, "bad argument");
+  int64_t cmax = 0;
+  const int rcs = gait_chunk_candidates(m, C, n_t, dump, &cmax);
+  if (rcs) return rcs;
+  if (!d_status && C > cmax) {  // the shared status workspace must cover the whole batch before chunks index into it
+    HSL_CUDA(m->status.need(sizeof(int32_t) * C));
+    d_status = (int32_t*)m->status.p;
+  }
+  for (int64_t c0 = 0; c0 < C; c0 += cmax) {
+    const int64_t cc = (C - c0 < cmax) ? C - c0 : cmax;
+    const int rc = eval_gaits_chunk(m, cc, n_t, d_params + c0 * HSL_NPARAM, flags, d_cot ? d_cot + c0 : nullptr, d_work ? d_work + c0 : nullptr,
+                                    d_min ? d_min + c0 : nullptr, d_max ? d_max + c0 : nullptr, d_status ? d_status + c0 : nullptr, dump, st);
+    if (rc) return rc;
+  }
+  return HSL_OK;
+}
+
 int hsl_eval_gaits(HslModel* m, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
                    double* d_min_cfz, double* d_max_mu, int32_t* d_status, void* stream) {
   return eval_gaits_dev(m, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, false, (cudaStream_t)stream);
@@ -253,8 +293,10 @@ static int eval_gaits_host_impl(HslModel* m, int64_t C, int n_t, const double* p
                                 double* min_cfz, double* max_mu, int32_t* status, bool dump, double* traj, double* x, double* z,
                                 double* tau, uint8_t* contacts) {
   if (!m || C < 1 || n_t < 1 || !params) return set_err(HSL_ERR_ARG, "bad argument");
-  int rc = ensure_stream(m);
+  int64_t cmax = 0;
+  int rc = gait_chunk_candidates(m, C, n_t, dump, &cmax);
   if (rc) return rc;
+  if ((rc = ensure_stream(m))) return rc;
   cudaStream_t st = m->stream;
   const size_t pbytes = sizeof(double) * HSL_NPARAM * C;
   HSL_CUDA(m->pin_in.need(pbytes));
@@ -307,6 +349,7 @@ int hsl_eval_gaits_detail_host(HslModel* m, int64_t n_cand, int n_t, const doubl
 int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* traj, const double* dt, double* work, double* min_cfz,
                                double* max_mu, int32_t* status, double* x, double* z, double* tau) {
   if (!m || C < 1 || n_t < 1 || !traj || !dt) return set_err(HSL_ERR_ARG, "bad argument");
+  if (C * ((int64_t)n_t + 5) > 0x7fffffff) return set_err(HSL_ERR_ARG, "more than 2^31 frame slots in one call: split the batch");
   int rc = ensure_stream(m);
   if (rc) return rc;
   cudaStream_t st = m->stream;
@@ -358,6 +401,7 @@ int hsl_solve_frames_host(HslModel* m, int64_t F, const double* pos, const doubl
                           int32_t* status) {
   if (!m || F < 1 || !pos || !jpos || !jzaxis || !mom_rate || !ang_mom_rate || !fpos || !contacts)
     return set_err(HSL_ERR_ARG, "bad argument");
+  if (F > 0x7fffffff) return set_err(HSL_ERR_ARG, "more than 2^31 frames in one call: split the batch");
   int rc = ensure_stream(m);
   if (rc) return rc;
   cudaStream_t st = m->stream;
@@ -457,6 +501,7 @@ int hsl_solve_forces_host(HslModel* m, int64_t F, const double* pos, const doubl
                           const double* ang_mom_rate, const double* fpos, const double* torques, double* z, int32_t* status) {
   if (!m || F < 1 || !pos || !jpos || !jzaxis || !mom_rate || !ang_mom_rate || !fpos || !torques || !z)
     return set_err(HSL_ERR_ARG, "bad argument");
+  if (F > 0x7fffffff) return set_err(HSL_ERR_ARG, "more than 2^31 frames in one call: split the batch");
   int rc = ensure_stream(m);
   if (rc) return rc;
   cudaStream_t st = m->stream;
@@ -493,6 +538,7 @@ int hsl_solve_forces_host(HslModel* m, int64_t F, const double* pos, const doubl
 int hsl_solve_forces_gait_host(HslModel* m, int64_t C, int n_t, const double* params, int flags, const double* torques, double* z,
                                int32_t* status) {
   if (!m || C < 1 || n_t < 1 || !params || !torques || !z) return set_err(HSL_ERR_ARG, "bad argument");
+  if (C * ((int64_t)n_t + 5) > 0x7fffffff) return set_err(HSL_ERR_ARG, "more than 2^31 frame slots in one call: split the batch");
   int rc = ensure_stream(m);
   if (rc) return rc;
   cudaStream_t st = m->stream;
@@ -531,6 +577,7 @@ int hsl_solve_forces_gait_host(HslModel* m, int64_t C, int n_t, const double* pa
 
 // out: [10][n] = hsl_div, a/b, hsl_sqrt(|a|), sqrt(|a|), hsl_atan2(a,b), atan2(a,b), then sin, sin_ref, cos, cos_ref of |a| (|a| <= pi)
 int hsl_math_selftest(int n, const double* a, const double* b, double* out) {
+  if (n < 1 || !a || !b || !out) return set_err(HSL_ERR_ARG, "bad argument");
   double *da = nullptr, *db = nullptr, *dout = nullptr;
   HSL_CUDA(cudaMalloc(&da, sizeof(double) * n));
   HSL_CUDA(cudaMalloc(&db, sizeof(double) * n));

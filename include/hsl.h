@@ -119,6 +119,10 @@ int hsl_set_rec_transform(HslModel* m, const double* transl /*[3]*/, const doubl
 
 /* tuning / measurement helpers */
 int hsl_set_tuning(HslModel* m, int fb, int maxreg);          /* cost-only kernel variant: frame slots per block (32|64), register cap per thread */
+/* hsl_eval_gaits / hsl_eval_gaits_host evaluate a batch of any size as consecutive chunks of at most max_slots frame
+ * slots (a candidate takes n_t + 4); default 2^26 (~2 GB of per-frame workspace), bounds 5 .. 2^31 - 1.  Results do
+ * not depend on the chunking. */
+int hsl_set_max_slots(HslModel* m, int64_t max_slots);
 int64_t hsl_launch_count(const HslModel* m);                  /* kernels launched through this handle so far */
 int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms); /* FP64 FMA throughput of the device */
 int hsl_math_selftest(int n, const double* a, const double* b, double* out /*[10][n]*/); /* accuracy of the kernels' branch-free div/sqrt/atan2/sincos vs the library ones (HOST pointers) */

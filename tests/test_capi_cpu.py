@@ -76,6 +76,25 @@ def test_bad_inputs_report_errors(hsl, tmp_path):
         hsl.Model(str(other))
 
 
+def test_size_bounds_are_argument_errors(hsl):
+    """Checked before any CUDA call: chunk bound limits, a candidate longer than one launch may be, per-frame entries
+    beyond the kernels' 32-bit frame-slot range."""
+    m = hsl.Model(hsl.model_path("hexapod"))
+    for bad in (0, 4, 1 << 31):
+        with pytest.raises(hsl.HslError, match="frame slots per launch"):
+            m.set_max_slots(bad)
+    m.set_max_slots(16)
+    with pytest.raises(hsl.HslError, match="exceed the launch bound"):
+        m.eval_gaits(hsl.make_params(torso_pos=(0, 0, -.1)), 20)
+    m.set_max_slots(1 << 26)
+    lib = hsl.api._load()
+    one = np.zeros(13)
+    assert lib.hsl_solve_forces_gait_host(m._h, 1 << 26, 60, one.ctypes.data, 0, one.ctypes.data, one.ctypes.data, None) == -1
+    assert b"split the batch" in lib.hsl_last_error()
+    assert lib.hsl_eval_trajectories_host(m._h, 1 << 26, 60, one.ctypes.data, one.ctypes.data, None, None, None, None, None, None, None) == -1
+    assert b"split the batch" in lib.hsl_last_error()
+
+
 def test_no_cpu_fallback(hsl):
     import torch
     if torch.cuda.is_available():

@@ -267,6 +267,36 @@ def test_small_and_ragged_batches(hsl, orc):
     assert np.abs(got["cot"] - ref["cot"]).max() <= TOL * np.abs(ref["cot"]).max()
 
 
+def test_chunked_batches_equal_single_launch(hsl, orc):
+    """hsl_set_max_slots: a batch evaluated as several consecutive launches (bounded workspace; also what keeps the
+    kernels' 32-bit slot indices exact for huge batches) gives bit-identical costs, statistics and status, including
+    a failed candidate in a later chunk and a last chunk that is not full."""
+    xml = model_xml("hexapod")
+    p, _ = orc.load_preset(PRESETS, 8)
+    batch = np.tile(p, (45, 1))
+    batch[:, 7] = np.linspace(2.0, 6.0, 45)
+    batch[:, 9] = np.linspace(0.02, 0.12, 45)
+    batch[31, 2] = 5.0            # torso far above the ground: unreachable (lik.cpp:142-146)
+    n_t = 20
+    m = hsl.Model(xml)
+    one = m.eval_gaits(batch, n_t)
+    launches = m.launch_count()
+    assert one["status"][31] != 0 and (np.delete(one["status"], 31) == 0).all()
+    for max_slots in (24 * 7, 24 * 44, 24 + 5):   # 7, 2 and 45 chunks (7 / 44 / 1 candidates each)
+        m.set_max_slots(max_slots)
+        before = m.launch_count()
+        got = m.eval_gaits(batch, n_t)
+        per = max_slots // (n_t + 4)
+        assert m.launch_count() - before == 3 * -(-45 // per)
+        for key in ("cot", "work", "min_cfz", "max_mu", "status"):
+            assert np.array_equal(got[key], one[key], equal_nan=(key != "status")), (max_slots, key)
+    assert launches == 3
+    m.set_max_slots(1 << 26)
+    ref = orc.Model(xml).eval_batch(batch, n_t, nthreads=8)
+    ok = ref["status"] == 0
+    assert np.abs(one["cot"][ok] - ref["cot"][ok]).max() <= TOL * np.abs(ref["cot"][ok]).max()
+
+
 @pytest.mark.parametrize("pid,transl,eas", [(8, (0, 0, 0), (0, 0, -1.571)), (1, (0, 0, 0), (0, 0, -1.571)), (12, (0.3, -0.2, 0), (0, 0, 0.7)),
                                             (8, (0, 0, -0.05), (0, 0, 0.3)), (24, (0, 0, 0), (0.02, 0.03, 0)), (9, (0.1, 0.1, 0), (0, 0, 2.5))])
 def test_rec_transform(hsl, orc, pid, transl, eas):
