@@ -65,6 +65,9 @@ def _load():
     lib.hsl_solve_forces_gait_host.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
     lib.hsl_set_max_slots.argtypes = [vp, i64]
+    lib.hsl_pinned_alloc.restype = vp
+    lib.hsl_pinned_alloc.argtypes = [C.c_size_t]
+    lib.hsl_pinned_free.argtypes = [vp]
     lib.hsl_set_rec_transform.argtypes = [vp, vp, vp]
     lib.hsl_launch_count.argtypes = [vp]
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
@@ -78,8 +81,47 @@ def exported_symbols():
     """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
-            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_set_max_slots", "hsl_launch_count",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
+
+
+class _Pinned:
+    """Owner of one hsl_pinned_alloc block (freed when the last numpy view goes away)."""
+
+    def __init__(self, nbytes):
+        self.ptr = _load().hsl_pinned_alloc(nbytes)
+        if not self.ptr:
+            raise HslError("hsl_pinned_alloc(%d): %s" % (nbytes, _load().hsl_last_error().decode()))
+        self.nbytes = nbytes
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                _load().hsl_pinned_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array in page-locked host memory (hsl_pinned_alloc): pass such arrays as `out=` of the per-frame entries,
+    or as their inputs, for copies at the full PCIe rate."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    owner = _Pinned(max(n, 1))
+    buf = (C.c_char * owner.nbytes).from_address(owner.ptr)
+    buf._hsl_owner = owner  # the array references buf (buffer protocol), buf keeps the allocation alive
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def _out(out, key, shape, dtype=np.float64):
+    """Caller-supplied output array (checked) or a fresh pageable one."""
+    if out is not None and key in out:
+        a = out[key]
+        if a.shape != tuple(shape) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous:
+            raise ValueError("out[%r] must be a C-contiguous %s array of shape %s" % (key, np.dtype(dtype), tuple(shape)))
+        return a
+    return np.empty(shape, dtype)
 
 
 def _check(rc):
@@ -179,37 +221,40 @@ class Model:
                                            _p(out["min_cfz"]), _p(out["max_mu"]), _p(out["status"])))
         return out
 
-    def eval_gaits_detail(self, params, n_t, flags=0):
+    def eval_gaits_detail(self, params, n_t, flags=0, out=None):
+        """out: optional dict of preallocated arrays (e.g. from pinned_empty) for any of the result keys."""
         params = np.ascontiguousarray(params, np.float64).reshape(-1, HSL_NPARAM)
         c = params.shape[0]
-        out = dict(cot=np.empty(c), work=np.empty(c), min_cfz=np.empty(c), max_mu=np.empty(c), status=np.empty(c, np.int32),
-                   traj=np.empty((c, n_t + 4, self.config_dim)), x=np.empty((c, n_t, 6 * self.n)),
-                   z=np.empty((c, n_t, 3 * self.nf)), tau=np.empty((c, n_t, self.nmj)),
-                   contacts=np.empty((c, n_t, self.nf), np.uint8))
-        _check(_load().hsl_eval_gaits_detail_host(self._h, c, n_t, _p(params), flags, *[_p(out[k]) for k in (
+        shapes = dict(cot=(c,), work=(c,), min_cfz=(c,), max_mu=(c,), traj=(c, n_t + 4, self.config_dim), x=(c, n_t, 6 * self.n),
+                      z=(c, n_t, 3 * self.nf), tau=(c, n_t, self.nmj))
+        res = {k: _out(out, k, sh) for k, sh in shapes.items()}
+        res["status"] = _out(out, "status", (c,), np.int32)
+        res["contacts"] = _out(out, "contacts", (c, n_t, self.nf), np.uint8)
+        _check(_load().hsl_eval_gaits_detail_host(self._h, c, n_t, _p(params), flags, *[_p(res[k]) for k in (
             "cot", "work", "min_cfz", "max_mu", "status", "traj", "x", "z", "tau", "contacts")]))
-        return out
+        return res
 
-    def eval_trajectories(self, traj, dt, n_t):
+    def eval_trajectories(self, traj, dt, n_t, out=None):
         traj = np.ascontiguousarray(traj, np.float64).reshape(-1, n_t + 5, self.config_dim)
         c = traj.shape[0]
         dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, np.float64), (c,)))
-        out = dict(work=np.empty(c), min_cfz=np.empty(c), max_mu=np.empty(c), status=np.empty(c, np.int32),
-                   x=np.empty((c, n_t, 6 * self.n)), z=np.empty((c, n_t, 3 * self.nf)), tau=np.empty((c, n_t, self.nmj)))
-        _check(_load().hsl_eval_trajectories_host(self._h, c, n_t, _p(traj), _p(dt), _p(out["work"]), _p(out["min_cfz"]),
-                                                  _p(out["max_mu"]), _p(out["status"]), _p(out["x"]), _p(out["z"]), _p(out["tau"])))
-        return out
+        shapes = dict(work=(c,), min_cfz=(c,), max_mu=(c,), x=(c, n_t, 6 * self.n), z=(c, n_t, 3 * self.nf), tau=(c, n_t, self.nmj))
+        res = {k: _out(out, k, sh) for k, sh in shapes.items()}
+        res["status"] = _out(out, "status", (c,), np.int32)
+        _check(_load().hsl_eval_trajectories_host(self._h, c, n_t, _p(traj), _p(dt), _p(res["work"]), _p(res["min_cfz"]),
+                                                  _p(res["max_mu"]), _p(res["status"]), _p(res["x"]), _p(res["z"]), _p(res["tau"])))
+        return res
 
-    def solve_frames(self, pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos, contacts):
+    def solve_frames(self, pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos, contacts, out=None):
         """forcetorquesolver::solve_forcetorques + get_motor_torques on populated dynrecords."""
         arrs = [np.ascontiguousarray(a, np.float64) for a in (pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos)]
         contacts = np.ascontiguousarray(contacts, np.uint8)
         f = arrs[0].shape[0]
-        out = dict(x=np.empty((f, 6 * self.n)), z=np.empty((f, 3 * self.nf)), tau=np.empty((f, self.nmj)),
-                   status=np.empty(f, np.int32))
-        _check(_load().hsl_solve_frames_host(self._h, f, *[_p(a) for a in arrs], _p(contacts), _p(out["x"]), _p(out["z"]),
-                                             _p(out["tau"]), _p(out["status"])))
-        return out
+        res = dict(x=_out(out, "x", (f, 6 * self.n)), z=_out(out, "z", (f, 3 * self.nf)), tau=_out(out, "tau", (f, self.nmj)),
+                   status=_out(out, "status", (f,), np.int32))
+        _check(_load().hsl_solve_frames_host(self._h, f, *[_p(a) for a in arrs], _p(contacts), _p(res["x"]), _p(res["z"]),
+                                             _p(res["tau"]), _p(res["status"])))
+        return res
 
     def gait_records(self, params, times, flags=0):
         """pergensetup::set_rec (pergen.cpp:225-239): records [C][len(times)][6+3nf] of the candidates at the given times."""

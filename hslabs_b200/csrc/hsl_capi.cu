@@ -62,11 +62,11 @@ struct HslModel {
   bool rec_on = false;           // pergensetup::rec_transform_flag
   double rec_R[9], rec_t[3];
   // workspace
-  DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b;
+  DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b, stage;
   PinBuf pin_in, pin_out;
   cudaStream_t stream = nullptr;
   ~HslModel() {
-    DevBuf* all[] = {&cand, &ttab, &wframe, &fmin, &fmax, &status, &params, &out4, &dump_x, &dump_z, &dump_tau, &dump_q, &dump_c, &in_a, &in_b};
+    DevBuf* all[] = {&cand, &ttab, &wframe, &fmin, &fmax, &status, &params, &out4, &dump_x, &dump_z, &dump_tau, &dump_q, &dump_c, &in_a, &in_b, &stage};
     for (DevBuf* b : all) b->release();
     pin_in.release();
     pin_out.release();
@@ -83,6 +83,18 @@ int hsl_device_count(void) {
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
   return n;
 }
+
+// Page-locked host memory for the callers' input / output arrays: the host entries copy straight from / into the
+// caller's buffers, which runs at the full PCIe rate only when they are pinned.
+void* hsl_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaMallocHost(&p, bytes) != cudaSuccess) {
+    set_err(HSL_ERR_CUDA, "CUDA: %s", bytes ? "cudaMallocHost failed" : "zero-size pinned allocation");
+    return nullptr;
+  }
+  return p;
+}
+void hsl_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
 int hsl_model_load_xml(const char* xml_path, HslModel** out) {
   if (!xml_path || !out) return set_err(HSL_ERR_ARG, "null argument");
@@ -276,16 +288,16 @@ static int ensure_stream(HslModel* m) {
   return HSL_OK;
 }
 
-// transposes a component-major device dump [comp][nfr] into the caller's row-major [nfr][comp] host array
-static int fetch_transposed(HslModel* m, const void* dsrc, int comps, int64_t nfr, double* dst, cudaStream_t st) {
+// Component-major device dump [comp][nfr] -> the caller's row-major [nfr][comp] host array: transposed on the device
+// (hsl_transpose_kernel), then one D2H copy straight into the caller's buffer (full PCIe rate when it is pinned).
+static int fetch_transposed(HslModel* m, const void* dsrc, int comps, int64_t nfr, void* dst, cudaStream_t st, int elem_size = 8) {
   if (!dst) return HSL_OK;
-  const size_t bytes = sizeof(double) * comps * nfr;
-  HSL_CUDA(m->pin_out.need(bytes));
-  HSL_CUDA(cudaMemcpyAsync(m->pin_out.p, dsrc, bytes, cudaMemcpyDeviceToHost, st));
+  const size_t bytes = (size_t)elem_size * comps * nfr;
+  HSL_CUDA(m->stage.need(bytes));
+  HSL_CUDA(hsl_launch_transpose(dsrc, m->stage.p, comps, nfr, elem_size, st));
+  m->launches += 1;
+  HSL_CUDA(cudaMemcpyAsync(dst, m->stage.p, bytes, cudaMemcpyDeviceToHost, st));
   HSL_CUDA(cudaStreamSynchronize(st));
-  const double* src = (const double*)m->pin_out.p;
-  for (int c = 0; c < comps; c++)
-    for (int64_t f = 0; f < nfr; f++) dst[f * comps + c] = src[(size_t)c * nfr + f];
   return HSL_OK;
 }
 
@@ -325,12 +337,7 @@ static int eval_gaits_host_impl(HslModel* m, int64_t C, int n_t, const double* p
     if ((rc = fetch_transposed(m, m->dump_z.p, 3 * P.nf, nfr, z, st))) return rc;
     if ((rc = fetch_transposed(m, m->dump_tau.p, P.nmj, nfr, tau, st))) return rc;
     if ((rc = fetch_transposed(m, m->dump_q.p, P.config_dim, C * (n_t + 4), traj, st))) return rc;
-    if (contacts) {
-      std::vector<uint8_t> tmp((size_t)P.nf * nfr);
-      HSL_CUDA(cudaMemcpy(tmp.data(), m->dump_c.p, tmp.size(), cudaMemcpyDeviceToHost));
-      for (int l = 0; l < P.nf; l++)
-        for (int64_t f = 0; f < nfr; f++) contacts[f * P.nf + l] = tmp[(size_t)l * nfr + f];
-    }
+    if ((rc = fetch_transposed(m, m->dump_c.p, P.nf, nfr, contacts, st, 1))) return rc;
   }
   return HSL_OK;
 }

@@ -464,6 +464,28 @@ __global__ void hsl_math_selftest_kernel(int n, const double* __restrict__ a, co
   out[6 * n + i] = sn; out[7 * n + i] = sr; out[8 * n + i] = cs; out[9 * n + i] = cr;
 }
 
+// Per-frame dumps leave the frame kernels component-major ([comp][frame]: the lanes of a warp are consecutive frames
+// and write consecutive addresses); the reference-facing arrays are row-major per frame ([frame][comp]).  This tiled
+// transpose turns one into the other at HBM speed on the device, so the host side is one plain D2H copy: 32 x 32
+// tiles through shared memory (33-column padding: no bank conflicts), both the read and the write coalesced.
+template <typename T>
+__global__ void hsl_transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, int comps, int64_t nfr) {
+  __shared__ T tile[32][33];
+  const int64_t f0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int c = c0 + r;
+    const int64_t f = f0 + threadIdx.x;
+    if (c < comps && f < nfr) tile[r][threadIdx.x] = src[(int64_t)c * nfr + f];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t f = f0 + r;
+    const int c = c0 + threadIdx.x;
+    if (c < comps && f < nfr) dst[f * comps + c] = tile[threadIdx.x][r];
+  }
+}
+
 // ------------------------------------------------------------------ launchers
 namespace {
 // floor(g / d) = (g * magic) >> shift for all 0 <= g < 2^31: shift = 31 + ceil(log2 d), magic = ceil(2^shift / d) < 2^32
@@ -638,5 +660,16 @@ cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, do
 
 cudaError_t hsl_launch_dfma_probe(double* out, int blocks, int threads, int iters, cudaStream_t st) {
   hsl_dfma_probe_kernel<<<blocks, threads, 0, st>>>(out, iters, 0.999999, 1e-9);
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_transpose(const void* src, void* dst, int comps, int64_t nfr, int elem_size, cudaStream_t st) {
+  if (comps < 1 || nfr < 1) return cudaSuccess;
+  const int64_t bx = (nfr + 31) / 32;
+  if (bx > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+  const dim3 grid((unsigned)bx, (unsigned)((comps + 31) / 32)), block(32, 8);
+  if (elem_size == 8) hsl_transpose_kernel<double><<<grid, block, 0, st>>>((const double*)src, (double*)dst, comps, nfr);
+  else if (elem_size == 1) hsl_transpose_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, comps, nfr);
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

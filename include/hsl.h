@@ -117,6 +117,11 @@ int hsl_solve_forces_gait_host(HslModel* m, int64_t n_cand, int n_t, const doubl
  * (pergen.cpp:446).  eas = (phi, theta, psi); either pointer may be NULL (= zero); both NULL switches it off. */
 int hsl_set_rec_transform(HslModel* m, const double* transl /*[3]*/, const double* eas /*[3]*/);
 
+/* Page-locked host memory for input / output arrays of the *_host entries (they copy straight from / into the caller's
+ * buffers; pageable memory works too, at the driver's staged-copy rate).  NULL on failure. */
+void* hsl_pinned_alloc(size_t bytes);
+void hsl_pinned_free(void* p);
+
 /* tuning / measurement helpers */
 int hsl_set_tuning(HslModel* m, int fb, int maxreg);          /* cost-only kernel variant: frame slots per block (32|64), register cap per thread */
 /* hsl_eval_gaits / hsl_eval_gaits_host evaluate a batch of any size as consecutive chunks of at most max_slots frame

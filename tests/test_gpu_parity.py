@@ -267,6 +267,29 @@ def test_small_and_ragged_batches(hsl, orc):
     assert np.abs(got["cot"] - ref["cot"]).max() <= TOL * np.abs(ref["cot"]).max()
 
 
+def test_pinned_and_preallocated_outputs(hsl, orc):
+    """hsl_pinned_alloc / `out=`: the per-frame entries write straight into caller-owned (page-locked) arrays; same bits
+    as the default pageable path; wrong shapes are refused before the call."""
+    p, name = orc.load_preset(PRESETS, 8)
+    m = hsl.Model(model_xml(name))
+    n_t = 23
+    batch = np.tile(p, (3, 1))
+    batch[:, 7] = (2.5, 3.0, 4.0)
+    ref = m.eval_gaits_detail(batch, n_t)
+    pin = {k: hsl.pinned_empty(ref[k].shape, ref[k].dtype) for k in ("traj", "x", "z", "tau", "contacts", "cot")}
+    got = m.eval_gaits_detail(batch, n_t, out=pin)
+    for k in pin:
+        assert got[k] is pin[k] and np.array_equal(got[k], ref[k]), k
+    traj = hsl.pinned_empty((3, n_t + 5, m.config_dim))
+    traj[:, :n_t + 4] = ref["traj"]; traj[:, -1] = ref["traj"][:, -1]
+    t = m.eval_trajectories(traj, batch[:, 7] / n_t, n_t, out={"x": pin["x"]})
+    assert t["x"] is pin["x"] and rel_err(t["x"], ref["x"]) < TOL and rel_err(t["tau"], ref["tau"]) < TOL
+    with pytest.raises(ValueError):
+        m.eval_gaits_detail(batch, n_t, out={"x": np.empty((3, n_t, 5))})
+    with pytest.raises(ValueError):
+        m.eval_gaits_detail(batch, n_t, out={"z": np.empty((3, n_t, 3 * m.nf), np.float32)})
+
+
 def test_chunked_batches_equal_single_launch(hsl, orc):
     """hsl_set_max_slots: a batch evaluated as several consecutive launches (bounded workspace; also what keeps the
     kernels' 32-bit slot indices exact for huge batches) gives bit-identical costs, statistics and status, including
