@@ -81,7 +81,7 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(rows)}
 
 
-def cpu_port_rate(params, n_t, nthreads, budget_s=15.0):
+def cpu_port_rate(params, n_t, nthreads, budget_s=15.0, max_rounds=8):
     """Times the CPU port of the reference path (oracle/, dense-QR stand-in for Eigen's sparse QR) on a bounded sample."""
     from oracle import orc
     m = orc.Model(os.path.join(ROOT, "hslabs_b200", "models", MODEL + ".xml"))
@@ -89,7 +89,7 @@ def cpu_port_rate(params, n_t, nthreads, budget_s=15.0):
     m.eval_batch(params[:nthreads], n_t, nthreads)       # one candidate per thread: calibrates the sample size
     t1 = time.perf_counter() - t0
     per_round = max(t1, 1e-3)
-    rounds = int(max(1, min(8, budget_s / per_round - 1)))
+    rounds = int(max(1, min(max_rounds, budget_s / per_round - 1, params.shape[0] // nthreads)))
     n = nthreads * rounds
     t0 = time.perf_counter()
     out = m.eval_batch(params[:n], n_t, nthreads)
@@ -301,7 +301,7 @@ def main():
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
-            rate, n, dt, ok = cpu_port_rate(params, n_t, cores, budget_s=15.0)
+            rate, n, dt, ok = cpu_port_rate(params, n_t, cores, budget_s=15.0, max_rounds=40)  # ~10-15 s of CPU work
             line["cpu_baseline"] = {"value": rate, "unit": "frame solves/s", "cores": cores, "kind": "port",
                                     "sample": "%d candidates x %d frames on %d threads (%.1f s)" % (n, n_t, cores, dt)}
         _emit(line)
