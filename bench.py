@@ -299,7 +299,7 @@ def main():
                                  "note": "cost-only mode moves ~%d B per candidate; HBM is not the bound" % (13 * 8 + 36)}},
             "clocks": clocks,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # reported at N = 1 only (the CPU path does not change with the GPU count)
             cores = os.cpu_count() or 1
             rate, n, dt, ok = cpu_port_rate(params, n_t, cores, budget_s=15.0, max_rounds=40)  # ~10-15 s of CPU work
             line["cpu_baseline"] = {"value": rate, "unit": "frame solves/s", "cores": cores, "kind": "port",
