@@ -228,7 +228,8 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = model.launch_count() - launches0 + args.steps  # setup + frames + finish per step, + the selection kernel
-    ms = sum(a.elapsed_time(b) for a, b in ev)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms = sum(step_ms)
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -286,6 +287,8 @@ def main():
                        "parallelism": "candidates sharded, costs all-gathered (NCCL)" if world > 1 else "single GPU",
                        "mean_contacts": kbar},
             "gpu_launches": launches,
+            # best and median of the timed steps (this rank's CUDA events), next to the mean above
+            "ms_per_step_best": float(min(step_ms)), "ms_per_step_median": float(np.median(step_ms)),
             "e2e": {"value": e2e_value, "unit": "frame solves/s", "h2d_bytes_per_step": int(params.nbytes),
                     "d2h_bytes_per_step": int(n_cand * (4 * 8 + 4))},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": dfma_tf, "unit": "TFLOP/s",
