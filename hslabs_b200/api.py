@@ -73,6 +73,7 @@ def _load():
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
     lib.hsl_math_selftest.argtypes = [i32, vp, vp, vp]
     lib.hsl_select_best.argtypes = [vp, i64, vp, vp, vp]
+    lib.hsl_select_topk.argtypes = [vp, i64, i32, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -82,7 +83,7 @@ def exported_symbols():
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
-            "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best"]
+            "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk"]
 
 
 class _Pinned:
@@ -302,6 +303,11 @@ class Model:
 def select_best_device(d_cost, n, d_index, d_value=0, stream=0):
     """Argmin over device-resident costs (NaN skipped); arguments are integer device addresses."""
     _check(_load().hsl_select_best(d_cost, n, d_index or None, d_value or None, stream or None))
+
+
+def select_topk_device(d_cost, n, k, d_index, d_value=0, stream=0):
+    """The k cheapest valid candidates in stable ascending order (NaN skipped, -1 / NaN past the valid ones); integer device addresses."""
+    _check(_load().hsl_select_topk(d_cost, n, k, d_index or None, d_value or None, stream or None))
 
 
 def dfma_probe(blocks=148 * 8, threads=256, iters=4096):

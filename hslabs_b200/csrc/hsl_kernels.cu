@@ -437,6 +437,61 @@ __global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, in
   }
 }
 
+// Selection of the k cheapest valid candidates in ascending (cost, index) order -- the order a stable sort of the costs
+// gives, NaN (failed candidates) never selected.  One block; pass j finds the smallest pair that is lexicographically
+// greater than the pair found by pass j-1, so nothing is marked or moved and the result does not depend on the thread
+// count.  k * n reads: meant for the elite sets of a search loop (k up to a few thousand) over the all-gathered costs.
+// Entries past the number of valid candidates get index -1 / value NaN.
+__global__ void hsl_topk_kernel(const double* __restrict__ cost, int64_t n, int k, int64_t* __restrict__ out_index,
+                                double* __restrict__ out_value) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ double prev_v;
+  __shared__ long long prev_i;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL), nanv = __longlong_as_double(0x7ff8000000000000LL);
+  auto better = [](double v, long long i, double bv, long long bidx) { return i >= 0 && (bidx < 0 || v < bv || (v == bv && i < bidx)); };
+  if (threadIdx.x == 0) { prev_v = -inf; prev_i = -1; }
+  __syncthreads();
+  for (int j = 0; j < k; j++) {
+    const double pv = prev_v;
+    const long long pi = prev_i;
+    double best = inf;
+    long long bi = -1;
+    if (j == 0 || pi >= 0) {  // once a pass finds nothing, every later pass finds nothing
+      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double c = cost[i];
+        const bool after = (j == 0) ? (c == c) : (c > pv || (c == pv && i > pi));  // NaN fails every comparison
+        if (after && (bi < 0 || c < best)) { best = c; bi = i; }              // ascending indices per thread: first hit wins ties
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int nw = (blockDim.x + 31) / 32;
+      best = (threadIdx.x < nw) ? sv[threadIdx.x] : inf;
+      bi = (threadIdx.x < nw) ? si[threadIdx.x] : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+      }
+      if (threadIdx.x == 0) {
+        if (out_index) out_index[j] = bi;
+        if (out_value) out_value[j] = (bi >= 0) ? best : nanv;
+        prev_v = best; prev_i = bi;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // FP64 FMA throughput probe: register-resident dependent chains, 8 per thread.  Used by bench.py for the
 // roofline denominator of this FP64-bound path (MEASURED_PEAKS.json has no FP64 figure).
 __global__ void hsl_dfma_probe_kernel(double* out, int iters, double a, double b) {
@@ -671,5 +726,10 @@ cudaError_t hsl_launch_transpose(const void* src, void* dst, int comps, int64_t 
   if (elem_size == 8) hsl_transpose_kernel<double><<<grid, block, 0, st>>>((const double*)src, (double*)dst, comps, nfr);
   else if (elem_size == 1) hsl_transpose_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)src, (uint8_t*)dst, comps, nfr);
   else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st) {
+  hsl_topk_kernel<<<1, 1024, 0, st>>>(cost, n, k, out_index, out_value);
   return cudaGetLastError();
 }

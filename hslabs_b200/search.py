@@ -61,11 +61,17 @@ class DeviceEvaluator:
 
 
 def top_k(cot, k):
-    """Indices and costs of the k cheapest valid candidates (NaN = failed candidate, ranked last; ties by index)."""
+    """Indices and costs of the k cheapest candidates in stable ascending order (`hsl_select_topk` on the device).
+    Failed candidates (NaN cost) are never selected: when fewer than k candidates are valid the result is shorter."""
     import torch
-    key = torch.nan_to_num(cot, nan=float("inf"))
-    order = torch.argsort(key, stable=True)[:k]
-    return order, cot[order]
+    from . import api
+    cot = cot.contiguous()
+    k = int(min(k, cot.numel()))
+    idx = torch.empty(k, dtype=torch.int64, device=cot.device)
+    val = torch.empty(k, dtype=torch.float64, device=cot.device)
+    api.select_topk_device(cot.data_ptr(), cot.numel(), k, idx.data_ptr(), val.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    n_ok = int((idx >= 0).sum())
+    return idx[:n_ok], val[:n_ok]
 
 
 def grid_search(model, base, axes, n_t, k=1, flags=0, device="cuda"):

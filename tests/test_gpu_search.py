@@ -74,3 +74,31 @@ def test_select_best_kernel(hsl):
     api.select_best_device(allnan.data_ptr(), 100, idx.data_ptr())
     torch.cuda.synchronize()
     assert int(idx) == -1
+
+
+def test_select_topk_kernel(hsl):
+    """hsl_select_topk = the first k entries of a stable ascending sort of the valid costs (ties by index, NaN never
+    selected, -1 / NaN once the valid candidates run out)."""
+    import torch
+    from hslabs_b200 import api, search
+    rng = np.random.default_rng(11)
+    for n, k in ((1, 1), (5, 5), (31, 7), (1024, 64), (4096 * 4 + 3, 100), (300, 300)):
+        c = rng.uniform(0.1, 5.0, n)
+        if n > 4:
+            c[rng.integers(0, n, max(1, n // 5))] = np.nan
+            c[rng.integers(0, n, n // 3)] = 1.25                      # many ties
+        t = torch.from_numpy(c).cuda()
+        idx = torch.empty(k, dtype=torch.int64, device="cuda")
+        val = torch.empty(k, dtype=torch.float64, device="cuda")
+        api.select_topk_device(t.data_ptr(), n, k, idx.data_ptr(), val.data_ptr())
+        torch.cuda.synchronize()
+        valid = np.flatnonzero(~np.isnan(c))
+        want = valid[np.argsort(c[valid], kind="stable")][:k]
+        got_i, got_v = idx.cpu().numpy(), val.cpu().numpy()
+        assert list(got_i[:want.size]) == list(want), (n, k)
+        assert np.array_equal(got_v[:want.size], c[want])
+        assert (got_i[want.size:] == -1).all() and np.isnan(got_v[want.size:]).all()
+        si, sv = search.top_k(t, k)                                   # the search loop's wrapper drops the exhausted tail
+        assert list(si.cpu().numpy()) == list(want) and np.array_equal(sv.cpu().numpy(), c[want])
+    with pytest.raises(hsl.HslError):
+        api.select_topk_device(t.data_ptr(), n, 0, idx.data_ptr())
