@@ -163,6 +163,10 @@ class GaitEvaluator {  // periodic + forcetorquesolver
         ci++;
       }
     }
+    // No foot on the ground: the reference goes on with 0-column matrices, Eigen's kernel() / image() of the
+    // 0 x 0 level-0 matrix come back 0 x 1 and the comma initialiser of ftsolver.cpp:222-223 asserts (abort);
+    // oracle/_ref reproduces that, so it is a breakdown here too.
+    if (delm == 0) return false;
     Mat N(m0, delm);
     if (delm > 0) {
       HouseholderQR qrt(Bt);
@@ -337,6 +341,10 @@ class GaitEvaluator {  // periodic + forcetorquesolver
       for (int i = 0; i < K; i++) mb[i] = -ntx0[i];
       Vec y0 = lu.solve(mb);
       Mat Ny = lu.kernel(), Ry = lu.image(ntn0);
+      // Eigen's kernel() of an invertible matrix is ONE zero column, so `m << ntn1*Ny, ntn0*Ry` (ftsolver.cpp:222-223)
+      // then passes K+1 columns to a K x K comma initialiser and Eigen's assertion aborts the reference (one foot
+      // on the ground: level 0 has full rank 3).  oracle/_ref reproduces the abort; report it as a breakdown here.
+      if (Ny.c == 0) return false;
       if (rank0 == lu.rank()) solver_warnings++;  // "decomposition threshold increased"
       rank0 = lu.rank();
       Vec t1 = matvec(ntn1, y0), b(K);
@@ -366,13 +374,13 @@ inline CotResult measure_cot(Model& model, GaitSetup& g, int n_t, real* traj_out
   CotResult r; r.cot = r.work = r.min_cfz = r.max_mu = 0; r.status = 0;
   GaitEvaluator ev(&model);
   if (!ev.record_trajectory(&g, n_t)) { r.status = 1; return r; }  // IK target unreachable
+  if (traj_out) for (int i = 0; i < ev.traj_size; i++) for (int j = 0; j < ev.config_dim; j++) traj_out[(size_t)i * ev.config_dim + j] = ev.traj[i][j];
   ev.compute_dynrecs();
   ev.compute_dynrec_ders();
   ev.switch_torso_penalty(true, true);
   if (!ev.work_over_period(r.work, x_dump, z_dump)) { r.status = 2; return r; }
   r.cot = r.work / (ev.total_mass() * g.pattern.step_length);
   r.min_cfz = ev.min_cfz; r.max_mu = ev.max_mu;
-  if (traj_out) for (int i = 0; i < ev.traj_size; i++) for (int j = 0; j < ev.config_dim; j++) traj_out[(size_t)i * ev.config_dim + j] = ev.traj[i][j];
   if (tau_dump) for (int i = 2; i < n_t + 2; i++) for (int j = 0; j < ev.nmj; j++) tau_dump[(size_t)(i - 2) * ev.nmj + j] = ev.torques[i % n_t][j];
   return r;
 }

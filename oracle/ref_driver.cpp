@@ -17,6 +17,7 @@
 // child's exit status becomes the return code (1 = the reference called exit(1), 2 = it aborted / crashed).
 //
 // Candidate parameter vector: 13 doubles, same layout as oracle/orc_capi.cpp and include/hsl.h.
+#include <signal.h>
 #include <sys/mman.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -74,6 +75,11 @@ struct Shm {
   ~Shm() { if (p) munmap(p, bytes); }
 };
 
+void child_signals() {  // a host process (pytest's faulthandler) may have installed dump handlers; the child dies quietly
+  const int sigs[] = {SIGABRT, SIGSEGV, SIGFPE, SIGBUS, SIGILL};
+  for (size_t i = 0; i < sizeof sigs / sizeof sigs[0]; i++) signal(sigs[i], SIG_DFL);
+}
+
 // Runs body(shared) in a forked child; returns 0, or 1 (reference exit(1)), 2 (abort / signal), -1 (fork failed).
 int run_isolated(size_t bytes, const std::function<void(char*)>& body, const std::function<void(const char*)>& collect) {
   if (!g_isolate) {
@@ -89,6 +95,7 @@ int run_isolated(size_t bytes, const std::function<void(char*)>& body, const std
   pid_t pid = fork();
   if (pid < 0) return -1;
   if (pid == 0) {
+    child_signals();
     body((char*)shm.p);
     _exit(0);
   }
@@ -131,16 +138,21 @@ Sizes sizes(const Handle* h, int n_t) {
 // measure_cot (player.cpp:269-285) with every intermediate copied out.  buf: out4 | traj | x | z | tau | complete
 void eval_candidate(Handle* h, pergensetup* pgs, int n_t, bool detail, double* buf) {
   modelplayer* mp = h->mp;
-  double cot = mp->measure_cot(pgs, n_t);  // the reference's own top-level call
-  buf[0] = cot;
+  // the body of modelplayer::measure_cot (player.cpp:269-275), kept open so that work and the contact statistics of
+  // the same pass can be returned; in detail mode the reference's own measure_cot is called as well
   periodic per(mp->model);
   mp->prepare_per_traj_dyn(per, pgs, n_t);
-  buf[1] = per.work_over_period();
+  double work = per.work_over_period();
+  double weight = per.get_total_mass();
+  double step_length = pgs->get_pergen()->get_step_length();
+  buf[0] = work / (weight * step_length);
+  buf[1] = work;
   double stat[2];
   per.get_contforce_stat(stat);
   buf[2] = stat[0];
   buf[3] = stat[1];
   if (!detail) return;
+  buf[0] = mp->measure_cot(pgs, n_t);
   Sizes s = sizes(h, n_t);
   double* traj = buf + 4;
   double* x = traj + s.traj;
@@ -564,6 +576,7 @@ int ref_eval_batch(void* hv, long n_cand, int n_t, const double* params, double*
     if (next[w] >= n_cand) { pids[w] = -1; return; }
     pid_t pid = fork();
     if (pid == 0) {
+      child_signals();
       Quiet q;
       for (long c = next[w]; c < n_cand; c += nprocs) {
         b[5 * c + 4] = 1;  // started

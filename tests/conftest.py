@@ -26,6 +26,30 @@ def orc():
 
 
 @pytest.fixture(scope="session")
+def refb():
+    """oracle/_ref: the reference's own sources compiled against shim headers (test infrastructure).  Built here when
+    /root/reference is present; on the GPU box the prebuilt library that travelled with the snapshot is used."""
+    from oracle import ref as r
+    r.build()
+    if not r.available():
+        pytest.skip("oracle/_ref/libhslref.so not built and /root/reference not present")
+    return r
+
+
+def ref_xml(name):
+    """Model file for the reference build: the reference's own XML when /root/reference is mounted, else the generated
+    one (bit-identical load-time constants: test_generated_xml_equals_reference_xml)."""
+    name = name if name.endswith(".xml") else name + ".xml"
+    p = os.path.join("/root/reference", name)
+    return p if os.path.exists(p) else os.path.join(MODELS, name)
+
+
+def ref_presets():
+    p = "/root/reference/pgs_config.txt"
+    return p if os.path.exists(p) else PRESETS
+
+
+@pytest.fixture(scope="session")
 def hsl():
     """The product package, with its CUDA library built (nvcc cross-compiles without a GPU)."""
     import hslabs_b200

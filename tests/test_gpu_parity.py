@@ -128,10 +128,21 @@ def test_status_codes_and_ignore_reach(hsl, orc):
     om.set_ignore_reach(True)
     ref = om.measure_cot(bad, 20, detail=True)
     got = m.eval_gaits_detail(bad, 20, flags=hsl.HSL_FLAG_IGNORE_REACH)
-    assert not (got["status"][0] & 2)
+    # every foot hangs in the air: the reference aborts in Eigen's comma initialiser (tests/test_ref_pins.py), the oracle
+    # reports the breakdown (2), the library flags HSL_ST_FEW_CONTACTS
+    assert ref["status"] == 2 and not (got["status"][0] & 2) and (got["status"][0] & hsl.HSL_ST_FEW_CONTACTS)
     # every leg is at (clamped) or within round-off of full extension here, where acos is infinitely ill-conditioned:
     # a 1-ulp difference in the foot target moves the knee angles by ~sqrt(ulp), so angles agree to 1e-7 only.
     assert _angle_err(got["traj"][0], ref["traj"][:24]) < 1e-7
+    # a stride too long for the stance ends only: the stretched feet leave the contact set, the rest carries the body
+    q = orc.make_params(torso_pos=(0, 0, -0.1), period=3.0, step_length=1.5, step_height=0.1, step_duration=0.5)
+    om.set_ignore_reach(False)
+    assert om.measure_cot(q, 20)["status"] == 1 and m.eval_gaits(q[None], 20)["status"][0] & 2
+    om.set_ignore_reach(True)
+    ref = om.measure_cot(q, 20, detail=True)
+    got = m.eval_gaits(q[None], 20, flags=hsl.HSL_FLAG_IGNORE_REACH)
+    assert ref["status"] == 0 and (got["status"][0] & 15) == 0
+    assert abs(got["cot"][0] - ref["cot"]) <= 1e-7 * abs(ref["cot"])
 
 
 @pytest.mark.parametrize("pid", [8, 9, 26])
