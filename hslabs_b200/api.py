@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 HSL_NPARAM = 13
 HSL_FLAG_IGNORE_REACH = 1
 ST_BAD_PARAMS, ST_UNREACHABLE, ST_SOLVER, ST_FEW_CONTACTS, ST_ILLCOND = 1, 2, 4, 8, 16
+HSL_ST_BAD_PARAMS, HSL_ST_UNREACHABLE, HSL_ST_SOLVER, HSL_ST_FEW_CONTACTS, HSL_ST_ILLCOND = 1, 2, 4, 8, 16  # include/hsl.h
 SWEEP_NAMES = {"step_duration": 6, "period": 7, "step_length": 8, "step_height": 9}  # pergen.cpp:423
 
 _lib = None

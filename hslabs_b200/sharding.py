@@ -16,8 +16,10 @@ def shard_bounds(n_cand, world, rank):
 
 def evaluate_sharded(eval_fn, params, world, rank, all_gather_fn):
     """eval_fn(local_params) -> cost array for the local shard (NaN = failed candidate).
-    all_gather_fn(padded_local_costs) -> array [world * per].  Returns (costs[C], best index, ranking)."""
-    params = np.asarray(params, np.float64).reshape(-1, params.shape[-1])
+    all_gather_fn(padded_local_costs) -> array [world * per].  Returns (costs[C], best index or -1, ranking of the valid
+    candidates)."""
+    params = np.asarray(params, np.float64)
+    params = params.reshape(-1, params.shape[-1])
     n = params.shape[0]
     lo, hi, per = shard_bounds(n, world, rank)
     local = np.full(per, np.nan)
@@ -25,9 +27,11 @@ def evaluate_sharded(eval_fn, params, world, rank, all_gather_fn):
         local[:hi - lo] = np.asarray(eval_fn(params[lo:hi]), np.float64)
     gathered = np.asarray(all_gather_fn(local), np.float64).reshape(world, per)
     costs = np.concatenate([gathered[r][:max(0, min(per, n - r * per))] for r in range(world)])
-    key = np.where(np.isnan(costs), np.inf, costs)
-    order = np.argsort(key, kind="stable")
-    return costs, int(order[0]), order
+    # same rule as hsl_select_best / hsl_select_topk on the device: failed candidates (NaN) are never ranked, ties go to
+    # the lowest index, best = -1 when nothing is valid
+    valid = np.flatnonzero(~np.isnan(costs))
+    order = valid[np.argsort(costs[valid], kind="stable")]
+    return costs, (int(order[0]) if order.size else -1), order
 
 
 def torch_all_gather(dist, device=None):

@@ -1,0 +1,51 @@
+"""Worker of tests/test_gpu_multirank.py: one process per GPU (torch.distributed.run), NCCL.
+Every rank checks that the sharded DeviceEvaluator / search results equal its own single-GPU evaluation of the whole
+batch and writes rank<r>.ok into the directory given on the command line."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main(out_dir):
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    import hslabs_b200 as hsl
+    from hslabs_b200 import search
+    model = hsl.Model(hsl.model_path("hexapod"))
+    rng = np.random.default_rng(3)
+    n, n_t = 1001, 32                      # odd count: ragged last shard
+    p = np.zeros((n, 13))
+    p[:, 2] = rng.uniform(-0.15, -0.05, n); p[:, 6] = rng.uniform(0, 1, n); p[:, 7] = rng.uniform(1, 6, n)
+    p[:, 8] = rng.uniform(0.1, 0.5, n); p[:, 9] = rng.uniform(0.02, 0.12, n); p[:, 11] = -1
+    p[17, 2] = 0.4                         # unreachable: NaN cost on every rank
+    single = model.eval_gaits(p, n_t)
+    cand = torch.from_numpy(p).to(dev)
+    cot, st = search.DeviceEvaluator(model, n_t)(cand)   # sharded over the ranks, all-gathered
+    got = cot.cpu().numpy()
+    assert np.array_equal(got, single["cot"], equal_nan=True), "sharded costs differ from the single-GPU evaluation"
+    assert np.array_equal(st.cpu().numpy(), single["status"])
+    idx, val = search.top_k(cot, 5)
+    key = np.where(np.isnan(single["cot"]), np.inf, single["cot"])
+    assert list(idx.cpu().numpy()) == list(np.argsort(key, kind="stable")[:5])
+    res = search.cem_search(model, p[0], {"period": (1.0, 6.0), "step_length": (0.1, 0.5)}, n_t, pop=256, elite=32, iters=3, seed=1)
+    allbest = [None] * world
+    dist.all_gather_object(allbest, float(res["best_cot"]))
+    assert all(b == allbest[0] for b in allbest), "ranks disagree on the search result"
+    # the C-ABI collective (hsl_allgather_costs over an ncclComm_t created from a broadcast unique id)
+    if hasattr(hsl.api, "nccl_allgather_selftest"):
+        hsl.api.nccl_allgather_selftest(rank, world, dist, dev)
+    dist.barrier()
+    open(os.path.join(out_dir, "rank%d.ok" % rank), "w").write("ok\n")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

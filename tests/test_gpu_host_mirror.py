@@ -73,7 +73,12 @@ def test_main_like_sequence(demo, orc, pid, tmp_path):
     n_t = int(params[7] / 0.02 + .5)
     assert rows.shape == (n_t, 2 * m.config_dim + m.nmj)
     ref2 = m.measure_cot(params, n_t, detail=True)
-    for tsi in (0, 1, 2, n_t - 1):
+    cd, dt = m.config_dim, params[7] / n_t
+    for tsi in range(n_t):
         t2 = tsi + n_t if tsi < 2 else tsi
-        assert np.allclose(rows[tsi, :m.config_dim], ref2["traj"][t2], rtol=2e-5, atol=2e-6)
-        assert np.allclose(rows[tsi, 2 * m.config_dim:], ref2["tau"][t2 - 2], rtol=2e-5, atol=2e-6)
+        assert np.allclose(rows[tsi, :cd], ref2["traj"][t2], rtol=2e-5, atol=2e-6)
+        # q-dot columns: periodic::compute_vel_traj (periodic.cpp:261-282), central difference with the +-pi wrap
+        d = ref2["traj"][t2 + 1] - ref2["traj"][t2 - 1]
+        d = np.where(d > np.pi, d - 2 * np.pi, np.where(d < -np.pi, d + 2 * np.pi, d))
+        assert np.allclose(rows[tsi, cd:2 * cd], d / (2 * dt), rtol=2e-5, atol=2e-6), tsi
+        assert np.allclose(rows[tsi, 2 * cd:], ref2["tau"][t2 - 2], rtol=2e-5, atol=2e-6)

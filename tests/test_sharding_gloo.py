@@ -68,5 +68,15 @@ def test_two_rank_gather_matches_single(orc, tmp_path):
     b = np.load(tmp_path / "rank1.npz")
     assert np.array_equal(a["costs"], b["costs"], equal_nan=True) and a["best"] == b["best"]
     assert np.array_equal(a["costs"], ref_cost, equal_nan=True)
-    assert np.isnan(a["costs"][3]) and a["order"][-1] == 3
+    assert np.isnan(a["costs"][3]) and 3 not in a["order"] and len(a["order"]) == n - 1  # failed candidates are not ranked
     assert a["best"] == int(np.nanargmin(ref_cost))
+
+
+def test_selection_rule_matches_the_device_one():
+    """no valid candidate -> best index -1 (like hsl_select_best), NaN never ranked, list input accepted."""
+    from hslabs_b200.sharding import evaluate_sharded
+    costs, best, order = evaluate_sharded(lambda p: np.full(len(p), np.nan), [[0.0] * 13] * 3, 1, 0, lambda x: x)
+    assert best == -1 and order.size == 0 and np.isnan(costs).all()
+    vals = np.array([2.0, np.nan, 1.0, 1.0])
+    costs, best, order = evaluate_sharded(lambda p: vals, np.zeros((4, 13)), 1, 0, lambda x: x)
+    assert best == 2 and list(order) == [2, 3, 0]
