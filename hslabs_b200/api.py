@@ -66,6 +66,9 @@ def _load():
     lib.hsl_solve_forces_gait_host.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp]
     lib.hsl_set_tuning.argtypes = [vp, i32, i32]
     lib.hsl_set_max_slots.argtypes = [vp, i64]
+    lib.hsl_get_tuning.argtypes = [vp, vp, vp]
+    lib.hsl_set_kernel_timing.argtypes = [vp, i32]
+    lib.hsl_last_kernel_ms.argtypes = [vp, vp]
     lib.hsl_pinned_alloc.restype = vp
     lib.hsl_pinned_alloc.argtypes = [C.c_size_t]
     lib.hsl_pinned_free.argtypes = [vp]
@@ -83,7 +86,7 @@ def exported_symbols():
     """Every entry point include/hsl.h declares (checked by the CPU test tier)."""
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
-            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
+            "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_get_tuning", "hsl_set_kernel_timing", "hsl_last_kernel_ms", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk"]
 
 
@@ -198,8 +201,25 @@ class Model:
         _check(_load().hsl_set_rec_transform(self._h, _p(tr), _p(ea)))
 
     # ---- measurement helpers
-    def set_tuning(self, fb=64, maxreg=128):
-        _check(_load().hsl_set_tuning(self._h, fb, maxreg))
+    def set_tuning(self, fb=None, maxreg=None):
+        """Cost-only kernel variant: frame slots per block (32 | 64) and register cap (64..255, or 1 for the persistent
+        pipelined kernel).  None keeps the value in use (the per-model library default unless changed before)."""
+        cur_fb, cur_mr = self.get_tuning()
+        _check(_load().hsl_set_tuning(self._h, cur_fb if fb is None else int(fb), cur_mr if maxreg is None else int(maxreg)))
+
+    def get_tuning(self):
+        fb, mr = C.c_int(0), C.c_int(0)
+        _check(_load().hsl_get_tuning(self._h, C.byref(fb), C.byref(mr)))
+        return fb.value, mr.value
+
+    def set_kernel_timing(self, on=True):
+        _check(_load().hsl_set_kernel_timing(self._h, int(bool(on))))
+
+    def last_kernel_ms(self):
+        """(setup, per-frame kernel, finish) durations in ms of the last gait-evaluation chunk on this handle."""
+        ms = (C.c_float * 3)()
+        _check(_load().hsl_last_kernel_ms(self._h, ms))
+        return float(ms[0]), float(ms[1]), float(ms[2])
 
     def set_max_slots(self, max_slots):
         """Frame slots per launch: larger batches run as consecutive chunks (bounded workspace, same results)."""

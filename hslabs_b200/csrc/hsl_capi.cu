@@ -65,7 +65,12 @@ struct HslModel {
   DevBuf cand, ttab, wframe, fmin, fmax, status, params, out4, dump_x, dump_z, dump_tau, dump_q, dump_c, in_a, in_b, stage;
   PinBuf pin_in, pin_out;
   cudaStream_t stream = nullptr;
+  // hsl_set_kernel_timing: CUDA events around the three kernels of the last gait-evaluation chunk (on its stream)
+  bool timing = false;
+  cudaEvent_t tev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool tev_valid = false;
   ~HslModel() {
+    for (cudaEvent_t e : tev) if (e) cudaEventDestroy(e);
     DevBuf* all[] = {&cand, &ttab, &wframe, &fmin, &fmax, &status, &params, &out4, &dump_x, &dump_z, &dump_tau, &dump_q, &dump_c, &in_a, &in_b, &stage};
     for (DevBuf* b : all) b->release();
     pin_in.release();
@@ -136,12 +141,31 @@ int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
   m->maxreg = maxreg;
   return HSL_OK;
 }
+int hsl_get_tuning(const HslModel* m, int* fb, int* maxreg) {
+  if (!m) return set_err(HSL_ERR_ARG, "null model");
+  if (fb) *fb = m->fb;
+  if (maxreg) *maxreg = m->maxreg;
+  return HSL_OK;
+}
 int hsl_set_max_slots(HslModel* m, int64_t max_slots) {
   if (!m || max_slots < 5 || max_slots > 0x7fffffff) return set_err(HSL_ERR_ARG, "frame slots per launch must be in 5 .. 2^31 - 1");
   m->max_slots = max_slots;
   return HSL_OK;
 }
 int64_t hsl_launch_count(const HslModel* m) { return m ? m->launches : 0; }
+int hsl_set_kernel_timing(HslModel* m, int on) {
+  if (!m) return set_err(HSL_ERR_ARG, "null model");
+  m->timing = (on != 0);
+  m->tev_valid = false;
+  return HSL_OK;
+}
+int hsl_last_kernel_ms(HslModel* m, float ms[3]) {
+  if (!m || !ms) return set_err(HSL_ERR_ARG, "null argument");
+  if (!m->tev_valid) return set_err(HSL_ERR_ARG, "no timed gait evaluation on this handle (hsl_set_kernel_timing)");
+  HSL_CUDA(cudaEventSynchronize(m->tev[3]));
+  for (int k = 0; k < 3; k++) HSL_CUDA(cudaEventElapsedTime(&ms[k], m->tev[k], m->tev[k + 1]));
+  return HSL_OK;
+}
 int hsl_set_rec_transform(HslModel* m, const double* transl, const double* eas) {
   if (!m) return set_err(HSL_ERR_ARG, "null model");
   if (!transl && !eas) { m->rec_on = false; return HSL_OK; }
@@ -197,8 +221,14 @@ static int eval_gaits_chunk(HslModel* m, int64_t C, int n_t, const double* d_par
   HSL_CUDA(clkbuf.need(sizeof(long long) * nblk * warps * 8));
   A.phase_clk = (long long*)clkbuf.p;
 #endif
+  if (m->timing) {
+    for (cudaEvent_t& e : m->tev) if (!e) HSL_CUDA(cudaEventCreate(&e));
+    HSL_CUDA(cudaEventRecord(m->tev[0], st));
+  }
   HSL_CUDA(hsl_launch_setup(m->pod, C, n_t, d_params, (HslCand*)m->cand.p, (double*)m->ttab.p, st_buf, st));
+  if (m->timing) HSL_CUDA(cudaEventRecord(m->tev[1], st));
   HSL_CUDA(hsl_launch_frames(m->pod, A, HSL_MODE_GAIT, dump, m->fb, m->maxreg, st));
+  if (m->timing) HSL_CUDA(cudaEventRecord(m->tev[2], st));
 #ifdef HSL_PHASE_CLOCKS
   {
     HSL_CUDA(cudaStreamSynchronize(st));
@@ -235,6 +265,7 @@ static int eval_gaits_chunk(HslModel* m, int64_t C, int n_t, const double* d_par
 #endif
   HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, (const HslCand*)m->cand.p, nullptr, A.wframe, A.fmin_cfz, A.fmax_mu, st_buf,
                              d_cot, d_work, d_min, d_max, st));
+  if (m->timing) { HSL_CUDA(cudaEventRecord(m->tev[3], st)); m->tev_valid = true; }
   m->launches += 3;
   return HSL_OK;
 }

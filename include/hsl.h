@@ -127,12 +127,18 @@ void* hsl_pinned_alloc(size_t bytes);
 void hsl_pinned_free(void* p);
 
 /* tuning / measurement helpers */
-int hsl_set_tuning(HslModel* m, int fb, int maxreg);          /* cost-only kernel variant: frame slots per block (32|64), register cap per thread */
+int hsl_set_tuning(HslModel* m, int fb, int maxreg);          /* cost-only kernel variant: frame slots per block (32|64), register cap per thread (64..255; 1 = persistent pipelined kernel) */
+int hsl_get_tuning(const HslModel* m, int* fb, int* maxreg);  /* the variant in use (the per-model default unless hsl_set_tuning was called) */
 /* hsl_eval_gaits / hsl_eval_gaits_host evaluate a batch of any size as consecutive chunks of at most max_slots frame
  * slots (a candidate takes n_t + 4); default 2^26 (~2 GB of per-frame workspace), bounds 5 .. 2^31 - 1.  Results do
  * not depend on the chunking. */
 int hsl_set_max_slots(HslModel* m, int64_t max_slots);
 int64_t hsl_launch_count(const HslModel* m);                  /* kernels launched through this handle so far */
+/* Measurement: with timing on, hsl_eval_gaits* brackets its three kernels (candidate setup, per-frame kernel, per-candidate
+ * finish) with CUDA events on the launching stream; hsl_last_kernel_ms waits for the last chunk evaluated on this handle and
+ * returns their durations.  bench.py takes the roofline's kernel time from ms[1]. */
+int hsl_set_kernel_timing(HslModel* m, int on);
+int hsl_last_kernel_ms(HslModel* m, float ms[3]);
 int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms); /* FP64 FMA throughput of the device */
 int hsl_math_selftest(int n, const double* a, const double* b, double* out /*[10][n]*/); /* accuracy of the kernels' branch-free div/sqrt/atan2/sincos vs the library ones (HOST pointers) */
 

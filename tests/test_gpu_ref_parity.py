@@ -78,9 +78,9 @@ def test_illcond_flag_on_the_device(hsl, orc):
     ref = om.eval_batch(p, n_t, nthreads=os.cpu_count() or 4)
     reach = ref["status"] != 1
     assert np.array_equal((gpu["status"] & 2) == 0, reach)
-    flagged = np.flatnonzero((gpu["status"] & hsl.HSL_ST_ILLCOND) != 0)
+    flagged = np.flatnonzero(gpu["status"] == hsl.HSL_ST_ILLCOND)  # the informational bit alone: results are valid
     clean = np.flatnonzero(gpu["status"] == 0)
-    assert 20 <= flagged.size <= 80 and clean.size >= 250
+    assert 20 <= flagged.size <= 120 and clean.size >= 250, (flagged.size, clean.size, np.bincount(gpu["status"]))
     for c in (91, 113, 114):  # the three candidates the host-emulation test pins
         assert c in flagged
     # unflagged: FP64 oracle to 1e-9, same ranking
