@@ -208,7 +208,9 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        # a short watchdog: a mismatched collective must fail in two minutes, not hold N GPUs for the default ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # 256 MiB > 126 MB L2
 
@@ -397,7 +399,8 @@ def main():
 
     # ------------------------------------------------------------------ sustained: the same step for >= 2 s
     if not args.no_extras:
-        n_long = int(max(200, 2200.0 / max(np.median(step_ms), 1e-3)))
+        # the same count on every rank (each step has a collective): derived from the max-over-ranks time, not a local one
+        n_long = int(max(200, 2200.0 / max(ms_total / args.steps, 1e-3)))
         sampler = ClockSampler(local)
         barrier()
         sampler.start()

@@ -77,6 +77,15 @@ def _load():
     lib.hsl_dfma_probe.argtypes = [i32, i32, i32, vp, vp]
     lib.hsl_math_selftest.argtypes = [i32, vp, vp, vp]
     lib.hsl_select_best.argtypes = [vp, i64, vp, vp, vp]
+    lib.hsl_eval_trajectories.argtypes = [vp, i64, i32] + [vp] * 10
+    lib.hsl_solve_frames.argtypes = [vp, i64] + [vp] * 12
+    lib.hsl_fk_records_host.argtypes = [vp, i64, vp, vp, vp]
+    lib.hsl_nccl_unique_id.argtypes = [vp]
+    lib.hsl_nccl_comm_init.argtypes = [C.POINTER(vp), i32, vp, i32]
+    lib.hsl_nccl_comm_destroy.argtypes = [vp]
+    lib.hsl_allgather_costs.argtypes = [vp, vp, i64, vp, vp]
+    lib.hsl_allgather_costs_host.argtypes = [vp, i32, vp, i64, vp]
+    lib.hsl_model_tables.argtypes = [vp] + [vp] * 6
     lib.hsl_select_topk.argtypes = [vp, i64, i32, vp, vp, vp]
     _lib = lib
     return lib
@@ -87,7 +96,8 @@ def exported_symbols():
     return ["hsl_model_load_xml", "hsl_model_free", "hsl_model_dims", "hsl_model_rcap", "hsl_model_pod", "hsl_last_error",
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_get_tuning", "hsl_set_kernel_timing", "hsl_last_kernel_ms", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
-            "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk"]
+            "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
+            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables"]
 
 
 class _Pinned:
@@ -295,6 +305,22 @@ class Model:
         _check(_load().hsl_ik_records_host(self._h, n, _p(rec), flags, _p(q), _p(status)))
         return dict(q=q, status=status)
 
+    def tables(self):
+        """periodic::set_dynparts data: parent ids, foot / limb-top body ids, masses, COM and foot-point offsets."""
+        out = dict(parent=np.zeros(self.n, np.int32), footis=np.zeros(self.nf, np.int32), limb_top=np.zeros(self.nf, np.int32),
+                   masses=np.zeros(self.n), com_offset=np.zeros((self.n, 3)), foot_offset=np.zeros((self.nf, 3)))
+        _check(_load().hsl_model_tables(self._h, *[_p(out[k]) for k in ("parent", "footis", "limb_top", "masses", "com_offset", "foot_offset")]))
+        return out
+
+    def fk_records(self, q):
+        """kinematicmodel::set_jvalues + recompute_modelnodes: ground frames of the bodies and of their joints, column-major
+        4x4 `affine`s [n][bodies][16] each, for joint values q [n][config_dim]."""
+        q = np.ascontiguousarray(q, np.float64).reshape(-1, self.config_dim)
+        n = q.shape[0]
+        A = np.empty((n, self.n, 16)); J = np.empty((n, self.n, 16))
+        _check(_load().hsl_fk_records_host(self._h, n, _p(q), _p(A), _p(J)))
+        return dict(A_ground=A, J_A_ground=J)
+
     def solve_forces(self, pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos, torques):
         """forcetorquesolver::solve_forces (ftsolver.cpp:331-378): contact forces of all feet for given motor torques."""
         arrs = [np.ascontiguousarray(a, np.float64) for a in (pos, jpos, jzaxis, mom_rate, ang_mom_rate, fpos)]
@@ -319,6 +345,64 @@ class Model:
                           stream=0):
         _check(_load().hsl_eval_gaits(self._h, n_cand, n_t, d_params, flags, d_cot or None, d_work or None,
                                       d_min_cfz or None, d_max_mu or None, d_status or None, stream or None))
+
+
+    def eval_trajectories_device(self, n_cand, n_t, d_traj, d_dt, d_work=0, d_min_cfz=0, d_max_mu=0, d_status=0, d_x=0, d_z=0, d_tau=0,
+                                 stream=0):
+        """hsl_eval_trajectories: the L2 entry on device-resident trajectories (integer device addresses, row-major layouts of
+        the host form; queued on `stream`, not synchronised)."""
+        _check(_load().hsl_eval_trajectories(self._h, n_cand, n_t, d_traj, d_dt, d_work or None, d_min_cfz or None, d_max_mu or None,
+                                             d_status or None, d_x or None, d_z or None, d_tau or None, stream or None))
+
+    def solve_frames_device(self, n_frames, d_pos, d_jpos, d_jzaxis, d_mom_rate, d_ang_mom_rate, d_fpos, d_contacts, d_x=0, d_z=0, d_tau=0,
+                            d_status=0, stream=0):
+        """hsl_solve_frames: the L1 entry on device-resident dynrecord arrays (integer device addresses)."""
+        _check(_load().hsl_solve_frames(self._h, n_frames, d_pos, d_jpos, d_jzaxis, d_mom_rate, d_ang_mom_rate, d_fpos, d_contacts,
+                                        d_x or None, d_z or None, d_tau or None, d_status or None, stream or None))
+
+
+class NcclComm:
+    """An ncclComm_t made through the C ABI (hsl_nccl_unique_id / hsl_nccl_comm_init), for hsl_allgather_costs.
+    `exchange(id_bytes_or_None) -> id_bytes` hands rank 0's 128-byte id to every rank (any side channel: a file, MPI,
+    torch.distributed.broadcast_object_list ...)."""
+
+    def __init__(self, rank, world, exchange):
+        ident = (C.c_char * 128)()
+        if rank == 0:
+            _check(_load().hsl_nccl_unique_id(ident))
+        raw = exchange(bytes(ident.raw) if rank == 0 else None)
+        ident = (C.c_char * 128).from_buffer_copy(raw)
+        self._c = C.c_void_p()
+        _check(_load().hsl_nccl_comm_init(C.byref(self._c), world, ident, rank))
+        self.rank, self.world = rank, world
+
+    def allgather_costs(self, d_local, n_per_rank, d_all, stream=0):
+        _check(_load().hsl_allgather_costs(self._c, d_local, n_per_rank, d_all, stream or None))
+
+    def destroy(self):
+        if self._c:
+            _check(_load().hsl_nccl_comm_destroy(self._c))
+            self._c = C.c_void_p()
+
+
+def nccl_allgather_selftest(rank, world, dist, dev):
+    """hsl_allgather_costs over a communicator made through the C ABI, against torch.distributed's all-gather."""
+    import torch
+
+    def exchange(raw):
+        box = [raw]
+        dist.broadcast_object_list(box, src=0)
+        return box[0]
+    comm = NcclComm(rank, world, exchange)
+    n = 1000
+    local = torch.arange(n, dtype=torch.float64, device=dev) + 1e6 * rank
+    mine = torch.empty(world * n, dtype=torch.float64, device=dev)
+    ref = torch.empty(world * n, dtype=torch.float64, device=dev)
+    comm.allgather_costs(local.data_ptr(), n, mine.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    dist.all_gather_into_tensor(ref, local)
+    torch.cuda.synchronize()
+    assert torch.equal(mine, ref), "hsl_allgather_costs differs from torch.distributed.all_gather_into_tensor"
+    comm.destroy()
 
 
 def select_best_device(d_cost, n, d_index, d_value=0, stream=0):

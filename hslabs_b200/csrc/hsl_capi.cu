@@ -1,6 +1,7 @@
 // C ABI of libhsl_b200.so (include/hsl.h): model handle, device workspace, host/device entry points.
 // No CPU fallback exists: every compute entry needs a CUDA device and fails with HSL_ERR_CUDA otherwise.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cstdio>
 #include <cstring>
@@ -134,6 +135,31 @@ double hsl_model_rcap(const HslModel* m) { return m ? m->pod.rcap : 0.0; }
 size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap) {
   if (m && dst) memcpy(dst, &m->pod, cap < sizeof(HslModelPod) ? cap : sizeof(HslModelPod));
   return sizeof(HslModelPod);
+}
+int hsl_model_tables(const HslModel* m, int32_t* parent, int32_t* footis, int32_t* limb_top, double* masses, double* com_offset,
+                     double* foot_offset) {
+  if (!m) return set_err(HSL_ERR_ARG, "null model");
+  const HslModelPod& P = m->pod;
+  for (int i = 0; i < P.n; i++) {
+    if (parent) parent[i] = P.parent[i];
+    if (masses) masses[i] = 0;
+  }
+  for (int t = 0; t < P.ntrunk; t++) {
+    const int b = P.trunk[t].body;
+    if (masses) masses[b] = P.trunk[t].mass;
+    if (com_offset) for (int k = 0; k < 3; k++) com_offset[3 * b + k] = P.trunk[t].com[k];
+  }
+  for (int l = 0; l < P.nf; l++) {
+    for (int h = 0; h < 3; h++) {
+      const int b = P.limb[l].h[h].body;
+      if (masses) masses[b] = P.limb[l].h[h].mass;
+      if (com_offset) for (int k = 0; k < 3; k++) com_offset[3 * b + k] = P.limb[l].h[h].com[k];
+    }
+    if (footis) footis[l] = P.limb[l].h[2].body;
+    if (limb_top) limb_top[l] = P.limb[l].h[0].body;
+    if (foot_offset) for (int k = 0; k < 3; k++) foot_offset[3 * l + k] = P.limb[l].foot[k];
+  }
+  return HSL_OK;
 }
 int hsl_set_tuning(HslModel* m, int fb, int maxreg) {
   if (!m || (fb != 32 && fb != 64) || (maxreg != 1 && (maxreg < 64 || maxreg > 255))) return set_err(HSL_ERR_ARG, "frame slots per block must be 32 or 64; register cap 64..255, or 1 for the pipelined kernel");
@@ -390,6 +416,66 @@ int hsl_eval_gaits_detail_host(HslModel* m, int64_t n_cand, int n_t, const doubl
   return eval_gaits_host_impl(m, n_cand, n_t, params, flags, cot, work, min_cfz, max_mu, status, true, traj, x, z, tau, contacts);
 }
 
+// L2: supplied joint trajectories.  Launch part shared by the device-pointer and the host entry: per-frame dumps go to
+// the component-major workspace (dump_x / dump_z / dump_tau), the per-candidate results to out4 = [cot | work | min | max].
+static int eval_trajectories_launch(HslModel* m, int64_t C, int n_t, const double* d_traj, const double* d_dt, int32_t* d_status,
+                                    bool dumps, cudaStream_t st) {
+  const HslModelPod& P = m->pod;
+  const int64_t nfr = C * n_t;
+  HSL_CUDA(m->wframe.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmin.need(sizeof(double) * nfr));
+  HSL_CUDA(m->fmax.need(sizeof(double) * nfr));
+  HSL_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * C, st));
+  HSL_CUDA(m->out4.need(sizeof(double) * 4 * C));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = C; A.n_t = n_t; A.n_frames = nfr;
+  A.traj = d_traj; A.dt_in = d_dt;
+  A.wframe = (double*)m->wframe.p; A.fmin_cfz = (double*)m->fmin.p; A.fmax_mu = (double*)m->fmax.p;
+  A.status = d_status;
+  if (dumps) {
+    HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * nfr));
+    HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * nfr));
+    HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * nfr));
+    A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
+  }
+  HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_TRAJ, true, 32, 1, st));
+  double* d4 = (double*)m->out4.p;
+  HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, nullptr, A.dt_in, A.wframe, A.fmin_cfz, A.fmax_mu, A.status, nullptr, d4 + C,
+                             d4 + 2 * C, d4 + 3 * C, st));
+  m->launches += 2;
+  return HSL_OK;
+}
+
+// [comps][nfr] workspace -> the caller's row-major [nfr][comps] DEVICE array
+static int transpose_to(HslModel* m, const void* dsrc, int comps, int64_t nfr, void* d_dst, cudaStream_t st) {
+  if (!d_dst) return HSL_OK;
+  HSL_CUDA(hsl_launch_transpose(dsrc, d_dst, comps, nfr, 8, st));
+  m->launches += 1;
+  return HSL_OK;
+}
+
+int hsl_eval_trajectories(HslModel* m, int64_t C, int n_t, const double* d_traj, const double* d_dt, double* d_work, double* d_min_cfz,
+                          double* d_max_mu, int32_t* d_status, double* d_x, double* d_z, double* d_tau, void* stream) {
+  if (!m || C < 1 || n_t < 1 || !d_traj || !d_dt) return set_err(HSL_ERR_ARG, "bad argument");
+  if (C * ((int64_t)n_t + 5) > 0x7fffffff) return set_err(HSL_ERR_ARG, "more than 2^31 frame slots in one call: split the batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const HslModelPod& P = m->pod;
+  const int64_t nfr = C * n_t;
+  int32_t* stp = d_status;
+  if (!stp) { HSL_CUDA(m->status.need(sizeof(int32_t) * C)); stp = (int32_t*)m->status.p; }
+  int rc = eval_trajectories_launch(m, C, n_t, d_traj, d_dt, stp, d_x || d_z || d_tau, st);
+  if (rc) return rc;
+  const double* d4 = (const double*)m->out4.p;
+  if (d_work) HSL_CUDA(cudaMemcpyAsync(d_work, d4 + C, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+  if (d_min_cfz) HSL_CUDA(cudaMemcpyAsync(d_min_cfz, d4 + 2 * C, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+  if (d_max_mu) HSL_CUDA(cudaMemcpyAsync(d_max_mu, d4 + 3 * C, sizeof(double) * C, cudaMemcpyDeviceToDevice, st));
+  if ((rc = transpose_to(m, m->dump_x.p, 6 * P.n, nfr, d_x, st))) return rc;
+  if ((rc = transpose_to(m, m->dump_z.p, 3 * P.nf, nfr, d_z, st))) return rc;
+  if ((rc = transpose_to(m, m->dump_tau.p, P.nmj, nfr, d_tau, st))) return rc;
+  return HSL_OK;
+}
+
 int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* traj, const double* dt, double* work, double* min_cfz,
                                double* max_mu, int32_t* status, double* x, double* z, double* tau) {
   if (!m || C < 1 || n_t < 1 || !traj || !dt) return set_err(HSL_ERR_ARG, "bad argument");
@@ -404,27 +490,9 @@ int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* tr
   HSL_CUDA(m->in_b.need(sizeof(double) * C));
   HSL_CUDA(cudaMemcpyAsync(m->in_a.p, traj, tbytes, cudaMemcpyHostToDevice, st));
   HSL_CUDA(cudaMemcpyAsync(m->in_b.p, dt, sizeof(double) * C, cudaMemcpyHostToDevice, st));
-  HSL_CUDA(m->wframe.need(sizeof(double) * nfr));
-  HSL_CUDA(m->fmin.need(sizeof(double) * nfr));
-  HSL_CUDA(m->fmax.need(sizeof(double) * nfr));
   HSL_CUDA(m->status.need(sizeof(int32_t) * C));
-  HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * C, st));
-  HSL_CUDA(m->out4.need(sizeof(double) * 4 * C));
-  HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * nfr));
-  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * nfr));
-  HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * nfr));
-  HslFrameArgs A;
-  memset(&A, 0, sizeof A);
-  A.n_cand = C; A.n_t = n_t; A.n_frames = nfr;
-  A.traj = (const double*)m->in_a.p; A.dt_in = (const double*)m->in_b.p;
-  A.wframe = (double*)m->wframe.p; A.fmin_cfz = (double*)m->fmin.p; A.fmax_mu = (double*)m->fmax.p;
-  A.status = (int32_t*)m->status.p;
-  A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
-  HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_TRAJ, true, 32, 1, st));
+  if ((rc = eval_trajectories_launch(m, C, n_t, (const double*)m->in_a.p, (const double*)m->in_b.p, (int32_t*)m->status.p, true, st))) return rc;
   double* d4 = (double*)m->out4.p;
-  HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, nullptr, A.dt_in, A.wframe, A.fmin_cfz, A.fmax_mu, A.status, nullptr, d4 + C,
-                             d4 + 2 * C, d4 + 3 * C, st));
-  m->launches += 2;
   HSL_CUDA(m->pin_in.need(sizeof(double) * 4 * C + sizeof(int32_t) * C));
   double* h4 = (double*)m->pin_in.p;
   HSL_CUDA(cudaMemcpyAsync(h4, d4, sizeof(double) * 4 * C, cudaMemcpyDeviceToHost, st));
@@ -437,6 +505,46 @@ int hsl_eval_trajectories_host(HslModel* m, int64_t C, int n_t, const double* tr
   if ((rc = fetch_transposed(m, m->dump_x.p, 6 * P.n, nfr, x, st))) return rc;
   if ((rc = fetch_transposed(m, m->dump_z.p, 3 * P.nf, nfr, z, st))) return rc;
   if ((rc = fetch_transposed(m, m->dump_tau.p, P.nmj, nfr, tau, st))) return rc;
+  return HSL_OK;
+}
+
+// L1: populated dynrecords.  Launch part shared by the device-pointer and the host entry.
+static int solve_frames_launch(HslModel* m, int64_t F, const double* d_pos, const double* d_jpos, const double* d_jz,
+                               const double* d_momrate, const double* d_angrate, const double* d_fpos, const uint8_t* d_contacts,
+                               int32_t* d_status, cudaStream_t st) {
+  const HslModelPod& P = m->pod;
+  HSL_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * F, st));
+  HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * F));
+  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * F));
+  HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * F));
+  HslFrameArgs A;
+  memset(&A, 0, sizeof A);
+  A.n_cand = F;  // status is per frame in this mode (slot.c is forced to the frame below)
+  A.n_t = 1; A.n_frames = F;
+  A.f_pos = d_pos; A.f_jpos = d_jpos; A.f_jz = d_jz; A.f_momrate = d_momrate; A.f_angrate = d_angrate;
+  A.f_fpos = d_fpos; A.f_contacts = d_contacts;
+  A.status = d_status;
+  A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
+  HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_FIELDS, true, 32, 1, st));
+  m->launches += 1;
+  return HSL_OK;
+}
+
+int hsl_solve_frames(HslModel* m, int64_t F, const double* d_pos, const double* d_jpos, const double* d_jzaxis, const double* d_mom_rate,
+                     const double* d_ang_mom_rate, const double* d_fpos, const uint8_t* d_contacts, double* d_x, double* d_z, double* d_tau,
+                     int32_t* d_status, void* stream) {
+  if (!m || F < 1 || !d_pos || !d_jpos || !d_jzaxis || !d_mom_rate || !d_ang_mom_rate || !d_fpos || !d_contacts)
+    return set_err(HSL_ERR_ARG, "bad argument");
+  if (F > 0x7fffffff) return set_err(HSL_ERR_ARG, "more than 2^31 frames in one call: split the batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  const HslModelPod& P = m->pod;
+  int32_t* stp = d_status;
+  if (!stp) { HSL_CUDA(m->status.need(sizeof(int32_t) * F)); stp = (int32_t*)m->status.p; }
+  int rc = solve_frames_launch(m, F, d_pos, d_jpos, d_jzaxis, d_mom_rate, d_ang_mom_rate, d_fpos, d_contacts, stp, st);
+  if (rc) return rc;
+  if ((rc = transpose_to(m, m->dump_x.p, 6 * P.n, F, d_x, st))) return rc;
+  if ((rc = transpose_to(m, m->dump_z.p, 3 * P.nf, F, d_z, st))) return rc;
+  if ((rc = transpose_to(m, m->dump_tau.p, P.nmj, F, d_tau, st))) return rc;
   return HSL_OK;
 }
 
@@ -458,21 +566,9 @@ int hsl_solve_frames_host(HslModel* m, int64_t F, const double* pos, const doubl
   HSL_CUDA(cudaMemcpyAsync(base + 5 * nb, fpos, fb, cudaMemcpyHostToDevice, st));
   HSL_CUDA(cudaMemcpyAsync(base + 5 * nb + fb, contacts, cb, cudaMemcpyHostToDevice, st));
   HSL_CUDA(m->status.need(sizeof(int32_t) * F));
-  HSL_CUDA(cudaMemsetAsync(m->status.p, 0, sizeof(int32_t) * F, st));
-  HSL_CUDA(m->dump_x.need(sizeof(double) * 6 * P.n * F));
-  HSL_CUDA(m->dump_z.need(sizeof(double) * 3 * P.nf * F));
-  HSL_CUDA(m->dump_tau.need(sizeof(double) * P.nmj * F));
-  HslFrameArgs A;
-  memset(&A, 0, sizeof A);
-  A.n_cand = F;  // status is per frame in this mode (slot.c is forced to the frame below)
-  A.n_t = 1; A.n_frames = F;
-  A.f_pos = (const double*)(base); A.f_jpos = (const double*)(base + nb); A.f_jz = (const double*)(base + 2 * nb);
-  A.f_momrate = (const double*)(base + 3 * nb); A.f_angrate = (const double*)(base + 4 * nb);
-  A.f_fpos = (const double*)(base + 5 * nb); A.f_contacts = (const uint8_t*)(base + 5 * nb + fb);
-  A.status = (int32_t*)m->status.p;
-  A.x = (double*)m->dump_x.p; A.z = (double*)m->dump_z.p; A.tau = (double*)m->dump_tau.p;
-  HSL_CUDA(hsl_launch_frames(P, A, HSL_MODE_FIELDS, true, 32, 1, st));
-  m->launches += 1;
+  if ((rc = solve_frames_launch(m, F, (const double*)base, (const double*)(base + nb), (const double*)(base + 2 * nb),
+                                (const double*)(base + 3 * nb), (const double*)(base + 4 * nb), (const double*)(base + 5 * nb),
+                                (const uint8_t*)(base + 5 * nb + fb), (int32_t*)m->status.p, st))) return rc;
   if (status) {
     HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * F, cudaMemcpyDeviceToHost, st));
     HSL_CUDA(cudaStreamSynchronize(st));
@@ -536,6 +632,26 @@ int hsl_ik_records_host(HslModel* m, int64_t n, const double* rec, int flags, do
   m->launches += 1;
   HSL_CUDA(cudaMemcpyAsync(q, m->in_b.p, qbytes, cudaMemcpyDeviceToHost, st));
   if (status) HSL_CUDA(cudaMemcpyAsync(status, m->status.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
+  return HSL_OK;
+}
+
+int hsl_fk_records_host(HslModel* m, int64_t n, const double* q, double* A_ground, double* J_A_ground) {
+  if (!m || n < 1 || !q || (!A_ground && !J_A_ground)) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  const size_t qbytes = sizeof(double) * P.config_dim * n, abytes = sizeof(double) * 16 * P.n * n;
+  HSL_CUDA(m->in_b.need(qbytes));
+  HSL_CUDA(m->in_a.need(2 * abytes));
+  HSL_CUDA(cudaMemcpyAsync(m->in_b.p, q, qbytes, cudaMemcpyHostToDevice, st));
+  double* dA = (double*)m->in_a.p;
+  double* dJ = (double*)((char*)m->in_a.p + abytes);
+  HSL_CUDA(hsl_launch_fk_records(P, n, (const double*)m->in_b.p, A_ground ? dA : nullptr, J_A_ground ? dJ : nullptr, st));
+  m->launches += 1;
+  if (A_ground) HSL_CUDA(cudaMemcpyAsync(A_ground, dA, abytes, cudaMemcpyDeviceToHost, st));
+  if (J_A_ground) HSL_CUDA(cudaMemcpyAsync(J_A_ground, dJ, abytes, cudaMemcpyDeviceToHost, st));
   HSL_CUDA(cudaStreamSynchronize(st));
   return HSL_OK;
 }
@@ -632,6 +748,87 @@ int hsl_math_selftest(int n, const double* a, const double* b, double* out) {
   HSL_CUDA(cudaMemcpy(out, dout, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return HSL_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU: the one collective of the path
+// Candidates shard over ranks and never span GPUs; the only exchange is an all-gather of the per-candidate costs
+// (8 B each) before selection.  NCCL is bound at run time (dlsym on the process image first, so a host
+// that already carries an NCCL -- e.g. torch's bundled one -- is reused; else dlopen of libnccl.so.2): the library has
+// no link-time NCCL dependency and single-GPU users never load it.
+namespace {
+struct NcclApi {
+  bool ok = false;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, HslNcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  void* h = dlsym(RTLD_DEFAULT, "ncclAllGather") ? RTLD_DEFAULT : dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return api;
+  api.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  api.CommInitRank = (int (*)(void**, int, HslNcclId, int))dlsym(h, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  api.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather;
+  return api;
+}
+int nccl_check(int rc, const char* what) {
+  if (rc == 0) return HSL_OK;
+  NcclApi& a = nccl_api();
+  const std::string msg = std::string(what) + " failed: " + (a.GetErrorString ? a.GetErrorString(rc) : "?");
+  return set_err(HSL_ERR_CUDA, "NCCL: %s", msg.c_str());
+}
+}  // namespace
+
+int hsl_nccl_unique_id(HslNcclId* id) {
+  NcclApi& a = nccl_api();
+  if (!a.ok) return set_err(HSL_ERR_UNSUPPORTED, "NCCL is not available in this process (libnccl.so.2 not found)");
+  if (!id) return set_err(HSL_ERR_ARG, "null argument");
+  return nccl_check(a.GetUniqueId(id), "ncclGetUniqueId");
+}
+int hsl_nccl_comm_init(void** comm, int nranks, const HslNcclId* id, int rank) {
+  NcclApi& a = nccl_api();
+  if (!a.ok) return set_err(HSL_ERR_UNSUPPORTED, "NCCL is not available in this process (libnccl.so.2 not found)");
+  if (!comm || !id || nranks < 1 || rank < 0 || rank >= nranks) return set_err(HSL_ERR_ARG, "bad argument");
+  return nccl_check(a.CommInitRank(comm, nranks, *id, rank), "ncclCommInitRank");
+}
+int hsl_nccl_comm_destroy(void* comm) {
+  NcclApi& a = nccl_api();
+  if (!a.ok || !comm) return set_err(HSL_ERR_ARG, "bad argument");
+  return nccl_check(a.CommDestroy(comm), "ncclCommDestroy");
+}
+int hsl_allgather_costs(void* nccl_comm, const double* d_local, int64_t n_per_rank, double* d_all, void* stream) {
+  NcclApi& a = nccl_api();
+  if (!a.ok) return set_err(HSL_ERR_UNSUPPORTED, "NCCL is not available in this process (libnccl.so.2 not found)");
+  if (!nccl_comm || !d_local || !d_all || n_per_rank < 1) return set_err(HSL_ERR_ARG, "bad argument");
+  return nccl_check(a.AllGather(d_local, d_all, (size_t)n_per_rank, 8 /* ncclFloat64 */, nccl_comm, (cudaStream_t)stream), "ncclAllGather");
+}
+
+int hsl_allgather_costs_host(void* nccl_comm, int nranks, const double* local, int64_t n_per_rank, double* all) {
+  if (!nccl_comm || !local || !all || n_per_rank < 1 || nranks < 1) return set_err(HSL_ERR_ARG, "bad argument");
+  DevBuf a, b;
+  cudaStream_t st = nullptr;
+  int rc = HSL_OK;
+  do {
+    if (a.need(sizeof(double) * n_per_rank) != cudaSuccess || b.need(sizeof(double) * n_per_rank * nranks) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) { rc = set_err(HSL_ERR_CUDA, "CUDA: %s", "allocation failed"); break; }
+    if (cudaMemcpyAsync(a.p, local, sizeof(double) * n_per_rank, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = set_err(HSL_ERR_CUDA, "CUDA: %s", "H2D copy failed"); break; }
+    if ((rc = hsl_allgather_costs(nccl_comm, (const double*)a.p, n_per_rank, (double*)b.p, st))) break;
+    if (cudaMemcpyAsync(all, b.p, sizeof(double) * n_per_rank * nranks, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+        cudaStreamSynchronize(st) != cudaSuccess) { rc = set_err(HSL_ERR_CUDA, "CUDA: %s", "D2H copy failed"); break; }
+  } while (0);
+  a.release();
+  b.release();
+  if (st) cudaStreamDestroy(st);
+  return rc;
 }
 
 int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms) {

@@ -1191,6 +1191,57 @@ HSL_HD bool ik_record(const HslModelPod& M, int role, const double* rec, bool ig
   return ok;
 }
 
+// kinematicmodel::set_jvalues + recompute_modelnodes (model.cpp:183-201,314-318,362-366): ground frames of the bodies
+// and of their joints for given joint values q[config_dim], as column-major 4x4 `affine`s (matrix.cpp:138-146).
+// role < nf: the three hinge bodies of that limb; role == nf: the torso and the jointless trunk bodies.
+// A [n][16] = modelnode::A_ground, J [n][16] = modeljoint::A_ground (joint frame before the joint's own transform;
+// zeros for bodies without a joint).  Either may be null.
+HSL_HD void hsl_put_affine(double* dst, const double* R, const double* t) {
+#pragma unroll
+  for (int j = 0; j < 3; j++) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) dst[4 * j + i] = R[3 * j + i];
+    dst[4 * j + 3] = 0;
+  }
+  dst[12] = t[0]; dst[13] = t[1]; dst[14] = t[2]; dst[15] = 1;
+}
+HSL_HD void fk_record(const HslModelPod& M, int role, const double* q, double* Aout, double* Jout) {
+  double R0[9], t0[3];
+  euler_to_R(q[3], q[4], q[5], R0);
+  torso_frame(M, q, R0, t0);
+  if (role >= M.nf) {
+    const double I3[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int tb = 0; tb < M.ntrunk; tb++) {
+      double ob[3];
+      m3_affine(R0, M.trunk[tb].off, t0, ob);
+      const int b = M.trunk[tb].body;
+      if (Aout) hsl_put_affine(Aout + 16 * b, R0, ob);
+      if (Jout) {
+        if (tb == 0) hsl_put_affine(Jout + 16 * b, I3, M.Pt);  // the free joint's A_ground = A_parent (model.cpp:158-161)
+        else for (int k = 0; k < 16; k++) Jout[16 * b + k] = 0;
+      }
+    }
+    return;
+  }
+  const HslLimb& L = M.limb[role];
+  double Rp[9], tp[3], Rb[9], tb[3];
+#pragma unroll
+  for (int k = 0; k < 9; k++) Rp[k] = R0[k];
+  m3_affine(R0, L.oatt, t0, tp);
+  for (int h = 0; h < 3; h++) {
+    double sn, cs, jpos[3], axis[3], com[3], ust[3], Rj[9];
+    sincos(q[6 + 3 * role + h], &sn, &cs);
+    m3_mul(Rp, L.h[h].Rjp, Rj);  // joint frame: parent frame times modeljoint::A_parent (model.cpp:64-66)
+    hinge_fk(L.h[h], cs, sn, Rp, tp, Rb, tb, jpos, axis, com, ust);
+    if (Aout) hsl_put_affine(Aout + 16 * L.h[h].body, Rb, tb);
+    if (Jout) hsl_put_affine(Jout + 16 * L.h[h].body, Rj, jpos);
+#pragma unroll
+    for (int k = 0; k < 9; k++) Rp[k] = Rb[k];
+#pragma unroll
+    for (int k = 0; k < 3; k++) tp[k] = tb[k];
+  }
+}
+
 // periodicgenerator::set_step_duration / compute_max_radius (pergen.cpp:30-51,144-154),
 // periodic::record_trajectory time base (periodic.cpp:84-91).  p = 13 candidate scalars (include/hsl.h).
 HSL_HD void setup_candidate(const HslModelPod& M, const double* p, int n_t, HslCand& cd, double* ttab) {

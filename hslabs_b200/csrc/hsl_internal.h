@@ -9,6 +9,7 @@ cudaError_t hsl_launch_frames(const HslModelPod& M, const HslFrameArgs& A, int m
 cudaError_t hsl_launch_forces(const HslModelPod& M, const HslFrameArgs& A, int mode, cudaStream_t st);
 cudaError_t hsl_launch_gait_records(const HslModelPod& M, const HslFrameArgs& A, int n_times, const double* times, double* rec,
                                     cudaStream_t st);
+cudaError_t hsl_launch_fk_records(const HslModelPod& M, int64_t n, const double* q, double* Aout, double* Jout, cudaStream_t st);
 cudaError_t hsl_launch_ik_records(const HslModelPod& M, int64_t n, int flags, const double* rec, double* q, int32_t* status,
                                   cudaStream_t st);
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,

@@ -353,6 +353,17 @@ __global__ void hsl_ik_records_kernel(const __grid_constant__ HslModelPod M, int
   if (!ik_record(M, role, rec + r * rl, (flags & HSL_FLAG_IGNORE_REACH) != 0, q + r * M.config_dim)) atomicOr(&status[r], HSL_ST_UNREACHABLE);
 }
 
+// A [n][nb][16], J [n][nb][16] for joint values q [n][config_dim]      (kinematicmodel::set_jvalues + recompute_modelnodes)
+__global__ void hsl_fk_records_kernel(const __grid_constant__ HslModelPod M, int64_t n, const double* __restrict__ q,
+                                      double* __restrict__ Aout, double* __restrict__ Jout) {
+  const int roles = M.nf + 1;
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t r = g / roles;
+  if (r >= n) return;
+  const int role = (int)(g - r * roles);
+  fk_record(M, role, q + r * M.config_dim, Aout ? Aout + r * M.n * 16 : nullptr, Jout ? Jout + r * M.n * 16 : nullptr);
+}
+
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
                                  HslCand* __restrict__ cand, double* __restrict__ ttab, int32_t* __restrict__ status) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -673,6 +684,11 @@ cudaError_t hsl_launch_forces(const HslModelPod& M, const HslFrameArgs& A, int m
   return cudaErrorInvalidValue;
 }
 
+cudaError_t hsl_launch_fk_records(const HslModelPod& M, int64_t n, const double* q, double* Aout, double* Jout, cudaStream_t st) {
+  const int64_t threads = n * (M.nf + 1);
+  hsl_fk_records_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(M, n, q, Aout, Jout);
+  return cudaGetLastError();
+}
 cudaError_t hsl_launch_gait_records(const HslModelPod& M, const HslFrameArgs& A, int n_times, const double* times, double* rec,
                                     cudaStream_t st) {
   const int64_t threads = A.n_cand * n_times * (M.nf + 1);

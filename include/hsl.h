@@ -52,6 +52,12 @@ void hsl_model_free(HslModel* m);
 /* dims[6] = n bodies, nf feet, nmj motor joints, config_dim, trunk bodies, lik index (0 myant,1 hexapod,2 spider) */
 int hsl_model_dims(const HslModel* m, int32_t dims[6]);
 double hsl_model_rcap(const HslModel* m); /* liksolver::get_rcap (lik.h:51) */
+/* What periodic::set_dynparts / dynpart::setup hand out (periodic.cpp:34-58, dynrec.cpp:5-16, periodic.h:44-48): parent
+ * ids [n] (-1 for the torso), foot body ids [nf] and limb top-link body ids [nf] in LIK order, masses [n], COM offset of
+ * every body in its body frame [n][3] (odepart::A_body_geom translation), foot point in the foot body's frame [nf][3]
+ * (odepart::capsule_to_pos).  Any pointer may be NULL. */
+int hsl_model_tables(const HslModel* m, int32_t* parent, int32_t* footis, int32_t* limb_top, double* masses, double* com_offset,
+                     double* foot_offset);
 /* packed model block (HslModelPod of hslabs_b200/csrc/hsl_model.h); returns its size, copies min(size,cap) bytes */
 size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap);
 const char* hsl_last_error(void);
@@ -93,6 +99,23 @@ int hsl_solve_frames_host(HslModel* m, int64_t n_frames, const double* pos, cons
                           const double* mom_rate, const double* ang_mom_rate, const double* fpos, const uint8_t* contacts,
                           double* x, double* z, double* tau, int32_t* status);
 
+/* Device-pointer forms of the two per-frame entries (L2 and L1), for callers whose dynrecords /
+ * trajectories already live in HBM: same layouts as the *_host forms below / above, every pointer a DEVICE pointer, work
+ * queued on `stream` (no synchronisation; outputs may be NULL).  status is zeroed by the call. */
+int hsl_eval_trajectories(HslModel* m, int64_t n_cand, int n_t, const double* d_traj, const double* d_dt, double* d_work,
+                          double* d_min_cfz, double* d_max_mu, int32_t* d_status, double* d_x, double* d_z, double* d_tau,
+                          void* stream);
+int hsl_solve_frames(HslModel* m, int64_t n_frames, const double* d_pos, const double* d_jpos, const double* d_jzaxis,
+                     const double* d_mom_rate, const double* d_ang_mom_rate, const double* d_fpos, const uint8_t* d_contacts,
+                     double* d_x, double* d_z, double* d_tau, int32_t* d_status, void* stream);
+
+/* kinematicmodel::set_jvalues + recompute_modelnodes + get_mnode(i)->get_A_ground() / get_joint()->get_A_ground()
+ * (model.cpp:183-201,314-318,362-366; what liksolver::get_limb_hip_pos and kinematicmodel::orient_torso read):
+ * joint values q [n][config_dim] -> A_ground [n][bodies][16], J_A_ground [n][bodies][16], column-major 4x4 like the
+ * reference's `affine` (matrix.cpp:138-146); joint frames of bodies without a joint are zero.  HOST pointers, either
+ * output may be NULL. */
+int hsl_fk_records_host(HslModel* m, int64_t n, const double* q, double* A_ground, double* J_A_ground);
+
 /* pergensetup::set_rec (pergen.cpp:225-239): frame records rec [n_cand][n_times][6+3nf] (torso position, Euler angles,
  * foot targets in LIK order) of the candidates params [n_cand][13] at the times [n_times]; honours
  * hsl_set_rec_transform.  status [n_cand] (HSL_ST_BAD_PARAMS).  HOST pointers. */
@@ -120,6 +143,20 @@ int hsl_solve_forces_gait_host(HslModel* m, int64_t n_cand, int n_t, const doubl
  * hsl_eval_gaits* calls on this handle -- the reference copies one rec_transform to every candidate of a sweep
  * (pergen.cpp:446).  eas = (phi, theta, psi); either pointer may be NULL (= zero); both NULL switches it off. */
 int hsl_set_rec_transform(HslModel* m, const double* transl /*[3]*/, const double* eas /*[3]*/);
+
+/* Multi-GPU: candidates shard over one process per GPU and never span GPUs; the path's one collective is
+ * the all-gather of the per-candidate costs before selection.  d_local [n_per_rank] -> d_all [nranks][n_per_rank] on
+ * every rank, DEVICE pointers, queued on `stream`; nccl_comm is an ncclComm_t (any communicator of the process: the
+ * host's own, or one made with the two helpers below from an id that rank 0 creates and hands to the other ranks by
+ * whatever means the launcher has).  NCCL is bound at run time; HSL_ERR_UNSUPPORTED when the process has none. */
+typedef struct HslNcclId { char internal[128]; } HslNcclId; /* ncclUniqueId */
+int hsl_nccl_unique_id(HslNcclId* id);
+int hsl_nccl_comm_init(void** nccl_comm, int nranks, const HslNcclId* id, int rank);
+int hsl_nccl_comm_destroy(void* nccl_comm);
+int hsl_allgather_costs(void* nccl_comm, const double* d_local, int64_t n_per_rank, double* d_all, void* stream);
+/* same with HOST arrays (staged through the device, synchronous): for hosts that keep no device memory of their own,
+ * e.g. the C++ mirror's sharded measure_cot_sweep. */
+int hsl_allgather_costs_host(void* nccl_comm, int nranks, const double* local, int64_t n_per_rank, double* all);
 
 /* Page-locked host memory for input / output arrays of the *_host entries (they copy straight from / into the caller's
  * buffers; pageable memory works too, at the driver's staged-copy rate).  NULL on failure. */

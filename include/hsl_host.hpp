@@ -9,6 +9,7 @@
 // Evaluation is lazy: periodic::record_trajectory only records the candidate; the GPU is invoked once by the first
 // call that needs results (work_over_period, compute_torques_over_period, solve_torques_contforces, ...).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -82,11 +83,129 @@ class kinematicmodel {
     if (status & HSL_ST_UNREACHABLE) throw error("LIK ERROR: limb position is unreachable");  // lik.cpp:161-164
   }
   void set_jvalues(const double* values) { jvalues_.assign(values, values + dims_[3]); }
-  void get_jvalues(double* values) const { for (size_t i = 0; i < jvalues_.size(); i++) values[i] = jvalues_[i]; }
+  void get_jvalues(double* values) const {
+    for (int i = 0; i < dims_[3]; i++) values[i] = (i < (int)jvalues_.size()) ? jvalues_[i] : 0.0;
+  }
   void set_ignore_reach_flag(bool v) { ignore_reach_ = v; }  // liksolver::set_ignore_reach_flag, lik.cpp:142-146
+  bool get_ignore_reach_flag() const { return ignore_reach_; }
+  // model.cpp:314-318: FK of the current joint values (one GPU launch); the frames are then read with get_A_ground /
+  // get_joint_A_ground (modelnode::get_A_ground, modeljoint::get_A_ground: column-major 4x4 like `affine`)
+  void recompute_modelnodes() {
+    if ((int)jvalues_.size() != dims_[3]) jvalues_.assign(dims_[3], 0.0);
+    A_.assign((size_t)16 * dims_[0], 0.0);
+    J_.assign((size_t)16 * dims_[0], 0.0);
+    check(hsl_fk_records_host(h_, 1, jvalues_.data(), A_.data(), J_.data()));
+  }
+  // model.cpp:403-409: new torso position / Euler angles, then FK
+  void orient_torso(const double orientation[2][3]) {
+    if ((int)jvalues_.size() != dims_[3]) jvalues_.assign(dims_[3], 0.0);
+    for (int i = 0; i < 2; i++) for (int j = 0; j < 3; j++) jvalues_[j + 3 * i] = orientation[i][j];
+    recompute_modelnodes();
+  }
+  const double* get_A_ground(int body) const { need_frames(); return &A_[(size_t)16 * body]; }        // get_mnode(i)->get_A_ground()
+  const double* get_joint_A_ground(int body) const { need_frames(); return &J_[(size_t)16 * body]; }  // ...->get_joint()->get_A_ground()
+  // periodic::set_dynparts tables (periodic.cpp:34-58)
+  struct tables_t {
+    std::vector<int32_t> parent, footis, limb_top;
+    std::vector<double> masses, com_offset, foot_offset;
+  };
+  const tables_t& tables() const {
+    if (tab_.parent.empty()) {
+      tab_.parent.resize(dims_[0]); tab_.footis.resize(dims_[1]); tab_.limb_top.resize(dims_[1]); tab_.masses.resize(dims_[0]);
+      tab_.com_offset.resize((size_t)3 * dims_[0]); tab_.foot_offset.resize((size_t)3 * dims_[1]);
+      check(hsl_model_tables(h_, tab_.parent.data(), tab_.footis.data(), tab_.limb_top.data(), tab_.masses.data(),
+                             tab_.com_offset.data(), tab_.foot_offset.data()));
+    }
+    return tab_;
+  }
+  // y = A_ground(body) * [v; 1]
+  void to_ground(int body, const double* v, double* y) const {
+    const double* A = get_A_ground(body);
+    for (int i = 0; i < 3; i++) y[i] = A[i] * v[0] + A[4 + i] * v[1] + A[8 + i] * v[2] + A[12 + i];
+  }
  private:
-  std::vector<double> jvalues_;
+  void need_frames() const { if (A_.empty()) throw error("ERROR: recompute_modelnodes() has not been called"); }
+  std::vector<double> jvalues_, A_, J_;
+  mutable tables_t tab_;
   bool ignore_reach_ = false;
+  friend class liksolver;
+};
+
+// liksolver (lik.h:40-56): limb inverse kinematics on the model's current configuration.  Each call is one small GPU
+// launch; batches of records go through hsl_ik_records_host / hsl_gait_records_host directly.
+class liksolver {
+  kinematicmodel* model_;
+ public:
+  explicit liksolver(kinematicmodel* model) : model_(model) {}
+  int get_number_of_limbs() const { return model_->number_of_limbs(); }
+  double get_rcap() const { return model_->get_rcap(); }
+  void set_ignore_reach_flag(bool value) const { model_->set_ignore_reach_flag(value); }
+  // lik.cpp:89-99: rec holds the ground positions of all feet (the part of a record after the six torso values);
+  // the torso stays where the model's joint values put it
+  void place_limbs(const double* rec) const {
+    const int nf = model_->number_of_limbs();
+    std::vector<double> full(6 + 3 * nf);
+    torso_values(full.data());
+    for (int i = 0; i < 3 * nf; i++) full[6 + i] = rec[i];
+    model_->set_jvalues_with_lik(full.data());
+  }
+  // lik.cpp:82-85: one limb; the other limbs keep their joint values
+  void place_limb(int limbi, double x, double y, double z) const {
+    const int nf = model_->number_of_limbs(), cd = model_->get_config_dim();
+    std::vector<double> keep(cd), full(6 + 3 * nf);
+    model_->get_jvalues(keep.data());
+    model_->recompute_modelnodes();
+    torso_values(full.data());
+    const kinematicmodel::tables_t& t = model_->tables();
+    for (int l = 0; l < nf; l++) model_->to_ground(t.footis[l], &t.foot_offset[3 * l], &full[6 + 3 * l]);  // current foot points: reachable
+    full[6 + 3 * limbi] = x; full[7 + 3 * limbi] = y; full[8 + 3 * limbi] = z;
+    model_->set_jvalues_with_lik(full.data());
+    std::vector<double> q(cd);
+    model_->get_jvalues(q.data());
+    for (int k = 0; k < 3; k++) keep[6 + 3 * limbi + k] = q[6 + 3 * limbi + k];
+    model_->set_jvalues(keep.data());
+  }
+  // lik.cpp:104-106: body position of the limb's top link (coincides with the hip joint in the reference models)
+  void get_limb_hip_pos(int limbi, double pos[3]) const {
+    model_->recompute_modelnodes();
+    const double* A = model_->get_A_ground(model_->tables().limb_top[limbi]);
+    for (int k = 0; k < 3; k++) pos[k] = A[12 + k];
+  }
+ private:
+  void torso_values(double* six) const {
+    std::vector<double> q(model_->get_config_dim());
+    model_->get_jvalues(q.data());
+    for (int k = 0; k < 6; k++) six[k] = q[k];
+  }
+};
+
+// dynpart (dynrec.h:29-72): static properties and current positions of one body; positions follow the model's last
+// recompute_modelnodes() (dynpart::recompute, dynrec.cpp:47-51)
+class dynpart {
+  const kinematicmodel* model_;
+  int id_;
+ public:
+  dynpart(const kinematicmodel* model, int id) : model_(model), id_(id) {}
+  int get_id() const { return id_; }
+  int get_parent_id() const { return model_->tables().parent[id_]; }
+  double get_mass() const { return model_->tables().masses[id_]; }
+  bool if_foot() const { for (int f : model_->tables().footis) if (f == id_) return true; return false; }
+  void get_com_pos(double pos[3]) const { model_->to_ground(id_, &model_->tables().com_offset[3 * id_], pos); }  // odepart::get_com_pos
+  void get_joint_pos(double pos[3]) const {  // dynrec.cpp:31-39: joint frame origin, or the body origin without a joint
+    const double* J = model_->get_joint_A_ground(id_);
+    const double* A = (J[15] != 0) ? J : model_->get_A_ground(id_);
+    for (int k = 0; k < 3; k++) pos[k] = A[12 + k];
+  }
+  void get_foot_pos(double pos[3]) const {   // odepart::get_foot_pos
+    const kinematicmodel::tables_t& t = model_->tables();
+    for (size_t l = 0; l < t.footis.size(); l++) if (t.footis[l] == id_) { model_->to_ground(id_, &t.foot_offset[3 * l], pos); return; }
+    throw error("dynpart::get_foot_pos: not a foot");
+  }
+  void get_joint_zaxis(double axis[3]) const {  // dynrec.cpp:84-93
+    const double* J = model_->get_joint_A_ground(id_);
+    for (int k = 0; k < 3; k++) axis[k] = (J[15] != 0) ? J[8 + k] : 0.0;
+  }
+  const double* get_A_ground() const { return model_->get_A_ground(id_); }
 };
 
 // periodicgenerator accessors used by callers (pergen.h:38-41)
@@ -281,12 +400,17 @@ class periodic {
   int get_nt() const { return n_t_; }
   int get_nfeet() const { return nf_; }
   int get_number_of_dynparts() const { return n_; }
+  // periodic.h:44-48: what forcetorquesolver and callers read from periodic
+  dynpart get_dynpart(int i) const { return dynpart(model_, i); }
+  const int32_t* get_parentis() const { return model_->tables().parent.data(); }
+  const int32_t* get_footis() const { return model_->tables().footis.data(); }
+  const double* get_masses() const { return model_->tables().masses.data(); }
   void set_ignore_reach_flag(bool v) { flags_ = v ? HSL_FLAG_IGNORE_REACH : 0; have_ = false; }
   void record_trajectory(const pergensetup* pgs, int n_t) { pcp_ = pgs->params(); rec_ = pgs->rec_transform(); n_t_ = n_t; have_ = false; }
   void compute_dynrecs() {}
   void compute_dynrec_ders() {}
   void switch_torso_penalty(bool force, bool torque) { pen_force_ = force; pen_torque_ = torque; }
-  double get_total_mass() const { return (double)n_; }  // unit masses (dynrec.cpp:62-68)
+  double get_total_mass() const { double s = 0; for (double m : model_->tables().masses) s += m; return s; }  // periodic.cpp:320-325
   void compute_torques_over_period() { evaluate(); }
   double work_over_period() { evaluate(); return work_; }
   double cost_of_transport() { evaluate(); return cot_; }
@@ -344,13 +468,23 @@ inline void save_2d_array(double** array, int n, int m, const std::string& fname
 }
 
 // modelplayer: the evaluation entry points (player.cpp:147-208, 230-285, 311-321, 619-655)
+// One process per GPU: rank / world and the NCCL communicator the costs are all-gathered over (hsl_nccl_comm_init or
+// the host application's own ncclComm_t).  world == 1: single GPU, no collective.
+struct shard {
+  int rank, world;
+  void* nccl_comm;
+  shard() : rank(0), world(1), nccl_comm(nullptr) {}
+};
+
 class modelplayer {
   kinematicmodel model_;
   bool contact_force_flag_;
   double play_dt_;
   int flags_;
+  shard shard_;
  public:
   modelplayer() : contact_force_flag_(false), play_dt_(.01), flags_(0) {}
+  void set_shard(const shard& s) { shard_ = s; }
   kinematicmodel* get_model() { return &model_; }
   void set_play_dt(double dt) { play_dt_ = dt; }
   void set_flag(const std::string& name, bool value) { if (name == "contact_force") contact_force_flag_ = value; }
@@ -430,10 +564,25 @@ class modelplayer {
       vals.push_back(sweeper.get_val());
     }
     std::vector<double> cot(vals.size());
-    std::vector<int32_t> status(vals.size());
     pgs->rec_transform().apply(model_.handle());
-    check(hsl_eval_gaits_host(model_.handle(), (int64_t)vals.size(), n_t, rows.data(), flags_, cot.data(), nullptr, nullptr, nullptr, status.data()));
-    for (size_t i = 0; i < vals.size(); i++) std::cout << "val = " << vals[i] << " COT = " << cot[i] << std::endl;
+    if (shard_.world <= 1) {
+      std::vector<int32_t> status(vals.size());
+      check(hsl_eval_gaits_host(model_.handle(), (int64_t)vals.size(), n_t, rows.data(), flags_, cot.data(), nullptr, nullptr, nullptr, status.data()));
+    } else {
+      // candidates shard over the ranks in contiguous blocks of ceil(C/G) (never across GPUs); the costs are all-gathered
+      // over NCCL so that every rank holds the whole sweep
+      const int64_t c = (int64_t)vals.size(), per = (c + shard_.world - 1) / shard_.world;
+      const int64_t lo = std::min<int64_t>(shard_.rank * per, c), hi = std::min<int64_t>(lo + per, c);
+      std::vector<double> local(per, std::nan("")), all((size_t)per * shard_.world);
+      if (hi > lo) {
+        std::vector<int32_t> status(hi - lo);
+        check(hsl_eval_gaits_host(model_.handle(), hi - lo, n_t, &rows[(size_t)lo * HSL_NPARAM], flags_, local.data(), nullptr, nullptr, nullptr, status.data()));
+      }
+      check(hsl_allgather_costs_host(shard_.nccl_comm, shard_.world, local.data(), per, all.data()));
+      for (int64_t i = 0; i < c; i++) cot[i] = all[i];  // rank r's block starts at r*per: contiguous for all but the padding
+    }
+    if (shard_.rank == 0)
+      for (size_t i = 0; i < vals.size(); i++) std::cout << "val = " << vals[i] << " COT = " << cot[i] << std::endl;
     if (vals_out) *vals_out = vals;
     if (cots_out) *cots_out = cot;
   }

@@ -3,6 +3,7 @@
 // test_dynamics (playerexperim.cpp:95-121).  Output is parsed by tests/test_gpu_host_mirror.py.
 #include <cstdio>
 #include <cstdlib>
+#include <ctime>
 
 #include "hsl_host.hpp"
 
@@ -61,6 +62,77 @@ int main(int argc, char** argv) {
     std::printf("rotated sweep:");
     for (size_t i = 0; i < cots.size(); i++) std::printf(" %.17g", cots[i]);
     std::printf("\n");
+    // liksolver / kinematicmodel::orient_torso / dynpart seams (lik.h:46-56, model.h:122-130, dynrec.h:29-72), the way
+    // pgssweeper::partial_setup_pergen uses them (pergen.cpp:454-467): orient the torso, read the hip positions
+    {
+      hsl::kinematicmodel* km = player0.get_model();
+      hsl::liksolver lik(km);
+      hsl::pgsconfigparams pcp;
+      pgs->get_config_params(&pcp);
+      km->orient_torso(pcp.orientation);
+      std::printf("rcap = %.17g nlimbs = %d\n", lik.get_rcap(), lik.get_number_of_limbs());
+      std::printf("hips:");
+      for (int l = 0; l < nf; l++) { double h[3]; lik.get_limb_hip_pos(l, h); std::printf(" %.17g %.17g %.17g", h[0], h[1], h[2]); }
+      std::printf("\n");
+      std::vector<double> rec(6 + 3 * nf), q(km->get_config_dim());
+      pgs->set_rec(rec.data(), 0.4);
+      double six[2][3] = {{rec[0], rec[1], rec[2]}, {rec[3], rec[4], rec[5]}};
+      km->orient_torso(six);
+      lik.place_limbs(rec.data() + 6);
+      km->get_jvalues(q.data());
+      std::printf("place_limbs:");
+      for (size_t i = 0; i < q.size(); i++) std::printf(" %.17g", q[i]);
+      std::printf("\n");
+      lik.place_limb(1, rec[9] + 0.05, rec[10], rec[11] + 0.03);  // move one foot, the others keep their joint values
+      km->get_jvalues(q.data());
+      std::printf("place_limb:");
+      for (size_t i = 0; i < q.size(); i++) std::printf(" %.17g", q[i]);
+      std::printf("\n");
+      km->recompute_modelnodes();
+      hsl::periodic per2(km);
+      std::printf("dynparts:");
+      for (int i = 0; i < per2.get_number_of_dynparts(); i++) {
+        hsl::dynpart dp = per2.get_dynpart(i);
+        double c[3], j[3], a[3];
+        dp.get_com_pos(c); dp.get_joint_pos(j); dp.get_joint_zaxis(a);
+        std::printf(" %d %d %g %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g", dp.get_id(), dp.get_parent_id(), dp.get_mass(),
+                    (int)dp.if_foot(), c[0], c[1], c[2], j[0], j[1], j[2], a[0], a[1], a[2]);
+      }
+      std::printf("\nfeet:");
+      for (int l = 0; l < nf; l++) { double f[3]; per2.get_dynpart(per2.get_footis()[l]).get_foot_pos(f); std::printf(" %.17g %.17g %.17g", f[0], f[1], f[2]); }
+      std::printf("\ntotal mass = %g\n", per2.get_total_mass());
+    }
+    // sharded sweep: one process per GPU, costs all-gathered through the C ABI's NCCL entries.
+    // HSL_RANK / HSL_WORLD / HSL_NCCL_ID_FILE come from the launcher (tests/test_gpu_multirank.py).
+    if (const char* w = std::getenv("HSL_WORLD")) {
+      hsl::shard sh;
+      sh.world = std::atoi(w);
+      sh.rank = std::atoi(std::getenv("HSL_RANK"));
+      const std::string idf = std::getenv("HSL_NCCL_ID_FILE");
+      HslNcclId id;
+      if (sh.rank == 0) {
+        hsl::check(hsl_nccl_unique_id(&id));
+        FILE* f = std::fopen((idf + ".tmp").c_str(), "wb");
+        std::fwrite(&id, sizeof id, 1, f);
+        std::fclose(f);
+        std::rename((idf + ".tmp").c_str(), idf.c_str());
+      } else {
+        FILE* f = nullptr;
+        for (int tries = 0; tries < 600 && !(f = std::fopen(idf.c_str(), "rb")); tries++) { struct timespec ts = {0, 100000000}; nanosleep(&ts, nullptr); }
+        if (!f || std::fread(&id, sizeof id, 1, f) != 1) throw hsl::error("no NCCL id from rank 0");
+        std::fclose(f);
+      }
+      hsl::check(hsl_nccl_comm_init(&sh.nccl_comm, sh.world, &id, sh.rank));
+      player0.set_shard(sh);
+      const double zero[3] = {0, 0, 0};
+      pgs->set_rec_rotation(zero);
+      std::vector<double> v2, c2;
+      player0.measure_cot_sweep(pgs, 20, "period", 3, 18, 15, &v2, &c2);
+      std::printf("sharded sweep rank %d:", sh.rank);
+      for (size_t i = 0; i < c2.size(); i++) std::printf(" %.17g", c2[i]);
+      std::printf("\n");
+      hsl::check(hsl_nccl_comm_destroy(sh.nccl_comm));
+    }
     delete pgs;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "%s\n", e.what());

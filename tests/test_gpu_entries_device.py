@@ -1,0 +1,91 @@
+"""GPU tier: the device-pointer forms of the per-frame entries (hsl_solve_frames, hsl_eval_trajectories: SURVEY.md 8b L1 / L2
+with a stream) and the FK record entry (hsl_fk_records_host), against the oracle and the host-buffer forms."""
+import numpy as np
+import pytest
+
+from conftest import PRESETS, model_xml, ref_xml, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("pid", [8, 9, 24])
+def test_frame_solve_on_device_pointers(hsl, orc, pid):
+    import torch
+    params, name = orc.load_preset(PRESETS, pid)
+    om = orc.Model(model_xml(name))
+    n_t = 24
+    f = om.frame_fields(params, n_t)
+    ref = om.measure_cot(params, n_t, detail=True)
+    m = hsl.Model(model_xml(name))
+    dev = torch.device("cuda")
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in f.items()}
+    x = torch.empty((n_t, 6 * m.n), dtype=torch.float64, device=dev)
+    z = torch.empty((n_t, 3 * m.nf), dtype=torch.float64, device=dev)
+    tau = torch.empty((n_t, m.nmj), dtype=torch.float64, device=dev)
+    st = torch.full((n_t,), 7, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    m.solve_frames_device(n_t, d["pos"].data_ptr(), d["jpos"].data_ptr(), d["jzaxis"].data_ptr(), d["mom_rate"].data_ptr(),
+                          d["ang_mom_rate"].data_ptr(), d["fpos"].data_ptr(), d["contacts"].data_ptr(), x.data_ptr(), z.data_ptr(),
+                          tau.data_ptr(), st.data_ptr(), s.cuda_stream)
+    s.synchronize()
+    assert (st.cpu().numpy() == 0).all()
+    assert rel_err(x.cpu().numpy(), ref["x"]) < TOL and rel_err(z.cpu().numpy(), ref["z"]) < TOL and rel_err(tau.cpu().numpy(), ref["tau"]) < TOL
+    host = m.solve_frames(f["pos"], f["jpos"], f["jzaxis"], f["mom_rate"], f["ang_mom_rate"], f["fpos"], f["contacts"])
+    assert np.array_equal(host["x"], x.cpu().numpy()) and np.array_equal(host["tau"], tau.cpu().numpy())
+
+
+@pytest.mark.parametrize("pid", [8, 1])
+def test_trajectory_entry_on_device_pointers(hsl, orc, pid):
+    import torch
+    params, name = orc.load_preset(PRESETS, pid)
+    om = orc.Model(model_xml(name))
+    n_t, c = 20, 3
+    ps = np.tile(params, (c, 1)); ps[1, 8] *= 0.8; ps[2, 7] *= 1.3
+    refs = [om.measure_cot(p, n_t, detail=True) for p in ps]
+    traj = np.stack([r["traj"] for r in refs])
+    dt = ps[:, 7] / n_t
+    m = hsl.Model(model_xml(name))
+    dev = torch.device("cuda")
+    d_traj, d_dt = torch.from_numpy(traj).to(dev), torch.from_numpy(dt).to(dev)
+    work = torch.empty(c, dtype=torch.float64, device=dev); mn = torch.empty_like(work); mx = torch.empty_like(work)
+    st = torch.empty(c, dtype=torch.int32, device=dev)
+    x = torch.empty((c, n_t, 6 * m.n), dtype=torch.float64, device=dev)
+    z = torch.empty((c, n_t, 3 * m.nf), dtype=torch.float64, device=dev)
+    tau = torch.empty((c, n_t, m.nmj), dtype=torch.float64, device=dev)
+    m.eval_trajectories_device(c, n_t, d_traj.data_ptr(), d_dt.data_ptr(), work.data_ptr(), mn.data_ptr(), mx.data_ptr(), st.data_ptr(),
+                               x.data_ptr(), z.data_ptr(), tau.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (st.cpu().numpy() == 0).all()
+    for i, r in enumerate(refs):
+        assert rel_err(x[i].cpu().numpy(), r["x"]) < TOL and rel_err(z[i].cpu().numpy(), r["z"]) < TOL and rel_err(tau[i].cpu().numpy(), r["tau"]) < TOL
+        assert abs(work[i].item() - r["work"]) <= TOL * abs(r["work"])
+    # costs only: no per-frame dump requested
+    work2 = torch.empty(c, dtype=torch.float64, device=dev)
+    m.eval_trajectories_device(c, n_t, d_traj.data_ptr(), d_dt.data_ptr(), work2.data_ptr(), 0, 0, 0, 0, 0, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(work, work2)
+
+
+@pytest.mark.parametrize("name", ["myant", "hexapod", "spider"])
+def test_fk_records(hsl, orc, refb, name):
+    """kinematicmodel::set_jvalues + recompute_modelnodes: body and joint frames against the oracle and the reference build."""
+    om, rm = orc.Model(model_xml(name)), refb.Model(ref_xml(name))
+    m = hsl.Model(model_xml(name))
+    rng = np.random.default_rng(4)
+    q = rng.uniform(-1.2, 1.2, (7, m.config_dim))
+    got = m.fk_records(q)
+    jointed = om.constants()["jkind"] != 0
+    for i in range(q.shape[0]):
+        for src in (om, rm):
+            A, J = src.fk(q[i])
+            assert np.abs(got["A_ground"][i] - A).max() < 1e-13
+            assert np.abs(got["J_A_ground"][i][jointed] - J[jointed]).max() < 1e-13
+        assert np.abs(got["J_A_ground"][i][~jointed]).max() == 0
+    t = m.tables()
+    cons = om.constants()
+    assert np.array_equal(t["parent"], cons["parent"]) and np.array_equal(t["footis"], cons["limb_foot"]) and np.array_equal(t["limb_top"], cons["limb_top"])
+    assert (t["masses"] == 1).all()
+    assert np.array_equal(t["com_offset"], cons["A_body_geom"][:, 12:15])
+    assert np.array_equal(t["foot_offset"], cons["capsule_to_pos"][cons["limb_foot"]])

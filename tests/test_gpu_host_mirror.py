@@ -82,3 +82,40 @@ def test_main_like_sequence(demo, orc, pid, tmp_path):
         d = np.where(d > np.pi, d - 2 * np.pi, np.where(d < -np.pi, d + 2 * np.pi, d))
         assert np.allclose(rows[tsi, cd:2 * cd], d / (2 * dt), rtol=2e-5, atol=2e-6), tsi
         assert np.allclose(rows[tsi, 2 * cd:], ref2["tau"][t2 - 2], rtol=2e-5, atol=2e-6)
+    # liksolver / orient_torso / dynpart seams (lik.h:46-56, model.h:122-130, dynrec.h:29-72)
+    cons = m.constants()
+    q0 = np.zeros(m.config_dim); q0[:6] = params[:6]
+    A0, _ = m.fk(q0)
+    hips = np.array([float(v) for v in re.search(r"^hips:(.*)$", out.stdout, re.M).group(1).split()]).reshape(-1, 3)
+    for l, top in enumerate(cons["limb_top"]):
+        assert np.abs(hips[l] - A0[top][12:15]).max() < 1e-12
+    assert abs(float(re.search(r"rcap = (\S+)", out.stdout).group(1)) - m.rcap) < 1e-15
+    rec4 = m.gait_rec(params, 0.4)
+    rc, q4 = m.ik(rec4)
+    pl = np.array([float(v) for v in re.search(r"^place_limbs:(.*)$", out.stdout, re.M).group(1).split()])
+    d = np.abs(pl - q4); d[6:] = np.minimum(d[6:], np.abs(d[6:] - 2 * np.pi))
+    assert rc == 0 and d.max() < 1e-12
+    rec5 = rec4.copy(); rec5[9] += 0.05; rec5[11] += 0.03
+    rc, q5 = m.ik(rec5)
+    want = q4.copy(); want[9:12] = q5[9:12]                    # only limb 1 moves
+    pl1 = np.array([float(v) for v in re.search(r"^place_limb:(.*)$", out.stdout, re.M).group(1).split()])
+    d = np.abs(pl1 - want); d[6:] = np.minimum(d[6:], np.abs(d[6:] - 2 * np.pi))
+    assert rc == 0 and d.max() < 1e-12
+    A5, J5 = m.fk(want)
+    dp = np.array([float(v) for v in re.search(r"^dynparts:(.*)$", out.stdout, re.M).group(1).split()]).reshape(m.n, 13)
+    assert np.array_equal(dp[:, 0], np.arange(m.n)) and np.array_equal(dp[:, 1], cons["parent"]) and (dp[:, 2] == 1).all()
+    assert np.array_equal(np.flatnonzero(dp[:, 3]), np.sort(cons["limb_foot"]))
+    for i in range(m.n):
+        Ag = A5[i].reshape(4, 4).T
+        com = Ag @ np.append(cons["A_body_geom"][i][12:15], 1.0)
+        assert np.abs(dp[i, 4:7] - com[:3]).max() < 1e-12
+        jointed = cons["jkind"][i] != 0
+        jp = J5[i][12:15] if jointed else A5[i][12:15]
+        assert np.abs(dp[i, 7:10] - jp).max() < 1e-12
+        ax = J5[i][8:11] if jointed else np.zeros(3)
+        assert np.abs(dp[i, 10:13] - ax).max() < 1e-12
+    feet = np.array([float(v) for v in re.search(r"^feet:(.*)$", out.stdout, re.M).group(1).split()]).reshape(-1, 3)
+    for l, fb in enumerate(cons["limb_foot"]):
+        fp = A5[fb].reshape(4, 4).T @ np.append(cons["capsule_to_pos"][fb], 1.0)
+        assert np.abs(feet[l] - fp[:3]).max() < 1e-12
+    assert float(re.search(r"total mass = (\S+)", out.stdout).group(1)) == m.n
