@@ -65,6 +65,8 @@ int main(int argc, char** argv) {
     // liksolver / kinematicmodel::orient_torso / dynpart seams (lik.h:46-56, model.h:122-130, dynrec.h:29-72), the way
     // pgssweeper::partial_setup_pergen uses them (pergen.cpp:454-467): orient the torso, read the hip positions
     {
+      const double no_rot[3] = {0, 0, 0};
+      pgs->set_rec_rotation(no_rot);  // back to the identity map for the records below
       hsl::kinematicmodel* km = player0.get_model();
       hsl::liksolver lik(km);
       hsl::pgsconfigparams pcp;

@@ -82,7 +82,7 @@ def test_fk_records(hsl, orc, refb, name):
             A, J = src.fk(q[i])
             assert np.abs(got["A_ground"][i] - A).max() < 1e-13
             assert np.abs(got["J_A_ground"][i][jointed] - J[jointed]).max() < 1e-13
-        assert np.abs(got["J_A_ground"][i][~jointed]).max() == 0
+        assert not got["J_A_ground"][i][~jointed].any()   # (spider has no jointless body)
     t = m.tables()
     cons = om.constants()
     assert np.array_equal(t["parent"], cons["parent"]) and np.array_equal(t["footis"], cons["limb_foot"]) and np.array_equal(t["limb_top"], cons["limb_top"])
