@@ -341,7 +341,7 @@ int hsl_select_best(const double* d_cost, int64_t n, int64_t* d_index, double* d
 }
 
 int hsl_select_topk(const double* d_cost, int64_t n, int k, int64_t* d_index, double* d_value, void* stream) {
-  if (!d_cost || n < 1 || k < 1 || k > 65536 || (!d_index && !d_value)) return set_err(HSL_ERR_ARG, "bad argument (1 <= k <= 65536)");
+  if (!d_cost || n < 1 || n > 0x7fffffff || k < 1 || k > n || (!d_index && !d_value)) return set_err(HSL_ERR_ARG, "bad argument (1 <= k <= n < 2^31)");
   HSL_CUDA(hsl_launch_topk(d_cost, n, k, d_index, d_value, (cudaStream_t)stream));
   return HSL_OK;
 }

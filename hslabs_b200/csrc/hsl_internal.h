@@ -19,6 +19,7 @@ cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const 
                               double* work, double* min_cfz, double* max_mu, cudaStream_t st);
 cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, double* out, cudaStream_t st);
 cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st);
+int hsl_topk_launches(int64_t n);  // kernels hsl_launch_topk issues for n costs
 cudaError_t hsl_launch_argmin(const double* cost, int64_t n, int64_t* out_index, double* out_value, cudaStream_t st);
 // [comps][nfr] -> [nfr][comps] on the device (elem_size 8: double, 1: uint8_t)
 cudaError_t hsl_launch_transpose(const void* src, void* dst, int comps, int64_t nfr, int elem_size, cudaStream_t st);

@@ -6,7 +6,7 @@
 //                         six-limbed models
 //   hsl_forces_kernel     contact forces of all feet from given motor torques (hsl_forces.h)  (a15)
 //   hsl_finish_kernel     one warp per candidate: work = sum_f (power_f * dt), COT, statistics (a14)
-//   hsl_argmin_kernel     selection after the all-gather of the costs
+//   (selection after the all-gather of the costs: hsl_select.cu)
 //
 // Block layout of hsl_frames_kernel: FB frame slots x (NF+1) roles, thread = role*FB + slot, so a warp
 // is one role over 32 consecutive frames of (normally) one candidate.  Blocks overlap by 4 slots: the
@@ -411,97 +411,7 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
   }
 }
 
-// Selection: index and value of the cheapest valid candidate (NaN = failed candidate, never selected; ties go to
-// the lowest index, as a stable sort of the costs would).  One block; used after the all-gather of the costs.
-__global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, int64_t* __restrict__ out_index, double* __restrict__ out_value) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  double best = __longlong_as_double(0x7ff0000000000000LL);  // +inf
-  long long bi = -1;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-    const double c = cost[i];
-    if (c < best) { best = c; bi = i; }  // NaN compares false; strided scan visits ascending indices per thread
-  }
-  auto better = [](double v, long long i, double bv, long long bidx) { return i >= 0 && (bidx < 0 || v < bv || (v == bv && i < bidx)); };
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
-  }
-  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int nw = (blockDim.x + 31) / 32;
-    best = (threadIdx.x < nw) ? sv[threadIdx.x] : __longlong_as_double(0x7ff0000000000000LL);
-    bi = (threadIdx.x < nw) ? si[threadIdx.x] : -1;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
-    }
-    if (threadIdx.x == 0) {
-      if (out_index) *out_index = bi;
-      if (out_value) *out_value = (bi >= 0) ? best : __longlong_as_double(0x7ff8000000000000LL);
-    }
-  }
-}
-
-// Selection of the k cheapest valid candidates in ascending (cost, index) order -- the order a stable sort of the costs
-// gives, NaN (failed candidates) never selected.  One block; pass j finds the smallest pair that is lexicographically
-// greater than the pair found by pass j-1, so nothing is marked or moved and the result does not depend on the thread
-// count.  k * n reads: meant for the elite sets of a search loop (k up to a few thousand) over the all-gathered costs.
-// Entries past the number of valid candidates get index -1 / value NaN.
-__global__ void hsl_topk_kernel(const double* __restrict__ cost, int64_t n, int k, int64_t* __restrict__ out_index,
-                                double* __restrict__ out_value) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  __shared__ double prev_v;
-  __shared__ long long prev_i;
-  const double inf = __longlong_as_double(0x7ff0000000000000LL), nanv = __longlong_as_double(0x7ff8000000000000LL);
-  auto better = [](double v, long long i, double bv, long long bidx) { return i >= 0 && (bidx < 0 || v < bv || (v == bv && i < bidx)); };
-  if (threadIdx.x == 0) { prev_v = -inf; prev_i = -1; }
-  __syncthreads();
-  for (int j = 0; j < k; j++) {
-    const double pv = prev_v;
-    const long long pi = prev_i;
-    double best = inf;
-    long long bi = -1;
-    if (j == 0 || pi >= 0) {  // once a pass finds nothing, every later pass finds nothing
-      for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
-        const double c = cost[i];
-        const bool after = (j == 0) ? (c == c) : (c > pv || (c == pv && i > pi));  // NaN fails every comparison
-        if (after && (bi < 0 || c < best)) { best = c; bi = i; }              // ascending indices per thread: first hit wins ties
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      const int nw = (blockDim.x + 31) / 32;
-      best = (threadIdx.x < nw) ? sv[threadIdx.x] : inf;
-      bi = (threadIdx.x < nw) ? si[threadIdx.x] : -1;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
-      }
-      if (threadIdx.x == 0) {
-        if (out_index) out_index[j] = bi;
-        if (out_value) out_value[j] = (bi >= 0) ? best : nanv;
-        prev_v = best; prev_i = bi;
-      }
-    }
-    __syncthreads();
-  }
-}
+// Selection (argmin / top-k over the all-gathered costs) lives in hsl_select.cu.
 
 // FP64 FMA throughput probe: register-resident dependent chains, 8 per thread.  Used by bench.py for the
 // roofline denominator of this FP64-bound path (MEASURED_PEAKS.json has no FP64 figure).
@@ -719,10 +629,6 @@ cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const 
   return cudaGetLastError();
 }
 
-cudaError_t hsl_launch_argmin(const double* cost, int64_t n, int64_t* out_index, double* out_value, cudaStream_t st) {
-  hsl_argmin_kernel<<<1, 1024, 0, st>>>(cost, n, out_index, out_value);
-  return cudaGetLastError();
-}
 
 cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, double* out, cudaStream_t st) {
   hsl_math_selftest_kernel<<<(n + 127) / 128, 128, 0, st>>>(n, a, b, out);
@@ -745,7 +651,3 @@ cudaError_t hsl_launch_transpose(const void* src, void* dst, int comps, int64_t 
   return cudaGetLastError();
 }
 
-cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st) {
-  hsl_topk_kernel<<<1, 1024, 0, st>>>(cost, n, k, out_index, out_value);
-  return cudaGetLastError();
-}

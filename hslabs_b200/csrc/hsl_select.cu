@@ -1,0 +1,180 @@
+// Selection over the (all-gathered) per-candidate costs: argmin and the k cheapest candidates.
+//
+// Order everywhere: ascending (cost, index) -- what a stable sort of the costs gives; NaN costs (failed candidates) are
+// never selected.  The costs of a search iteration are small (8 B per candidate: 512 KiB for BASELINE config 3), so the
+// kernels are latency bound, not bandwidth bound:
+//
+//   hsl_argmin_kernel   one block, eight independent loads per thread and iteration (the round-1 kernel issued one
+//                       dependent load per iteration and grew with the number of gathered shards)
+//   top-k               a bitonic sort of (sortable 64-bit image of the cost, index) pairs over all n costs in a
+//                       stream-ordered workspace, then the first k are emitted.  Tiles of 4096 pairs are sorted / merged
+//                       in shared memory; only the compare-exchange steps whose partner lies in another tile are separate
+//                       launches (none for n <= 4096, 10 + 5 for n = 65536).  The round-1 kernel made k passes over n in
+//                       ONE block (2.7e8 loads for the elite 4096 of 65536).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hsl_internal.h"
+
+namespace {
+
+__device__ __forceinline__ bool hsl_better(double v, long long i, double bv, long long bidx) {
+  return i >= 0 && (bidx < 0 || v < bv || (v == bv && i < bidx));
+}
+
+__global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, int64_t* __restrict__ out_index, double* __restrict__ out_value) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  double best = inf;
+  long long bi = -1;
+  constexpr int U = 8;
+  const int64_t stride = (int64_t)blockDim.x * U;
+  for (int64_t base = threadIdx.x; base < n; base += stride) {
+    double c[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const int64_t i = base + (int64_t)u * blockDim.x;
+      c[u] = (i < n) ? cost[i] : inf;   // independent loads: one round trip per U candidates
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      if (c[u] < best) { best = c[u]; bi = base + (int64_t)u * blockDim.x; }  // NaN compares false; ascending indices per thread
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (hsl_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = (blockDim.x + 31) / 32;
+    best = (threadIdx.x < nw) ? sv[threadIdx.x] : inf;
+    bi = (threadIdx.x < nw) ? si[threadIdx.x] : -1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (hsl_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      if (out_index) *out_index = bi;
+      if (out_value) *out_value = (bi >= 0) ? best : __longlong_as_double(0x7ff8000000000000LL);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- bitonic sort of (key, index) pairs
+constexpr int TILE = 4096, SORT_THREADS = 1024;
+constexpr uint64_t KEY_INVALID = ~0ull;
+
+// order-preserving image of a double in an unsigned 64-bit integer; NaN -> KEY_INVALID (sorts last, never emitted)
+__device__ __forceinline__ uint64_t sort_key(double c) {
+  if (c != c) return KEY_INVALID;
+  const uint64_t b = (uint64_t)__double_as_longlong(c);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_value(uint64_t k) {
+  const uint64_t b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__device__ __forceinline__ bool pair_less(uint64_t ka, uint32_t ia, uint64_t kb, uint32_t ib) { return ka < kb || (ka == kb && ia < ib); }
+
+// compare-exchange steps j = j0, j0/2, ..., 1 of stage s on one tile held in shared memory
+__device__ __forceinline__ void tile_steps(uint64_t* sk, uint32_t* si, int64_t tile_base, int64_t s, int j0) {
+  for (int j = j0; j > 0; j >>= 1) {
+    for (int t = threadIdx.x; t < TILE / 2; t += SORT_THREADS) {
+      const int lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+      const bool up = (((tile_base + lo) & s) == 0);
+      const uint64_t ka = sk[lo], kb = sk[hi];
+      const uint32_t ia = si[lo], ib = si[hi];
+      if (pair_less(kb, ib, ka, ia) == up) { sk[lo] = kb; sk[hi] = ka; si[lo] = ib; si[hi] = ia; }
+    }
+    __syncthreads();
+  }
+}
+
+// keys / indices of the padded array [P] from the costs, each tile sorted through stage s = TILE
+__global__ void __launch_bounds__(SORT_THREADS) hsl_sort_tiles_kernel(const double* __restrict__ cost, int64_t n, uint64_t* __restrict__ keys,
+                                                                      uint32_t* __restrict__ idxs) {
+  __shared__ uint64_t sk[TILE];
+  __shared__ uint32_t si[TILE];
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) {
+    const int64_t i = base + t;
+    sk[t] = (i < n) ? sort_key(cost[i]) : KEY_INVALID;
+    si[t] = (i < n) ? (uint32_t)i : 0xffffffffu;
+  }
+  __syncthreads();
+  for (int64_t s = 2; s <= TILE; s <<= 1) tile_steps(sk, si, base, s, (int)(s >> 1));
+  for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) { keys[base + t] = sk[t]; idxs[base + t] = si[t]; }
+}
+// one compare-exchange step (stage s, distance j >= TILE) across tiles
+__global__ void hsl_sort_global_step_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ idxs, int64_t P, int64_t s, int64_t j) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P / 2) return;
+  const int64_t lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+  const bool up = ((lo & s) == 0);
+  const uint64_t ka = keys[lo], kb = keys[hi];
+  const uint32_t ia = idxs[lo], ib = idxs[hi];
+  if (pair_less(kb, ib, ka, ia) == up) { keys[lo] = kb; keys[hi] = ka; idxs[lo] = ib; idxs[hi] = ia; }
+}
+// the remaining steps j = TILE/2 .. 1 of stage s, tile by tile in shared memory
+__global__ void __launch_bounds__(SORT_THREADS) hsl_sort_merge_kernel(uint64_t* __restrict__ keys, uint32_t* __restrict__ idxs, int64_t s) {
+  __shared__ uint64_t sk[TILE];
+  __shared__ uint32_t si[TILE];
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) { sk[t] = keys[base + t]; si[t] = idxs[base + t]; }
+  __syncthreads();
+  tile_steps(sk, si, base, s, TILE / 2);
+  for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) { keys[base + t] = sk[t]; idxs[base + t] = si[t]; }
+}
+__global__ void hsl_topk_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idxs, int k, int64_t* __restrict__ out_index,
+                                     double* __restrict__ out_value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k) return;
+  const uint64_t key = keys[i];
+  const bool ok = key != KEY_INVALID;
+  if (out_index) out_index[i] = ok ? (int64_t)idxs[i] : -1;
+  if (out_value) out_value[i] = ok ? key_value(key) : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+}  // namespace
+
+cudaError_t hsl_launch_argmin(const double* cost, int64_t n, int64_t* out_index, double* out_value, cudaStream_t st) {
+  hsl_argmin_kernel<<<1, 1024, 0, st>>>(cost, n, out_index, out_value);
+  return cudaGetLastError();
+}
+
+cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st) {
+  int64_t P = TILE;
+  while (P < n) P <<= 1;
+  uint64_t* keys = nullptr;
+  cudaError_t e = cudaMallocAsync((void**)&keys, (size_t)P * (sizeof(uint64_t) + sizeof(uint32_t)), st);  // stream-ordered workspace
+  if (e != cudaSuccess) return e;
+  uint32_t* idxs = (uint32_t*)(keys + P);
+  const unsigned tiles = (unsigned)(P / TILE);
+  hsl_sort_tiles_kernel<<<tiles, SORT_THREADS, 0, st>>>(cost, n, keys, idxs);
+  for (int64_t s = 2 * (int64_t)TILE; s <= P; s <<= 1) {
+    for (int64_t j = s >> 1; j >= TILE; j >>= 1)
+      hsl_sort_global_step_kernel<<<(unsigned)((P / 2 + 255) / 256), 256, 0, st>>>(keys, idxs, P, s, j);
+    hsl_sort_merge_kernel<<<tiles, SORT_THREADS, 0, st>>>(keys, idxs, s);
+  }
+  hsl_topk_emit_kernel<<<(k + 255) / 256, 256, 0, st>>>(keys, idxs, k, out_index, out_value);
+  e = cudaGetLastError();
+  const cudaError_t e2 = cudaFreeAsync(keys, st);
+  return e != cudaSuccess ? e : e2;
+}
+
+int hsl_topk_launches(int64_t n) {  // kernels hsl_launch_topk issues for n costs (for the callers' launch counters)
+  int64_t P = TILE;
+  while (P < n) P <<= 1;
+  int c = 2;
+  for (int64_t s = 2 * (int64_t)TILE; s <= P; s <<= 1) {
+    for (int64_t j = s >> 1; j >= TILE; j >>= 1) c++;
+    c++;
+  }
+  return c;
+}

@@ -60,9 +60,11 @@ class DeviceEvaluator:
         return cot[:c], st[:c]
 
 
-def top_k(cot, k):
-    """Indices and costs of the k cheapest candidates in stable ascending order (`hsl_select_topk` on the device).
-    Failed candidates (NaN cost) are never selected: when fewer than k candidates are valid the result is shorter."""
+def top_k(cot, k, trim=True):
+    """Indices and costs of the k cheapest candidates in stable ascending order (`hsl_select_topk` on the device: a
+    multi-block bitonic sort of (cost, index) pairs).  Failed candidates (NaN cost) are never selected: the entries past
+    the number of valid candidates are -1 / NaN.  trim=True cuts them off (one host synchronisation, for interactive
+    use); trim=False returns the padded length-k tensors without touching the host."""
     import torch
     from . import api
     cot = cot.contiguous()
@@ -70,6 +72,8 @@ def top_k(cot, k):
     idx = torch.empty(k, dtype=torch.int64, device=cot.device)
     val = torch.empty(k, dtype=torch.float64, device=cot.device)
     api.select_topk_device(cot.data_ptr(), cot.numel(), k, idx.data_ptr(), val.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    if not trim:
+        return idx, val
     n_ok = int((idx >= 0).sum())
     return idx[:n_ok], val[:n_ok]
 
@@ -96,7 +100,10 @@ def random_search(model, base, ranges, n_cand, n_t, seed=0, k=1, flags=0, device
 
 
 def cem_search(model, base, ranges, n_t, pop=1024, elite=64, iters=8, seed=0, flags=0, device="cuda"):
-    """Cross-entropy method over the named parameters: sample a Gaussian population, evaluate, refit to the elite."""
+    """Cross-entropy method over the named parameters: sample a Gaussian population, evaluate, refit to the elite.
+    The loop never synchronises with the host: population, costs, elite set, the Gaussian's moments and the running best
+    stay on the device (an iteration without a single valid candidate leaves the distribution unchanged); results are
+    read back once at the end."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -107,21 +114,31 @@ def cem_search(model, base, ranges, n_t, pop=1024, elite=64, iters=8, seed=0, fl
     cols = [SWEEP_NAMES[n] for n in names]
     base_t = torch.from_numpy(np.asarray(base, np.float64)).to(device)
     ev = DeviceEvaluator(model, n_t, flags)
-    history, best = [], (float("inf"), None)
+    inf = torch.tensor(float("inf"), dtype=torch.float64, device=device)
+    best_cot = inf.clone()
+    best_cand = torch.full((HSL_NPARAM,), float("nan"), dtype=torch.float64, device=device)
+    history = []
     for _ in range(iters):
         z = torch.randn(pop, len(names), dtype=torch.float64, device=device, generator=g)
         x = torch.minimum(torch.maximum(mean + std * z, lo), hi)
         cand = base_t.repeat(pop, 1)
         cand[:, cols] = x
         cot, st = ev(cand)
-        idx, c = top_k(cot, elite)
-        ok = torch.isfinite(c)
-        if int(ok.sum()) == 0:
-            break
-        el = x[idx][ok]
-        mean, std = el.mean(0), el.std(0, unbiased=False) + 1e-6 * (hi - lo)
-        cbest = float(c[0])
+        idx, c = top_k(cot, elite, trim=False)          # padded with -1 / NaN past the valid candidates
+        w = (idx >= 0).to(torch.float64)                  # elite membership weights
+        cnt = w.sum()
+        el = x[idx.clamp(min=0)]
+        m1 = (w[:, None] * el).sum(0) / cnt.clamp(min=1.0)
+        var = (w[:, None] * (el - m1) ** 2).sum(0) / cnt.clamp(min=1.0)
+        any_ok = cnt > 0
+        mean = torch.where(any_ok, m1, mean)
+        std = torch.where(any_ok, var.sqrt() + 1e-6 * (hi - lo), std)
+        cbest = torch.where(any_ok, c[0], inf)
         history.append(cbest)
-        if cbest < best[0]:
-            best = (cbest, cand[idx[0]].clone())
-    return dict(best_cot=best[0], best_candidate=best[1], history=history, mean=mean, std=std)
+        improved = cbest < best_cot
+        best_cand = torch.where(improved, cand[idx[0].clamp(min=0)], best_cand)
+        best_cot = torch.where(improved, cbest, best_cot)
+    hist = [float(v) for v in torch.stack(history).cpu()] if history else []   # the one read-back
+    hist = [v for v in hist if np.isfinite(v)]
+    bc = float(best_cot)
+    return dict(best_cot=bc, best_candidate=best_cand if np.isfinite(bc) else None, history=hist, mean=mean, std=std)

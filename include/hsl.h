@@ -72,9 +72,10 @@ int hsl_eval_gaits(HslModel* m, int64_t n_cand, int n_t, const double* d_params,
  * candidates) are never selected, ties go to the lowest index; index -1 / value NaN when nothing is valid.
  * DEVICE pointers. */
 int hsl_select_best(const double* d_cost, int64_t n, int64_t* d_index, double* d_value, void* stream);
-/* The k cheapest valid candidates in ascending (cost, index) order (what a stable sort of the costs gives; NaN never
- * selected): d_index [k], d_value [k] (either may be NULL); entries past the number of valid candidates get -1 / NaN.
- * One block, k passes over the costs: meant for elite sets (k <= 65536).  DEVICE pointers. */
+/* The k cheapest valid candidates (1 <= k <= n) in ascending (cost, index) order (what a stable sort of the costs gives;
+ * NaN never selected): d_index [k], d_value [k] (either may be NULL); entries past the number of valid candidates get
+ * -1 / NaN.  A bitonic sort of (cost, index) pairs over all n costs in a stream-ordered workspace (tiles of 4096 sorted in
+ * shared memory); DEVICE pointers, queued on `stream`. */
 int hsl_select_topk(const double* d_cost, int64_t n, int k, int64_t* d_index, double* d_value, void* stream);
 /* same, HOST pointers (pinned staging inside). */
 int hsl_eval_gaits_host(HslModel* m, int64_t n_cand, int n_t, const double* params, int flags, double* cot, double* work,
