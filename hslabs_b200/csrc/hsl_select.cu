@@ -11,6 +11,7 @@
 //                       in shared memory; only the compare-exchange steps whose partner lies in another tile are separate
 //                       launches (none for n <= 4096, 10 + 5 for n = 65536).  The round-1 kernel made k passes over n in
 //                       ONE block (2.7e8 loads for the elite 4096 of 65536).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -131,6 +132,52 @@ __global__ void __launch_bounds__(SORT_THREADS) hsl_sort_merge_kernel(uint64_t* 
   tile_steps(sk, si, base, s, TILE / 2);
   for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) { keys[base + t] = sk[t]; idxs[base + t] = si[t]; }
 }
+// The whole sort and the emission in ONE cooperative launch when every tile can be resident at once (P / TILE <= the
+// number of co-resident blocks: up to 148 tiles = 606 208 costs on a B200): grid-wide barriers replace the ~16 dependent
+// launches of the multi-kernel path, whose launch latencies dominated (168 us -> see profiles/ for top-4096 of 65536).
+__global__ void __launch_bounds__(SORT_THREADS) hsl_topk_coop_kernel(const double* __restrict__ cost, int64_t n, uint64_t* __restrict__ keys,
+                                                                     uint32_t* __restrict__ idxs, int64_t P, int k,
+                                                                     int64_t* __restrict__ out_index, double* __restrict__ out_value) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint64_t sk[TILE];
+  __shared__ uint32_t si[TILE];
+  const int64_t base = (int64_t)blockIdx.x * TILE;
+  for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) {
+    const int64_t i = base + t;
+    sk[t] = (i < n) ? sort_key(cost[i]) : KEY_INVALID;
+    si[t] = (i < n) ? (uint32_t)i : 0xffffffffu;
+  }
+  __syncthreads();
+  for (int64_t s = 2; s <= TILE; s <<= 1) tile_steps(sk, si, base, s, (int)(s >> 1));
+  for (int64_t s = 2 * (int64_t)TILE; s <= P; s <<= 1) {
+    for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) { keys[base + t] = sk[t]; idxs[base + t] = si[t]; }
+    grid.sync();
+    for (int64_t j = s >> 1; j >= TILE; j >>= 1) {
+      // this block's share of the P/2 compare-exchange pairs of the step
+      for (int64_t t = (int64_t)blockIdx.x * (TILE / 2) + threadIdx.x; t < (int64_t)(blockIdx.x + 1) * (TILE / 2); t += SORT_THREADS) {
+        const int64_t lo = ((t / j) * 2 * j) + (t % j), hi = lo + j;
+        const bool up = ((lo & s) == 0);
+        const uint64_t ka = keys[lo], kb = keys[hi];
+        const uint32_t ia = idxs[lo], ib = idxs[hi];
+        if (pair_less(kb, ib, ka, ia) == up) { keys[lo] = kb; keys[hi] = ka; idxs[lo] = ib; idxs[hi] = ia; }
+      }
+      grid.sync();
+    }
+    for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) { sk[t] = keys[base + t]; si[t] = idxs[base + t]; }
+    __syncthreads();
+    tile_steps(sk, si, base, s, TILE / 2);
+  }
+  // emit: the first k pairs of the sorted array live in the first tiles
+  for (int t = threadIdx.x; t < TILE; t += SORT_THREADS) {
+    const int64_t i = base + t;
+    if (i >= k) continue;
+    const bool ok = sk[t] != KEY_INVALID;
+    if (out_index) out_index[i] = ok ? (int64_t)si[t] : -1;
+    if (out_value) out_value[i] = ok ? key_value(sk[t]) : __longlong_as_double(0x7ff8000000000000LL);
+  }
+}
+
 __global__ void hsl_topk_emit_kernel(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ idxs, int k, int64_t* __restrict__ out_index,
                                      double* __restrict__ out_value) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,6 +203,28 @@ cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_i
   if (e != cudaSuccess) return e;
   uint32_t* idxs = (uint32_t*)(keys + P);
   const unsigned tiles = (unsigned)(P / TILE);
+  {
+    static int coop_blocks[64];  // co-resident blocks of the cooperative kernel, per device (0 = not queried yet, -1 = unsupported)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+      if (coop_blocks[dev] == 0) {
+        int coop = 0, sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hsl_topk_coop_kernel, SORT_THREADS, 0);
+        coop_blocks[dev] = (coop && per_sm > 0) ? sms * per_sm : -1;
+      }
+      if (coop_blocks[dev] > 0 && (int)tiles <= coop_blocks[dev]) {
+        int64_t n_ = n, P_ = P;
+        int k_ = k;
+        void* args[] = {(void*)&cost, (void*)&n_, (void*)&keys, (void*)&idxs, (void*)&P_, (void*)&k_, (void*)&out_index, (void*)&out_value};
+        e = cudaLaunchCooperativeKernel((const void*)hsl_topk_coop_kernel, dim3(tiles), dim3(SORT_THREADS), args, 0, st);
+        const cudaError_t ef = cudaFreeAsync(keys, st);
+        return e != cudaSuccess ? e : ef;
+      }
+    }
+  }
   hsl_sort_tiles_kernel<<<tiles, SORT_THREADS, 0, st>>>(cost, n, keys, idxs);
   for (int64_t s = 2 * (int64_t)TILE; s <= P; s <<= 1) {
     for (int64_t j = s >> 1; j >= TILE; j >>= 1)
@@ -168,7 +237,7 @@ cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_i
   return e != cudaSuccess ? e : e2;
 }
 
-int hsl_topk_launches(int64_t n) {  // kernels hsl_launch_topk issues for n costs (for the callers' launch counters)
+int hsl_topk_launches(int64_t n) {  // kernels the multi-launch path of hsl_launch_topk issues for n costs (the cooperative path: 1)
   int64_t P = TILE;
   while (P < n) P <<= 1;
   int c = 2;
