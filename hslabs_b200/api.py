@@ -86,6 +86,7 @@ def _load():
     lib.hsl_allgather_costs.argtypes = [vp, vp, i64, vp, vp]
     lib.hsl_allgather_costs_host.argtypes = [vp, i32, vp, i64, vp]
     lib.hsl_model_tables.argtypes = [vp] + [vp] * 6
+    lib.hsl_fall_sweep_host.argtypes = [vp, i64, vp, C.c_double, C.c_double, i32, vp, vp, C.c_double, C.c_double] + [vp] * 6
     lib.hsl_select_topk.argtypes = [vp, i64, i32, vp, vp, vp]
     _lib = lib
     return lib
@@ -97,7 +98,7 @@ def exported_symbols():
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_get_tuning", "hsl_set_kernel_timing", "hsl_last_kernel_ms", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
-            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables"]
+            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host"]
 
 
 class _Pinned:
@@ -304,6 +305,23 @@ class Model:
         q = np.empty((n, self.config_dim)); status = np.empty(n, np.int32)
         _check(_load().hsl_ik_records_host(self._h, n, _p(rec), flags, _p(q), _p(status)))
         return dict(q=q, status=status)
+
+    def fall_sweep(self, params, n_steps, kick_step=None, kick_dv=None, play_dt=0.02, t0=0.0, hc=0.7, tmin=0.1, n_worlds=None, want_traj=False):
+        """hsl_fall_sweep_host: n_worlds copies of the reference's position-control loop with one torso kick each
+        (kick_step [W], kick_dv [W][3]); returns fell, t_end, final_z, status (+ traj [W][n_steps][3]) and kernel_ms."""
+        ks = None if kick_step is None else np.ascontiguousarray(kick_step, np.int32)
+        kv = None if kick_dv is None else np.ascontiguousarray(kick_dv, np.float64).reshape(-1, 3)
+        w = n_worlds or (ks.shape[0] if ks is not None else kv.shape[0] if kv is not None else 1)
+        params = np.ascontiguousarray(params, np.float64)
+        out = dict(fell=np.zeros(w, np.uint8), t_end=np.zeros(w), final_z=np.zeros(w), status=np.zeros(w, np.int32))
+        traj = np.zeros((w, n_steps, 3)) if want_traj else None
+        ms = C.c_float(0)
+        _check(_load().hsl_fall_sweep_host(self._h, w, _p(params), play_dt, t0, n_steps, _p(ks), _p(kv), hc, tmin, _p(out["fell"]), _p(out["t_end"]),
+                                           _p(out["final_z"]), _p(out["status"]), _p(traj), C.cast(C.byref(ms), C.c_void_p)))
+        out["kernel_ms"] = float(ms.value)
+        if want_traj:
+            out["traj"] = traj
+        return out
 
     def tables(self):
         """periodic::set_dynparts data: parent ids, foot / limb-top body ids, masses, COM and foot-point offsets."""

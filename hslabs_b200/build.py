@@ -11,8 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhsl_b200.so")
-SOURCES = ["hsl_kernels.cu", "hsl_select.cu", "hsl_capi.cu", "hsl_model_load.cpp"]
-HEADERS = ["hsl_frame.h", "hsl_forces.h", "hsl_pipe.h", "hsl_fastmath.h", "hsl_model.h", "hsl_internal.h", os.path.join("..", "..", "include", "hsl.h")]
+SOURCES = ["hsl_kernels.cu", "hsl_select.cu", "hsl_fall.cu", "hsl_capi.cu", "hsl_model_load.cpp"]
+HEADERS = ["hsl_fall.h", "hsl_frame.h", "hsl_forces.h", "hsl_pipe.h", "hsl_fastmath.h", "hsl_model.h", "hsl_internal.h", os.path.join("..", "..", "include", "hsl.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v", "--resource-usage"]
 

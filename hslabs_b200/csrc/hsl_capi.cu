@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/hsl.h"
+#include "hsl_fall.h"
 #include "hsl_internal.h"
 
 namespace {
@@ -56,6 +57,8 @@ struct PinBuf {  // grow-only pinned host buffer
 
 struct HslModel {
   HslModelPod pod;
+  HslSimPod sim;        // constants of the fall sweep (hsl_fall.cu)
+  bool sim_ok = false;
   double total_mass;
   int fb = 64, maxreg = 128;
   int64_t max_slots = (int64_t)1 << 26;  // frame slots per launch (hsl_set_max_slots)
@@ -111,6 +114,7 @@ int hsl_model_load_xml(const char* xml_path, HslModel** out) {
     delete m;
     return set_err(rc, "%s", err);
   }
+  m->sim_ok = (hsl_build_sim_pod(xml_path, &m->pod, &m->sim, err, sizeof err) == 0);
   m->total_mass = 0;  // periodic::get_total_mass, periodic.cpp:320-325 (DFS order)
   std::vector<double> mass(m->pod.n, 0.0);
   for (int t = 0; t < m->pod.ntrunk; t++) mass[m->pod.trunk[t].body] = m->pod.trunk[t].mass;
@@ -747,6 +751,91 @@ int hsl_math_selftest(int n, const double* a, const double* b, double* out) {
   HSL_CUDA(hsl_launch_math_selftest(n, da, db, dout, nullptr));
   HSL_CUDA(cudaMemcpy(out, dout, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost));
   cudaFree(da); cudaFree(db); cudaFree(dout);
+  return HSL_OK;
+}
+
+// ---------------------------------------------------------------- fall / perturbation sweep
+int hsl_fall_sweep_host(HslModel* m, int64_t n_worlds, const double* params, double play_dt, double t0, int n_steps, const int32_t* kick_step,
+                        const double* kick_dv, double hc, double tmin, uint8_t* fell, double* t_end, double* final_z, int32_t* status,
+                        double* traj, float* kernel_ms) {
+  if (!m || n_worlds < 1 || !params || !(play_dt > 0) || n_steps < 1) return set_err(HSL_ERR_ARG, "bad argument");
+  if (!m->sim_ok) return set_err(HSL_ERR_UNSUPPORTED, "no simulation constants for this model");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  const HslModelPod& P = m->pod;
+  // setup_per_controller (player.cpp:370-382): the gait at n_t = int(T / play_dt + .5) frames, evaluated by the hot path
+  const int n_t = (int)(params[7] / play_dt + .5);
+  if (n_t < 1) return set_err(HSL_ERR_ARG, "period shorter than play_dt");
+  const size_t pbytes = sizeof(double) * HSL_NPARAM;
+  HSL_CUDA(m->params.need(pbytes));
+  HSL_CUDA(cudaMemcpyAsync(m->params.p, params, pbytes, cudaMemcpyHostToDevice, st));
+  HSL_CUDA(m->out4.need(sizeof(double) * 4 + sizeof(int32_t)));
+  double* d4 = (double*)m->out4.p;
+  int32_t* dst = (int32_t*)(d4 + 4);
+  // ignore_reach: set_fall_test switches it on (player.cpp:785)
+  rc = eval_gaits_dev(m, 1, n_t, (const double*)m->params.p, HSL_FLAG_IGNORE_REACH, d4, d4 + 1, d4 + 2, d4 + 3, dst, true, st);
+  if (rc) return rc;
+  int32_t gait_status = 0;
+  HSL_CUDA(cudaMemcpyAsync(&gait_status, dst, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  DevBuf ctrl, dks, dkv, dfell, dtend, dz, dstat, dsteps, dtraj, dq1, dA;
+  auto cleanup = [&]() { DevBuf* all[] = {&ctrl, &dks, &dkv, &dfell, &dtend, &dz, &dstat, &dsteps, &dtraj, &dq1, &dA}; for (DevBuf* b : all) b->release(); };
+#define HSL_CUDA_F(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { cleanup(); return set_err(HSL_ERR_CUDA, "CUDA: %s", cudaGetErrorString(e_)); } } while (0)
+  HSL_CUDA_F(ctrl.need(sizeof(double) * (size_t)n_t * 3 * P.nmj));
+  HSL_CUDA_F(hsl_launch_fall_ctrl(n_t, P.nmj, params[7] / n_t, (const double*)m->dump_q.p, (const double*)m->dump_tau.p, (double*)ctrl.p, st));
+  // init_play_config (player.cpp:349-355): joint values of the gait at play_t (frame index of the trajectory dump), FK, body poses
+  const double play_t0 = (double)(int)(t0 / play_dt + .5) * play_dt;
+  const int f0 = (int)(play_t0 / (params[7] / n_t) + .5);
+  std::vector<double> q0(P.config_dim), A0((size_t)16 * P.n);
+  if (f0 > n_t + 3) { cleanup(); return set_err(HSL_ERR_ARG, "t0 beyond the recorded trajectory (t0 <= period)"); }
+  HSL_CUDA_F(dq1.need(sizeof(double) * P.config_dim));
+  HSL_CUDA_F(dA.need(sizeof(double) * 16 * P.n));
+  HSL_CUDA_F(cudaMemcpy2DAsync(dq1.p, sizeof(double), (const double*)m->dump_q.p + f0, sizeof(double) * (n_t + 4), sizeof(double), P.config_dim,
+                               cudaMemcpyDeviceToDevice, st));  // column f0 of the component-major trajectory
+  HSL_CUDA_F(hsl_launch_fk_records(P, 1, (const double*)dq1.p, (double*)dA.p, nullptr, st));
+  HSL_CUDA_F(cudaMemcpyAsync(A0.data(), dA.p, sizeof(double) * 16 * P.n, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA_F(cudaStreamSynchronize(st));
+  if (gait_status & (HSL_ST_BAD_PARAMS | HSL_ST_SOLVER | HSL_ST_FEW_CONTACTS)) { cleanup(); return set_err(HSL_ERR_ARG, "the gait itself does not evaluate (status bits set)"); }
+  HslFallArgs A;
+  memset(&A, 0, sizeof A);
+  hsl_sim_state_from_frames(&m->sim, A0.data(), A.pos0, A.quat0);
+  A.n_worlds = n_worlds; A.n_steps = n_steps; A.n_t = n_t; A.iterations = 20;
+  A.play_dt = play_dt; A.play_t0 = play_t0; A.hc = hc; A.tmin = tmin;
+  A.erp = 0.8; A.cfm = 1e-10; A.soft_cfm = 1e-3; A.bounce = 0.5; A.bounce_vel = 0.1; A.gravity = 1.0; A.kp = 100.0;
+  A.ctrl = (const double*)ctrl.p;
+  if (kick_step) {
+    HSL_CUDA_F(dks.need(sizeof(int32_t) * n_worlds));
+    HSL_CUDA_F(cudaMemcpyAsync(dks.p, kick_step, sizeof(int32_t) * n_worlds, cudaMemcpyHostToDevice, st));
+    A.kick_step = (const int32_t*)dks.p;
+  }
+  if (kick_dv) {
+    HSL_CUDA_F(dkv.need(sizeof(double) * 3 * n_worlds));
+    HSL_CUDA_F(cudaMemcpyAsync(dkv.p, kick_dv, sizeof(double) * 3 * n_worlds, cudaMemcpyHostToDevice, st));
+    A.kick_dv = (const double*)dkv.p;
+  }
+  HSL_CUDA_F(dfell.need(n_worlds)); HSL_CUDA_F(dtend.need(sizeof(double) * n_worlds)); HSL_CUDA_F(dz.need(sizeof(double) * n_worlds));
+  HSL_CUDA_F(dstat.need(sizeof(int32_t) * n_worlds)); HSL_CUDA_F(dsteps.need(sizeof(int32_t) * n_worlds));
+  A.fell = (uint8_t*)dfell.p; A.t_end = (double*)dtend.p; A.final_z = (double*)dz.p; A.status = (int32_t*)dstat.p; A.steps_done = (int32_t*)dsteps.p;
+  if (traj) { HSL_CUDA_F(dtraj.need(sizeof(double) * 3 * (size_t)n_worlds * n_steps)); HSL_CUDA_F(cudaMemsetAsync(dtraj.p, 0, sizeof(double) * 3 * (size_t)n_worlds * n_steps, st)); A.traj = (double*)dtraj.p; }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  HSL_CUDA_F(cudaEventCreate(&e0)); HSL_CUDA_F(cudaEventCreate(&e1));
+  HSL_CUDA_F(cudaEventRecord(e0, st));
+  cudaError_t le = hsl_launch_fall(m->sim, A, st);
+  cudaEventRecord(e1, st);
+  m->launches += 3;
+  if (le == cudaSuccess) le = cudaStreamSynchronize(st);
+  float ms = 0;
+  if (le == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (le != cudaSuccess) { cleanup(); return set_err(HSL_ERR_CUDA, "CUDA: %s", cudaGetErrorString(le)); }
+  if (kernel_ms) *kernel_ms = ms;
+  if (fell) HSL_CUDA_F(cudaMemcpy(fell, dfell.p, n_worlds, cudaMemcpyDeviceToHost));
+  if (t_end) HSL_CUDA_F(cudaMemcpy(t_end, dtend.p, sizeof(double) * n_worlds, cudaMemcpyDeviceToHost));
+  if (final_z) HSL_CUDA_F(cudaMemcpy(final_z, dz.p, sizeof(double) * n_worlds, cudaMemcpyDeviceToHost));
+  if (status) HSL_CUDA_F(cudaMemcpy(status, dstat.p, sizeof(int32_t) * n_worlds, cudaMemcpyDeviceToHost));
+  if (traj) HSL_CUDA_F(cudaMemcpy(traj, dtraj.p, sizeof(double) * 3 * (size_t)n_worlds * n_steps, cudaMemcpyDeviceToHost));
+#undef HSL_CUDA_F
+  cleanup();
   return HSL_OK;
 }
 

@@ -27,3 +27,4 @@ cudaError_t hsl_launch_dfma_probe(double* out, int blocks, int threads, int iter
 
 // hsl_model_load.cpp
 int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int errlen);
+int hsl_build_sim_pod(const char* xml_path, const HslModelPod* pod, HslSimPod* sim, char* err, int errlen);

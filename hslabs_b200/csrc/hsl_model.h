@@ -66,6 +66,34 @@ typedef struct HslModelPod {
   int32_t motor_of_body[HSL_MAX_BODIES];  // hinge index in joint-value order, -1 otherwise
 } HslModelPod;
 
+// Constants of the fall / perturbation sweep (hsl_fall.cu): what the reference hands to ODE when it
+// builds the simulated robot -- one rigid body per model body at its COM (odepart::make, visualization.cpp:442-491),
+// its first geom as collision shape (sphere and capsule collide with the ground plane, visualization.cpp:296-306), a
+// hinge per hinge joint and a fixed joint per jointless body (kinematicmodel::set_ode_joints, model.cpp:375-400;
+// odepart::make_hinge_joint / make_fixed_joint, visualization.cpp:506-533), all set up in the zero configuration.
+// Body frames here: origin at the COM, axes of the model body frame.
+typedef struct HslSimBody {
+  int32_t geom;          // 0 does not collide (cylinder), 1 sphere, 2 capsule
+  int32_t pad;
+  double radius;
+  double p0[3], p1[3];   // capsule end points / sphere centre (p0 = p1) relative to the COM, body axes
+  double mass, inertia;
+} HslSimBody;
+typedef struct HslSimJoint {
+  int32_t kind;          // 1 hinge, 2 fixed
+  int32_t b1, b2;        // ODE's body order: hinge (child, parent), fixed (parent, child)
+  int32_t motor;         // hinge: index in joint-value order
+  double anchor1[3], anchor2[3], axis1[3], axis2[3];  // in the bodies' own frames
+  double qrel[4];        // q1^-1 q2 in the zero configuration
+  double offset[3];      // fixed: R1^T (p1 - p2)
+} HslSimJoint;
+typedef struct HslSimPod {
+  int32_t n, nj, nmotor, pad;
+  HslSimBody body[HSL_MAX_BODIES];
+  HslSimJoint joint[HSL_MAX_BODIES];
+  double com[HSL_MAX_BODIES][3];  // COM offset in the model body frame (initial poses: A_ground * com)
+} HslSimPod;
+
 // Per-candidate constants written by the setup kernel (reference: pgssweeper::setup_pergen and
 // friends, pergen.cpp:453-507; periodicgenerator::set_step_duration, pergen.cpp:30-51).
 typedef struct HslCand {

@@ -137,6 +137,8 @@ struct RawBody {
   double jpos[3] = {0, 0, 0}, axis[3] = {0, 0, 1};
   double com[3] = {0, 0, 0}, tip[3] = {0, 0, 0};
   double rcap = 0;
+  int geom = 0;  // 1 sphere, 2 capsule, 0 cylinder (does not collide with the ground in the reference)
+  double gsize = 0, from[3] = {0, 0, 0};
 };
 
 bool flatten(const Elem& e, int parent, std::vector<RawBody>& out, std::string& err) {
@@ -148,12 +150,13 @@ bool flatten(const Elem& e, int parent, std::vector<RawBody>& out, std::string& 
   std::string type = g->get("type");
   double size = 0;
   numbers(g->get("size"), &size, 1);
-  if (type == "sphere") numbers(g->get("pos"), b.com, 3);
+  b.gsize = size;
+  if (type == "sphere") { numbers(g->get("pos"), b.com, 3); b.geom = 1; for (int k = 0; k < 3; k++) b.from[k] = b.tip[k] = b.com[k]; }
   else if (type == "capsule" || type == "cylinder") {
     double ft[6] = {0, 0, 0, 0, 0, 0};
     numbers(g->get("fromto"), ft, 6);
-    for (int k = 0; k < 3; k++) { b.com[k] = (ft[k] + ft[k + 3]) / 2.; b.tip[k] = ft[k + 3]; }
-    if (type == "capsule") b.rcap = size;
+    for (int k = 0; k < 3; k++) { b.com[k] = (ft[k] + ft[k + 3]) / 2.; b.tip[k] = ft[k + 3]; b.from[k] = ft[k]; }
+    if (type == "capsule") { b.rcap = size; b.geom = 2; }
   } else { err = "unsupported geom type " + type; return false; }
   if (const Elem* j = e.child("joint")) {
     std::string jt = j->get("type") ? j->get("type") : "";
@@ -290,5 +293,111 @@ int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* errbuf, in
     L.ysign = (M.lik_index == 0) ? ((l < 2) ? 1 : -1) : ((l % 2 == 0) ? 1 : -1);  // lik.cpp:231,237,243
   }
   if ((M.lik_index == 0 && M.nf != 4) || (M.lik_index != 0 && M.nf != 6)) return fail(-3, "limb count does not match the model's LIK table");
+  return 0;
+}
+
+
+// ---------------------------------------------------------------------------------------------------- simulation constants
+#include "hsl_frame.h"
+
+namespace {
+void quat_from_colmajor(const double* R, double* q) {  // ODE dRtoQ on the matrix whose element (i,j) is R[3*j+i]
+  auto e = [&](int i, int j) { return R[3 * j + i]; };
+  const double tr = e(0, 0) + e(1, 1) + e(2, 2);
+  double s;
+  if (tr >= 0) {
+    s = std::sqrt(tr + 1); q[0] = 0.5 * s; s = 0.5 / s;
+    q[1] = (e(2, 1) - e(1, 2)) * s; q[2] = (e(0, 2) - e(2, 0)) * s; q[3] = (e(1, 0) - e(0, 1)) * s;
+  } else if (e(1, 1) > e(0, 0) && e(1, 1) >= e(2, 2)) {
+    s = std::sqrt((e(1, 1) - (e(2, 2) + e(0, 0))) + 1); q[2] = 0.5 * s; s = 0.5 / s;
+    q[3] = (e(2, 1) + e(1, 2)) * s; q[1] = (e(1, 0) + e(0, 1)) * s; q[0] = (e(0, 2) - e(2, 0)) * s;
+  } else if (e(2, 2) > e(0, 0) && e(2, 2) > e(1, 1)) {
+    s = std::sqrt((e(2, 2) - (e(0, 0) + e(1, 1))) + 1); q[3] = 0.5 * s; s = 0.5 / s;
+    q[1] = (e(0, 2) + e(2, 0)) * s; q[2] = (e(2, 1) + e(1, 2)) * s; q[0] = (e(1, 0) - e(0, 1)) * s;
+  } else {
+    s = std::sqrt((e(0, 0) - (e(1, 1) + e(2, 2))) + 1); q[1] = 0.5 * s; s = 0.5 / s;
+    q[2] = (e(1, 0) + e(0, 1)) * s; q[3] = (e(0, 2) + e(2, 0)) * s; q[0] = (e(2, 1) - e(1, 2)) * s;
+  }
+}
+void qmul(const double* b, const double* c, double* a) {
+  a[0] = b[0] * c[0] - b[1] * c[1] - b[2] * c[2] - b[3] * c[3];
+  a[1] = b[0] * c[1] + b[1] * c[0] + b[2] * c[3] - b[3] * c[2];
+  a[2] = b[0] * c[2] + b[2] * c[0] + b[3] * c[1] - b[1] * c[3];
+  a[3] = b[0] * c[3] + b[3] * c[0] + b[1] * c[2] - b[2] * c[1];
+}
+// v (world) -> body axes: R^T v, R column-major with element (i,j) at [4*j+i] of an affine
+void to_body_axes(const double* A, const double* v, double* o) { for (int j = 0; j < 3; j++) o[j] = A[4 * j] * v[0] + A[4 * j + 1] * v[1] + A[4 * j + 2] * v[2]; }
+}  // namespace
+
+// Body poses and quaternions of a configuration from its body frames A [n][16]: pos = A * com, q = quaternion of the rotation.
+void hsl_sim_state_from_frames(const HslSimPod* sim, const double* A, double* pos, double* quat) {
+  for (int b = 0; b < sim->n; b++) {
+    const double* Ab = A + 16 * b;
+    for (int i = 0; i < 3; i++) pos[3 * b + i] = Ab[i] * sim->com[b][0] + Ab[4 + i] * sim->com[b][1] + Ab[8 + i] * sim->com[b][2] + Ab[12 + i];
+    double R[9];
+    for (int j = 0; j < 3; j++) for (int i = 0; i < 3; i++) R[3 * j + i] = Ab[4 * j + i];
+    quat_from_colmajor(R, quat + 4 * b);
+  }
+}
+
+int hsl_build_sim_pod(const char* xml_path, const HslModelPod* pod, HslSimPod* sim, char* errbuf, int errlen) {
+  auto fail = [&](int code, const std::string& msg) { snprintf(errbuf, errlen, "%s", msg.c_str()); return code; };
+  std::ifstream f(xml_path, std::ios::binary);
+  if (!f) return fail(-2, std::string("cannot open ") + xml_path);
+  std::stringstream buf;
+  buf << f.rdbuf();
+  const std::string src = buf.str();
+  Reader rd{src.data(), src.data() + src.size()};
+  Elem root;
+  if (!rd.read(root) || rd.fail) return fail(-2, "not a mujoco file");
+  const Elem* wb = root.child("worldbody");
+  const Elem* tb = wb ? wb->child("body") : nullptr;
+  std::vector<RawBody> B;
+  std::string err;
+  if (!tb || !flatten(*tb, -1, B, err)) return fail(-3, err);
+  const int n = (int)B.size();
+  memset(sim, 0, sizeof *sim);
+  sim->n = n;
+  // zero configuration (every joint value 0): the state in which the reference creates the ODE joints (player.cpp:43-49)
+  std::vector<double> q(pod->config_dim, 0.0), A(16 * (size_t)n), J(16 * (size_t)n);
+  for (int role = 0; role <= pod->nf; role++) fk_record(*pod, role, q.data(), A.data(), J.data());
+  std::vector<double> pos(3 * (size_t)n), quat(4 * (size_t)n);
+  for (int b = 0; b < n; b++) {
+    HslSimBody& sb = sim->body[b];
+    sb.geom = B[b].geom;
+    sb.radius = B[b].gsize;
+    for (int k = 0; k < 3; k++) { sim->com[b][k] = B[b].com[k]; sb.p0[k] = B[b].from[k] - B[b].com[k]; sb.p1[k] = B[b].tip[k] - B[b].com[k]; }
+    sb.mass = 1.0; sb.inertia = 1.0;  // ODE dBodyCreate defaults: the reference never sets a mass (dynrec.cpp:62-68)
+  }
+  hsl_sim_state_from_frames(sim, A.data(), pos.data(), quat.data());
+  int nj = 0;
+  for (int b = 1; b < n; b++) {  // kinematicmodel::set_ode_joints: every body with a parent, in body order
+    const int p = pod->parent[b];
+    HslSimJoint& jt = sim->joint[nj++];
+    double qc[4], t4[4];
+    if (pod->jkind[b] == 2) {
+      jt.kind = 1; jt.b1 = b; jt.b2 = p; jt.motor = pod->motor_of_body[b];   // dJointAttach(hinge, odebody, parent_odebody)
+      const double* Jb = J.data() + 16 * b;
+      double anc[3] = {Jb[12], Jb[13], Jb[14]}, axis[3] = {Jb[8], Jb[9], Jb[10]}, d[3];
+      for (int k = 0; k < 3; k++) d[k] = anc[k] - pos[3 * b + k];
+      to_body_axes(A.data() + 16 * b, d, jt.anchor1);
+      for (int k = 0; k < 3; k++) d[k] = anc[k] - pos[3 * p + k];
+      to_body_axes(A.data() + 16 * p, d, jt.anchor2);
+      to_body_axes(A.data() + 16 * b, axis, jt.axis1);
+      to_body_axes(A.data() + 16 * p, axis, jt.axis2);
+    } else if (pod->jkind[b] == 0) {
+      jt.kind = 2; jt.b1 = p; jt.b2 = b; jt.motor = -1;                        // dJointAttach(joint, parent_odebody, odebody)
+      double d[3];
+      for (int k = 0; k < 3; k++) d[k] = pos[3 * jt.b1 + k] - pos[3 * jt.b2 + k];
+      to_body_axes(A.data() + 16 * jt.b1, d, jt.offset);
+    } else {
+      return fail(-3, "unsupported joint below the torso");
+    }
+    qc[0] = quat[4 * jt.b1]; qc[1] = -quat[4 * jt.b1 + 1]; qc[2] = -quat[4 * jt.b1 + 2]; qc[3] = -quat[4 * jt.b1 + 3];
+    qmul(qc, quat.data() + 4 * jt.b2, t4);
+    for (int k = 0; k < 4; k++) jt.qrel[k] = t4[k];
+  }
+  sim->nj = nj;
+  sim->nmotor = pod->nmj;
   return 0;
 }

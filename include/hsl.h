@@ -145,6 +145,19 @@ int hsl_solve_forces_gait_host(HslModel* m, int64_t n_cand, int n_t, const doubl
  * (pergen.cpp:446).  eas = (phi, theta, psi); either pointer may be NULL (= zero); both NULL switches it off. */
 int hsl_set_rec_transform(HslModel* m, const double* transl /*[3]*/, const double* eas /*[3]*/);
 
+/* Fall / perturbation sweep (BASELINE configs[4]; run_fall_test.sh, main.cpp:48-50,64): n_worlds copies of the reference's
+ * closed loop -- position_control_test(pgs, t0) with set_fall_test(hc, tmin, .) and torso kicks (player.cpp:358-382,
+ * 326-340, 393-432, 585-605, 669-681) -- each with its own kick: kick_step [W] (step index, < 0 never) and kick_dv [W][3]
+ * (velocity change, applied as the force dv / play_dt for one step), either may be NULL.  params [13]: ONE gait (the
+ * controller's targets and feed-forward torques come from its evaluation at n_t = int(period / play_dt + .5)).
+ * Outputs [W] (any may be NULL): fell, t_end (time of the fall or end time), final torso COM height, status
+ * (bit 0: more than 16 bodies touched the ground); traj optional [W][n_steps][3] torso COM after every step;
+ * kernel_ms optional: duration of the sweep kernel.  The rigid-body stepper restates what the reference asks of ODE
+ * (dWorldQuickStep: DESIGN.md section 9); agreement with a real ODE build is statistical.  HOST pointers. */
+int hsl_fall_sweep_host(HslModel* m, int64_t n_worlds, const double* params, double play_dt, double t0, int n_steps,
+                        const int32_t* kick_step, const double* kick_dv, double hc, double tmin, uint8_t* fell, double* t_end,
+                        double* final_z, int32_t* status, double* traj, float* kernel_ms);
+
 /* Multi-GPU: candidates shard over one process per GPU and never span GPUs; the path's one collective is
  * the all-gather of the per-candidate costs before selection.  d_local [n_per_rank] -> d_all [nranks][n_per_rank] on
  * every rank, DEVICE pointers, queued on `stream`; nccl_comm is an ncclComm_t (any communicator of the process: the

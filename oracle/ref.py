@@ -186,3 +186,34 @@ class Model:
 
     def lik_solver_test(self, n=100):
         return lib().ref_lik_solver_test(self.h, C.c_int(n))
+
+    def fall_run(self, params, n_steps, play_dt=0.02, t0=0.0, kick_step=-1, kick_dv=(0.0, 0.0, 0.0), hc=0.7, tmin=0.1, want_traj=False):
+        """The reference's position-control loop on the ODE shim's stepper with one torso kick (oracle/ref_driver.cpp
+        ref_fall_run).  Only valid in a process where this is the only model loaded."""
+        params = np.ascontiguousarray(params, np.float64)
+        dv = np.ascontiguousarray(kick_dv, np.float64)
+        out = np.zeros(4)
+        traj = np.zeros((n_steps, 3)) if want_traj else None
+        lib().ref_fall_run.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double,
+                                       C.c_void_p, C.c_void_p]
+        rc = lib().ref_fall_run(self.h, _p(params), play_dt, t0, n_steps, kick_step, _p(dv), hc, tmin, _p(out), _p(traj))
+        if rc:
+            raise RuntimeError("ref_fall_run failed: %d" % rc)
+        res = dict(fell=bool(out[0]), t=out[1], z=out[2], steps=int(out[3]))
+        if want_traj:
+            res["traj"] = traj[:max(res["steps"], 0)]
+        return res
+
+    def fall_batch(self, params, n_steps, kick_step, kick_dv, play_dt=0.02, t0=0.0, hc=0.7, tmin=0.1, nprocs=1):
+        """fall_run for W worlds on forked worker processes (one pristine reference process per world)."""
+        params = np.ascontiguousarray(params, np.float64)
+        ks = np.ascontiguousarray(kick_step, np.int32)
+        kv = np.ascontiguousarray(kick_dv, np.float64).reshape(-1, 3)
+        w = ks.shape[0]
+        fell = np.zeros(w, np.uint8); t_end = np.zeros(w); z = np.zeros(w)
+        lib().ref_fall_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                         C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        rc = lib().ref_fall_batch(self.h, _p(params), w, play_dt, t0, n_steps, _p(ks), _p(kv), hc, tmin, _p(fell), _p(t_end), _p(z), nprocs)
+        if rc:
+            raise RuntimeError("ref_fall_batch failed: %d" % rc)
+        return dict(fell=fell, t_end=t_end, final_z=z)

@@ -38,6 +38,7 @@
 #include "ftsolver.h"
 
 extern long ds_shim_max_steps;
+void dShimSeedRandom(unsigned long s);
 
 namespace {
 
@@ -53,6 +54,7 @@ class NullBuf : public std::streambuf {
   std::streamsize xsputn(const char*, std::streamsize n) { return n; }
 };
 NullBuf g_nullbuf;
+int g_models_loaded = 0;  // the reference keeps ONE static ODE world (visualization.cpp:165): simulation needs a process with one model
 bool g_quiet = true;   // discard the reference's stdout chatter (warnings, "sweeping over ...")
 bool g_isolate = true;
 
@@ -238,6 +240,7 @@ void* ref_model_load(const char* dir, const char* xml) {
       h->xml = xml;
       h->mp = new modelplayer;
       h->mp->load_model(xml);
+      g_models_loaded++;
       h->n = (int)h->mp->model->get_odeparts()->size();
       h->nf = h->mp->model->get_lik()->get_number_of_limbs();
       h->nmj = h->mp->model->number_of_motor_joints();
@@ -641,6 +644,97 @@ int ref_load_preset(void* hv, const char* file, int id, double* params, char* xm
         std::memcpy(xml_name, shm + 13 * sizeof(double), 64);
         xml_name[63] = 0;
       });
+}
+
+// Fall / perturbation run (BASELINE configs[4]): the reference's own closed loop
+//   position_control_test -> setup_per_controller -> step() -> simulate_ode   (player.cpp:358-382, 326-340, 393-432)
+// on the ODE shim's world stepper (oracle/shim/ode_step.cpp), driven step by step instead of through drawstuff's loop
+// so that the kick (kick_torso, player.cpp:585-605: a force dv/dt on the torso for one step) and the fall check
+// (fall_check, player.cpp:669-681: torso z < hc once play_t >= tmin) take their parameters from the caller.
+// params[13] as everywhere; kick_dv[3] = velocity change of the kick applied at step kick_step (< 0: never).
+// out[4] = fell (0/1), time of the fall (or end time), final torso z, steps simulated; traj (optional)
+// [n_steps][3] torso position after every step.  Needs a process in which only this model was loaded.
+int ref_fall_run(void* hv, const double* params, double play_dt, double t0, int n_steps, int kick_step, const double* kick_dv, double hc,
+                 double tmin, double* out, double* traj) {
+  Handle* h = (Handle*)hv;
+  if (g_models_loaded != 1) return -3;
+  const size_t nd = 4 + 3 * (size_t)n_steps;
+  return run_isolated(
+      nd * sizeof(double),
+      [&](char* shm) {
+        Quiet q;
+        double* b = (double*)shm;
+        modelplayer* mp = h->mp;
+        mp->set_play_dt(play_dt);
+        pergensetup* pgs = make_pgs(h, params);
+        mp->ignore_reach();                          // set_fall_test does (player.cpp:785)
+        mp->set_flag("position_control", true);      // position_control_test, player.cpp:358-360
+        mp->setup_per_controller(pgs, t0);
+        dShimSeedRandom(0);                           // a fresh ODE process
+        dBodyID torso = mp->get_torso_odebody();
+        int fell = 0, step = 0;
+        double t_fall = 0;
+        for (; step < n_steps; step++) {
+          const dReal* pos = dBodyGetPosition(torso);
+          if (mp->play_t >= tmin && pos[2] < hc) { fell = 1; t_fall = mp->play_t; break; }   // fall_check
+          if (step == kick_step) {
+            double f[3] = {kick_dv[0] / play_dt, kick_dv[1] / play_dt, kick_dv[2] / play_dt};
+            mp->get_vis()->add_force(torso, f);
+          }
+          mp->step();                                 // case 6: simulate_ode()
+          pos = dBodyGetPosition(torso);
+          for (int k = 0; k < 3; k++) b[4 + 3 * step + k] = pos[k];
+        }
+        b[0] = fell;
+        b[1] = fell ? t_fall : mp->play_t;
+        b[2] = dBodyGetPosition(torso)[2];
+        b[3] = step;
+      },
+      [&](const char* shm) {
+        const double* b = (const double*)shm;
+        std::memcpy(out, b, 4 * sizeof(double));
+        if (traj) std::memcpy(traj, b + 4, 3 * (size_t)n_steps * sizeof(double));
+      });
+}
+
+// W fall runs on `nprocs` forked workers (each world is its own reference process, like run_fall_test.sh's loop).
+// fell / t_end / final_z: [W].
+int ref_fall_batch(void* hv, const double* params, long W, double play_dt, double t0, int n_steps, const int* kick_step, const double* kick_dv,
+                   double hc, double tmin, unsigned char* fell, double* t_end, double* final_z, int nprocs) {
+  if (g_models_loaded != 1) return -3;
+  if (nprocs < 1) nprocs = 1;
+  Shm shm((size_t)W * 4 * sizeof(double));
+  if (!shm.p) return -1;
+  double* b = (double*)shm.p;
+  for (long i = 0; i < 4 * W; i++) b[i] = NAN;
+  bool was = g_isolate;
+  fflush(0);
+  std::vector<pid_t> pids;
+  for (int w = 0; w < nprocs; w++) {
+    pid_t pid = fork();
+    if (pid == 0) {
+      child_signals();
+      g_isolate = false;  // already in a child: run the worlds of this worker in-process, one after the other
+      for (long i = w; i < W; i += nprocs) {
+        // every world needs the pristine post-load state: fork once more per world
+        pid_t p2 = fork();
+        if (p2 == 0) {
+          double out[4];
+          int rc = ref_fall_run(hv, params, play_dt, t0, n_steps, kick_step ? kick_step[i] : -1, kick_dv ? kick_dv + 3 * i : params, hc, tmin, out, 0);
+          if (rc == 0) for (int k = 0; k < 4; k++) b[4 * i + k] = out[k];
+          _exit(rc == 0 ? 0 : 1);
+        }
+        int st = 0;
+        waitpid(p2, &st, 0);
+      }
+      _exit(0);
+    }
+    if (pid > 0) pids.push_back(pid);
+  }
+  for (size_t i = 0; i < pids.size(); i++) { int st = 0; waitpid(pids[i], &st, 0); }
+  g_isolate = was;
+  for (long i = 0; i < W; i++) { fell[i] = (unsigned char)(b[4 * i] == 1.0); t_end[i] = b[4 * i + 1]; final_z[i] = b[4 * i + 2]; }
+  return 0;
 }
 
 // liksolver::solver_test (lik.cpp:123-128): the reference's own IK round-trip self-check; exit(1) on failure.

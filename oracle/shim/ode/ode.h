@@ -55,6 +55,7 @@ struct dxBody {
   dQuaternion q;
   dVector3 lvel, avel, facc, tacc;
   dMass mass;
+  int tag;  // index in the world's body array during a step
 };
 
 struct dxGeom {
@@ -103,7 +104,8 @@ struct dxWorld {
   dReal erp, cfm;
   int qs_iterations;
   std::vector<dxBody*> bodies;
-  std::vector<dxJoint*> joints;  // persistent joints (hinge, fixed); contacts live in their group
+  std::vector<dxJoint*> joints;         // persistent joints (hinge, fixed)
+  std::vector<dxJoint*> step_contacts;  // contact joints created since the last dJointGroupEmpty (they live in their group)
 };
 struct dxTriMeshData {
   const dReal* vertices;
@@ -195,6 +197,7 @@ inline void dWorldSetERP(dWorldID w, dReal erp) { w->erp = erp; }
 inline void dWorldSetCFM(dWorldID w, dReal cfm) { w->cfm = cfm; }
 inline void dWorldSetQuickStepNumIterations(dWorldID w, int n) { w->qs_iterations = n; }
 int dWorldQuickStep(dWorldID w, dReal stepsize);
+void dShimSeedRandom(unsigned long s);  // ODE's dRandSetSeed: seed of the constraint re-ordering (0 in a fresh process)
 
 inline dSpaceID dHashSpaceCreate(dSpaceID) { return new dxSpace; }
 void dSpaceDestroy(dSpaceID s);

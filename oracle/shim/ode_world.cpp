@@ -60,7 +60,14 @@ void dGeomDestroy(dGeomID g) {
   delete g;
 }
 void dJointGroupEmpty(dJointGroupID g) {
-  for (size_t i = 0; i < g->joints.size(); i++) delete g->joints[i];
+  for (size_t i = 0; i < g->joints.size(); i++) {
+    dxJoint* j = g->joints[i];
+    if (j->world) {
+      std::vector<dxJoint*>& v = j->world->step_contacts;
+      for (size_t k = 0; k < v.size(); k++) if (v[k] == j) { v.erase(v.begin() + k); break; }
+    }
+    delete j;
+  }
   g->joints.clear();
 }
 
@@ -78,6 +85,7 @@ dJointID dJointCreateFixed(dWorldID w, dJointGroupID g) { return new_joint(w, g,
 dJointID dJointCreateContact(dWorldID w, dJointGroupID g, const dContact* c) {
   dxJoint* j = new_joint(w, g, dShimJointContact);
   j->contact = *c;
+  if (w) w->step_contacts.push_back(j);
   return j;
 }
 void dJointAttach(dJointID j, dBodyID b1, dBodyID b2) {

@@ -1,0 +1,79 @@
+"""GPU tier: the fall / perturbation sweep (BASELINE configs[4]).
+
+hsl_fall_sweep_host integrates many copies of the reference's closed loop (PD position control about the evaluated
+gait, one torso kick, fall check) with a batched restatement of ODE's quickstep.  The checker is the reference's own
+player.cpp running on the ODE shim (oracle/shim/ode_step.cpp), in a separate process.  Both follow the same arithmetic
+row for row, so short horizons agree to round-off; over long horizons the contact dynamics amplify round-off, so fall
+outcomes are compared world by world with a small disagreement allowance and as statistics (fall rate, time-to-fall
+histogram)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import PRESETS, ROOT, model_xml
+
+pytestmark = pytest.mark.gpu
+
+
+def cpu_side(tmp_path, xml, params, n_steps, kick_step, kick_dv, n_traj=0, nprocs=None, **kw):
+    from oracle import ref
+    ref.build()
+    if not ref.available():
+        pytest.skip("oracle/_ref not built")
+    inp, outp = str(tmp_path / "in.npz"), str(tmp_path / "out.npz")
+    np.savez(inp, xml=xml, params=params, n_steps=n_steps, kick_step=np.asarray(kick_step, np.int32), kick_dv=np.asarray(kick_dv, np.float64),
+             play_dt=kw.get("play_dt", 0.02), t0=kw.get("t0", 0.0), hc=kw.get("hc", 0.7), tmin=kw.get("tmin", 0.1),
+             nprocs=nprocs or os.cpu_count() or 4, n_traj=n_traj)
+    subprocess.check_call([sys.executable, os.path.join(ROOT, "tests", "fall_cpu_worker.py"), inp, outp], timeout=1500)
+    return np.load(outp)
+
+
+def test_short_horizon_follows_the_cpu_stepper(hsl, tmp_path):
+    params, name = hsl.load_preset(PRESETS, 8)
+    xml = model_xml(name)
+    kicks = np.array([[0, 0, 0], [4, 0, 0], [0, 10, 0], [0, -7, 2], [3, 9, -1], [0, 14, 0]], float)
+    ks = np.array([-1, 30, 30, 10, 45, 20], np.int32)
+    n_steps = 150
+    cpu = cpu_side(tmp_path, xml, params, n_steps, ks, kicks, n_traj=len(ks))
+    gpu = hsl.Model(xml).fall_sweep(params, n_steps, ks, kicks, want_traj=True)
+    assert (gpu["status"] == 0).all()
+    for i in range(len(ks)):
+        a, b = gpu["traj"][i], cpu["traj"][i]
+        # same arithmetic, different summation grouping: round-off level until the contact dynamics amplify it
+        assert np.abs(a[:60] - b[:60]).max() < 1e-7, (i, np.abs(a[:60] - b[:60]).max())
+        n_ok = int(np.isfinite(b[:, 0]).sum())
+        assert np.abs(a[:n_ok] - b[:n_ok]).max() < 5e-2, i
+    assert np.array_equal(gpu["fell"], cpu["fell"])
+    both = gpu["fell"].astype(bool)
+    assert np.abs(gpu["t_end"][both] - cpu["t_end"][both]).max() <= 0.1
+
+
+def test_fall_statistics_against_the_cpu_stepper(hsl, tmp_path):
+    """1024 random kicks (direction uniform in the horizontal plane, |dv| U[0, 16], kick time U[0.5 s, 3.5 s)): fall rate and
+    time-to-fall histogram of the sweep kernel against the CPU stepper on the same kicks."""
+    params, name = hsl.load_preset(PRESETS, 8)
+    xml = model_xml(name)
+    rng = np.random.default_rng(20261019)
+    w, n_steps = 1024, 300
+    mag, th = rng.uniform(0, 16, w), rng.uniform(0, 2 * np.pi, w)
+    kicks = np.stack([mag * np.cos(th), mag * np.sin(th), np.zeros(w)], axis=1)
+    ks = rng.integers(25, 175, w).astype(np.int32)
+    cpu = cpu_side(tmp_path, xml, params, n_steps, ks, kicks)
+    gpu = hsl.Model(xml).fall_sweep(params, n_steps, ks, kicks)
+    fr_c, fr_g = cpu["fell"].mean(), gpu["fell"].mean()
+    print("fall rate cpu %.4f gpu %.4f, per-world agreement %.4f, kernel %.1f ms (%.3g world-steps/s)" %
+          (fr_c, fr_g, (cpu["fell"] == gpu["fell"]).mean(), gpu["kernel_ms"], w * n_steps / (gpu["kernel_ms"] * 1e-3)))
+    assert 0.05 < fr_c < 0.95                      # the kick range brackets the stability limit
+    assert abs(fr_c - fr_g) <= 0.02
+    assert (cpu["fell"] == gpu["fell"]).mean() >= 0.97
+    hc, _ = np.histogram(cpu["t_end"][cpu["fell"] == 1], bins=12, range=(0, n_steps * 0.02))
+    hg, _ = np.histogram(gpu["t_end"][gpu["fell"] == 1], bins=12, range=(0, n_steps * 0.02))
+    assert np.abs(hc - hg).sum() <= 0.1 * max(hc.sum(), 1)
+    # no kick, no fall; a kick far beyond the limit always falls
+    calm = hsl.Model(xml).fall_sweep(params, n_steps, np.full(4, -1, np.int32), np.zeros((4, 3)))
+    assert not calm["fell"].any() and np.abs(calm["final_z"] - 0.8).max() < 0.02
+    hard = hsl.Model(xml).fall_sweep(params, n_steps, np.full(4, 20, np.int32), np.tile([0.0, 40.0, 0.0], (4, 1)))
+    assert hard["fell"].all()
