@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -817,6 +818,17 @@ int hsl_fall_sweep_host(HslModel* m, int64_t n_worlds, const double* params, dou
   HSL_CUDA_F(dstat.need(sizeof(int32_t) * n_worlds)); HSL_CUDA_F(dsteps.need(sizeof(int32_t) * n_worlds));
   A.fell = (uint8_t*)dfell.p; A.t_end = (double*)dtend.p; A.final_z = (double*)dz.p; A.status = (int32_t*)dstat.p; A.steps_done = (int32_t*)dsteps.p;
   if (traj) { HSL_CUDA_F(dtraj.need(sizeof(double) * 3 * (size_t)n_worlds * n_steps)); HSL_CUDA_F(cudaMemsetAsync(dtraj.p, 0, sizeof(double) * 3 * (size_t)n_worlds * n_steps, st)); A.traj = (double*)dtraj.p; }
+  if (const char* dbg = getenv("HSL_FALL_DEBUG")) {  // dump the kernel's inputs (control table, initial poses) for inspection
+    std::vector<double> hc((size_t)n_t * 3 * P.nmj);
+    HSL_CUDA_F(cudaMemcpy(hc.data(), ctrl.p, sizeof(double) * hc.size(), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(dbg, "wb")) {
+      fwrite(hc.data(), sizeof(double), hc.size(), f);
+      fwrite(A.pos0, sizeof(double), 3 * HSL_MAX_BODIES, f);
+      fwrite(A.quat0, sizeof(double), 4 * HSL_MAX_BODIES, f);
+      fwrite(&m->sim, sizeof(HslSimPod), 1, f);
+      fclose(f);
+    }
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   HSL_CUDA_F(cudaEventCreate(&e0)); HSL_CUDA_F(cudaEventCreate(&e1));
   HSL_CUDA_F(cudaEventRecord(e0, st));

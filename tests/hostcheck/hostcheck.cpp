@@ -4,6 +4,7 @@
 // This lets the CPU-only test tier check the exact arithmetic the CUDA kernels run (same source) against
 // the oracle.  It is never used by the product: hslabs_b200/ has no CPU path.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -12,8 +13,10 @@
 #include "../../hslabs_b200/csrc/hsl_forces.h"
 #include "../../hslabs_b200/csrc/hsl_model.h"
 #include "../../hslabs_b200/csrc/hsl_pipe.h"
+#include "../../hslabs_b200/csrc/hsl_fall_world.h"
 
 int hsl_build_model_pod(const char* xml_path, HslModelPod* pod, char* err, int errlen);
+int hsl_build_sim_pod(const char* xml_path, const HslModelPod* pod, HslSimPod* sim, char* err, int errlen);
 
 namespace {
 bool g_axis_special = true;  // emulate the kernels specialised for the model's hinge-axis pattern when there is one
@@ -328,6 +331,54 @@ int hc_eval_gaits(const char* xml, int64_t C, int n_t, const double* params, int
   if (contacts)
     for (int l = 0; l < M.nf; l++)
       for (int64_t f = 0; f < nfr; f++) contacts[f * M.nf + l] = dc[(size_t)l * nfr + f];
+  return 0;
+}
+
+// The fall / perturbation sweep (hsl_fall_sweep_host) with the kernel's per-world code run serially on the host: same
+// sequence as hsl_capi.cu (gait evaluation with ignore_reach -> control table -> initial body poses -> worlds).
+int hc_fall_sweep(const char* xml, int64_t W, const double* params, double play_dt, double t0, int n_steps, const int32_t* kick_step,
+                  const double* kick_dv, double hc, double tmin, uint8_t* fell, double* t_end, double* final_z, int32_t* status, double* traj) {
+  HslModelPod M;
+  static HslSimPod S;
+  char err[256];
+  int rc = hsl_build_model_pod(xml, &M, err, sizeof err);
+  if (rc) return rc;
+  if ((rc = hsl_build_sim_pod(xml, &M, &S, err, sizeof err))) return rc;
+  const int n_t = (int)(params[7] / play_dt + .5);
+  std::vector<double> cot(1), work(1), mn(1), mx(1), q((size_t)(n_t + 4) * M.config_dim), x((size_t)n_t * 6 * M.n), z((size_t)n_t * 3 * M.nf),
+      tau((size_t)n_t * M.nmj);
+  int32_t gst = 0;
+  rc = hc_eval_gaits(xml, 1, n_t, params, HSL_FLAG_IGNORE_REACH, cot.data(), work.data(), mn.data(), mx.data(), &gst, q.data(), x.data(), z.data(),
+                     tau.data(), nullptr);
+  if (rc) return rc;
+  std::vector<double> ctrl((size_t)n_t * 3 * M.nmj);
+  for (int tm = 0; tm < n_t; tm++)
+    for (int j = 0; j < M.nmj; j++)
+      hsl_fall::fall_ctrl_entry(n_t, M.nmj, params[7] / n_t, q.data(), M.config_dim, 1, tau.data(), M.nmj, 1, tm, j, ctrl.data());
+  const double play_t0 = (double)(int)(t0 / play_dt + .5) * play_dt;
+  const int f0 = (int)(play_t0 / (params[7] / n_t) + .5);
+  std::vector<double> A0((size_t)16 * M.n);
+  for (int role = 0; role <= M.nf; role++) fk_record(M, role, &q[(size_t)f0 * M.config_dim], A0.data(), nullptr);
+  static HslFallArgs A;
+  memset(&A, 0, sizeof A);
+  hsl_sim_state_from_frames(&S, A0.data(), A.pos0, A.quat0);
+  A.n_worlds = W; A.n_steps = n_steps; A.n_t = n_t; A.iterations = 20;
+  A.play_dt = play_dt; A.play_t0 = play_t0; A.hc = hc; A.tmin = tmin;
+  A.erp = 0.8; A.cfm = 1e-10; A.soft_cfm = 1e-3; A.bounce = 0.5; A.bounce_vel = 0.1; A.gravity = 1.0; A.kp = 100.0;
+  A.ctrl = ctrl.data(); A.kick_step = kick_step; A.kick_dv = kick_dv;
+  A.fell = fell; A.t_end = t_end; A.final_z = final_z; A.status = status; A.traj = traj;
+  if (const char* dbg = getenv("HSL_FALL_DEBUG")) {
+    if (FILE* f = fopen(dbg, "wb")) {
+      fwrite(ctrl.data(), sizeof(double), ctrl.size(), f);
+      fwrite(A.pos0, sizeof(double), 3 * HSL_MAX_BODIES, f);
+      fwrite(A.quat0, sizeof(double), 4 * HSL_MAX_BODIES, f);
+      fwrite(&S, sizeof(HslSimPod), 1, f);
+      fclose(f);
+    }
+  }
+  hsl_fall::World* w = new hsl_fall::World;
+  for (int64_t wi = 0; wi < W; wi++) hsl_fall::fall_world(S, A, wi, *w);
+  delete w;
   return 0;
 }
 

@@ -137,3 +137,19 @@ def eval_gaits_pipe(xml, params, n_t, flags=0, fb=64, grid=3):
                                   *[_p(out[k]) for k in ("cot", "work", "min_cfz", "max_mu", "status")])
     assert rc == 0, rc
     return out
+
+
+def fall_sweep(xml, params, n_steps, kick_step, kick_dv, play_dt=0.02, t0=0.0, hc=0.7, tmin=0.1, want_traj=False):
+    """hsl_fall_sweep_host with the sweep kernel's per-world code run serially on the host."""
+    params = np.ascontiguousarray(params, np.float64)
+    ks = np.ascontiguousarray(kick_step, np.int32)
+    kv = np.ascontiguousarray(kick_dv, np.float64).reshape(-1, 3)
+    w = ks.shape[0]
+    out = dict(fell=np.zeros(w, np.uint8), t_end=np.zeros(w), final_z=np.zeros(w), status=np.zeros(w, np.int32))
+    traj = np.zeros((w, n_steps, 3)) if want_traj else None
+    rc = lib().hc_fall_sweep(xml.encode(), C.c_int64(w), _p(params), C.c_double(play_dt), C.c_double(t0), C.c_int(n_steps), _p(ks), _p(kv),
+                             C.c_double(hc), C.c_double(tmin), _p(out["fell"]), _p(out["t_end"]), _p(out["final_z"]), _p(out["status"]), _p(traj))
+    assert rc == 0, rc
+    if want_traj:
+        out["traj"] = traj
+    return out
