@@ -445,6 +445,26 @@ def main():
             line["config3"] = rec
         del c3
 
+    # ------------------------------------------------------------------ fall / perturbation sweep (BASELINE configs[4])
+    if not args.no_extras:
+        fm = hsl.Model(hsl.model_path("hexapod"))
+        fparams, _ = hsl.load_preset(os.path.join(ROOT, "hslabs_b200", "models", "pgs_presets.txt"), 8)
+        fw, fsteps = 131072, 50                      # worlds per GPU (fills 148 SMs x 7 blocks x 128 threads), steps of 0.02 s
+        frng = np.random.default_rng(SEED + 77 + rank)
+        mag, th = frng.uniform(0, 16, fw), frng.uniform(0, 2 * np.pi, fw)
+        fk = np.stack([mag * np.cos(th), mag * np.sin(th), np.zeros(fw)], axis=1)
+        fks = frng.integers(5, 25, fw).astype(np.int32)
+        fm.fall_sweep(fparams, 5, fks[:4096], fk[:4096])                 # warm-up
+        barrier()
+        fres = fm.fall_sweep(fparams, fsteps, fks, fk)
+        f_ms = max_over_ranks(fres["kernel_ms"])
+        if rank == 0:
+            line["fall_sweep"] = {"workload": "hexapod.xml preset 8 under PD position control, %d worlds per GPU x %d steps of 0.02 s, one random torso kick each (BASELINE configs[4])" % (fw, fsteps),
+                                  "value": world * fw * fsteps / (f_ms * 1e-3), "unit": "world-steps/s", "kernel_ms": f_ms,
+                                  "fall_rate": float(fres["fell"].mean()), "status_all_zero": bool((fres["status"] == 0).all()),
+                                  "note": "one thread per world; bound by the L2 / HBM traffic of the thread-local working set (DESIGN.md section 9)"}
+        del fm
+
     # ------------------------------------------------------------------ CPU arm + parity of the timed batch (N = 1 only)
     if rank == 0 and not args.no_cpu and world == 1:
         cores = os.cpu_count() or 1

@@ -36,7 +36,7 @@ def test_short_horizon_follows_the_cpu_stepper(hsl, tmp_path):
     xml = model_xml(name)
     kicks = np.array([[0, 0, 0], [4, 0, 0], [0, 10, 0], [0, -7, 2], [3, 9, -1], [0, 14, 0]], float)
     ks = np.array([-1, 30, 30, 10, 45, 20], np.int32)
-    n_steps = 150
+    n_steps = 300
     cpu = cpu_side(tmp_path, xml, params, n_steps, ks, kicks, n_traj=len(ks))
     gpu = hsl.Model(xml).fall_sweep(params, n_steps, ks, kicks, want_traj=True)
     assert (gpu["status"] == 0).all()
@@ -51,6 +51,7 @@ def test_short_horizon_follows_the_cpu_stepper(hsl, tmp_path):
         assert np.abs(a[:n_ok] - b[:n_ok]).max() < 8e-2, i
     assert np.array_equal(gpu["fell"], cpu["fell"])
     both = gpu["fell"].astype(bool)
+    assert both.any() and not both.all()          # the kicks bracket the stability limit
     assert np.abs(gpu["t_end"][both] - cpu["t_end"][both]).max() <= 0.1
 
 
