@@ -743,15 +743,16 @@ int hsl_solve_forces_gait_host(HslModel* m, int64_t C, int n_t, const double* pa
 // out: [10][n] = hsl_div, a/b, hsl_sqrt(|a|), sqrt(|a|), hsl_atan2(a,b), atan2(a,b), then sin, sin_ref, cos, cos_ref of |a| (|a| <= pi)
 int hsl_math_selftest(int n, const double* a, const double* b, double* out) {
   if (n < 1 || !a || !b || !out) return set_err(HSL_ERR_ARG, "bad argument");
-  double *da = nullptr, *db = nullptr, *dout = nullptr;
-  HSL_CUDA(cudaMalloc(&da, sizeof(double) * n));
-  HSL_CUDA(cudaMalloc(&db, sizeof(double) * n));
-  HSL_CUDA(cudaMalloc(&dout, sizeof(double) * 10 * n));
-  HSL_CUDA(cudaMemcpy(da, a, sizeof(double) * n, cudaMemcpyHostToDevice));
-  HSL_CUDA(cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice));
-  HSL_CUDA(hsl_launch_math_selftest(n, da, db, dout, nullptr));
-  HSL_CUDA(cudaMemcpy(out, dout, sizeof(double) * 10 * n, cudaMemcpyDeviceToHost));
-  cudaFree(da); cudaFree(db); cudaFree(dout);
+  DevBuf da, db, dout;  // released on every path
+  cudaError_t e = da.need(sizeof(double) * n);
+  if (e == cudaSuccess) e = db.need(sizeof(double) * n);
+  if (e == cudaSuccess) e = dout.need(sizeof(double) * 10 * (size_t)n);
+  if (e == cudaSuccess) e = cudaMemcpy(da.p, a, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db.p, b, sizeof(double) * n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = hsl_launch_math_selftest(n, (const double*)da.p, (const double*)db.p, (double*)dout.p, nullptr);
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout.p, sizeof(double) * 10 * (size_t)n, cudaMemcpyDeviceToHost);
+  da.release(); db.release(); dout.release();
+  if (e != cudaSuccess) return set_err(HSL_ERR_CUDA, "CUDA: %s", cudaGetErrorString(e));
   return HSL_OK;
 }
 
@@ -933,26 +934,29 @@ int hsl_allgather_costs_host(void* nccl_comm, int nranks, const double* local, i
 }
 
 int hsl_dfma_probe(int blocks, int threads, int iters, double* tflops, float* ms) {
-  double* d = nullptr;
-  HSL_CUDA(cudaMalloc(&d, sizeof(double) * blocks * threads));
-  cudaEvent_t e0, e1;
-  HSL_CUDA(cudaEventCreate(&e0));
-  HSL_CUDA(cudaEventCreate(&e1));
-  HSL_CUDA(hsl_launch_dfma_probe(d, blocks, threads, iters, nullptr));  // warm-up
-  HSL_CUDA(cudaDeviceSynchronize());
+  if (blocks < 1 || threads < 1 || threads > 1024 || iters < 1 || (size_t)blocks * (size_t)threads > ((size_t)1 << 28))
+    return set_err(HSL_ERR_ARG, "bad argument (blocks, iters >= 1, 1 <= threads <= 1024, blocks * threads <= 2^28)");
+  DevBuf d;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
   float best = 1e30f;
-  for (int rep = 0; rep < 5; rep++) {
-    HSL_CUDA(cudaEventRecord(e0, nullptr));
-    HSL_CUDA(hsl_launch_dfma_probe(d, blocks, threads, iters, nullptr));
-    HSL_CUDA(cudaEventRecord(e1, nullptr));
-    HSL_CUDA(cudaEventSynchronize(e1));
+  cudaError_t e = d.need(sizeof(double) * (size_t)blocks * (size_t)threads);
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e == cudaSuccess) e = hsl_launch_dfma_probe((double*)d.p, blocks, threads, iters, nullptr);  // warm-up
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  for (int rep = 0; rep < 5 && e == cudaSuccess; rep++) {
+    e = cudaEventRecord(e0, nullptr);
+    if (e == cudaSuccess) e = hsl_launch_dfma_probe((double*)d.p, blocks, threads, iters, nullptr);
+    if (e == cudaSuccess) e = cudaEventRecord(e1, nullptr);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
     float t = 0;
-    HSL_CUDA(cudaEventElapsedTime(&t, e0, e1));
-    if (t < best) best = t;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, e0, e1);
+    if (e == cudaSuccess && t < best) best = t;
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(d);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  d.release();
+  if (e != cudaSuccess) return set_err(HSL_ERR_CUDA, "CUDA: %s", cudaGetErrorString(e));
   if (ms) *ms = best;
   if (tflops) *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
   return HSL_OK;

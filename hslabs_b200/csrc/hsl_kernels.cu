@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <mutex>
 
 #include "hsl_forces.h"
 #include "hsl_frame.h"
@@ -505,23 +506,31 @@ template <int NF, int FB, int AXP = HSL_AXP_GENERIC>
 cudaError_t launch_gait_pipe(const HslModelPod& M, const HslFrameArgs& A, cudaStream_t st) {
   const size_t smem = (size_t)HslPipeSmem<NF, FB>::doubles_per_slot(M.ntrunk) * FB * sizeof(double);
   auto kern = hsl_gait_pipe_kernel<NF, FB, AXP>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  cudaError_t e = cudaSuccess;
   const int64_t slots = A.n_cand * (A.n_t + 4);
   int64_t n_tiles = (slots - 4 + (FB - 4) - 1) / (FB - 4);
   if (n_tiles < 1) n_tiles = 1;
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  // persistent grid = SMs x co-resident blocks of THIS kernel on THE CURRENT device: queried once per (kernel instance, device)
+  struct DevInfo { int sms, per_sm; size_t smem; };
+  static DevInfo info[64];          // zero-initialised; slot = device ordinal
+  static std::mutex info_mu;
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  DevInfo di = {0, 0, 0};
+  {
+    std::lock_guard<std::mutex> lk(info_mu);
+    if (dev >= 0 && dev < 64) di = info[dev];
+    if (di.sms == 0 || di.smem != smem) {  // first use on this device, or a model with another trunk-body count
+      di.smem = smem;
+      if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      cudaDeviceGetAttribute(&di.sms, cudaDevAttrMultiProcessorCount, dev);
+      if (di.sms <= 0) di.sms = 148;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&di.per_sm, kern, HSL_PIPE_ROLES(NF) * FB, smem)) != cudaSuccess) return e;
+      if (di.per_sm < 1) return cudaErrorInvalidConfiguration;
+      if (dev >= 0 && dev < 64) info[dev] = di;
+    }
   }
-  int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HSL_PIPE_ROLES(NF) * FB, smem);
-  if (e != cudaSuccess) return e;
-  if (per_sm < 1) return cudaErrorInvalidConfiguration;
-  int64_t grid = (int64_t)sms * per_sm;
+  int64_t grid = (int64_t)di.sms * di.per_sm;
   if (grid > n_tiles) grid = n_tiles;
   kern<<<(unsigned)grid, HSL_PIPE_ROLES(NF) * FB, smem, st>>>(M, A, n_tiles);
   return cudaGetLastError();

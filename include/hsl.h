@@ -63,6 +63,14 @@ size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap);
 const char* hsl_last_error(void);
 int hsl_device_count(void);
 
+/* Two deliberate differences from the reference's outputs, valid for every entry below:
+ *  - min_cfz / max_mu are taken over the feet ON THE GROUND.  periodic::analyze_contforces (periodic.cpp:347-357) loops
+ *    over all nfeet and so folds in the swing feet's contact-force slots, which hold round-off of the null-space basis
+ *    (1e-17): preset 8 reports max_mu = 350 in FP64 and 19.9 when the same code runs in __float128.
+ *  - z (contact forces) is always [3 nf], in LIK limb order, with exact zeros for feet in the air; the reference's
+ *    solve_forcetorques returns the same layout (extract_N_contact, ftsolver.cpp:276-284) but with that round-off
+ *    in the swing-foot slots. */
+
 /* modelplayer::measure_cot over a batch (player.cpp:269-285 inside the sweep of player.cpp:311-321):
  * candidates -> cost of transport, work per period, min contact z-force, max friction ratio.
  * d_params [n_cand][13], outputs [n_cand] (any output may be NULL); all DEVICE pointers. */

@@ -75,9 +75,45 @@ def launches(rnd):
     print("\n".join(lines[-7:]))
 
 
+ENTRY_WANT = WANT[:8] + ['sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__inst_executed.sum',
+                         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active',
+                         'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+                         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct',
+                         'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores', 'smsp__average_warp_latency_per_inst_issued.ratio',
+                         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+                         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio']
+
+
+def entries(rnd, stem, header, keep=None):
+    """gpurun_out/<round>_<stem>.ncu-rep -> profiles/<round>_ncu_<stem>_summary.txt: the first capture of every distinct kernel."""
+    rep = os.path.join(ROOT, "gpurun_out", "%s_%s.ncu-rep" % (rnd, stem))
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    ik = hdr.index('Kernel Name')
+    seen, out = set(), ['# ' + h for h in header] + ['']
+    for r in rows[2:]:
+        name = re.sub(r'\(.*', '', r[ik])
+        key = (name, r[hdr.index('launch__grid_size')])
+        if key in seen or (keep and not any(k in name for k in keep)):
+            continue
+        seen.add(key)
+        for w in ENTRY_WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                out.append('%-95s %-16s %s' % (w, units[i], r[i]))
+        out.append('')
+    open(os.path.join(ROOT, "profiles", "%s_ncu_%s_summary.txt" % (rnd, stem)), "w").write("\n".join(out) + "\n")
+    print("\n".join(out))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--round", default="r01")
+    ap.add_argument("--entries", default="", help="stem of an extra capture (gpurun_out/<round>_<stem>.ncu-rep) to summarise per kernel")
     a = ap.parse_args()
-    full(a.round)
-    launches(a.round)
+    if a.entries:
+        entries(a.round, a.entries, ["ncu --set full --clock-control none --import-source on ... python tools/profile_entries.py (see tools/profile_r02.sh)"])
+    else:
+        full(a.round)
+        launches(a.round)
