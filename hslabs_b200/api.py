@@ -88,6 +88,7 @@ def _load():
     lib.hsl_model_tables.argtypes = [vp] + [vp] * 6
     lib.hsl_fall_sweep_host.argtypes = [vp, i64, vp, C.c_double, C.c_double, i32, vp, vp, C.c_double, C.c_double] + [vp] * 6
     lib.hsl_select_topk.argtypes = [vp, i64, i32, vp, vp, vp]
+    lib.hsl_set_fall_variant.argtypes = [vp, i32]
     _lib = lib
     return lib
 
@@ -98,7 +99,7 @@ def exported_symbols():
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_get_tuning", "hsl_set_kernel_timing", "hsl_last_kernel_ms", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
-            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host"]
+            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host", "hsl_set_fall_variant"]
 
 
 class _Pinned:
@@ -305,6 +306,10 @@ class Model:
         q = np.empty((n, self.config_dim)); status = np.empty(n, np.int32)
         _check(_load().hsl_ik_records_host(self._h, n, _p(rec), flags, _p(q), _p(status)))
         return dict(q=q, status=status)
+
+    def set_fall_variant(self, variant):
+        """Kernel of fall_sweep: 1 (default) a warp per world, 0 a thread per world."""
+        _check(_load().hsl_set_fall_variant(self._h, int(variant)))
 
     def fall_sweep(self, params, n_steps, kick_step=None, kick_dv=None, play_dt=0.02, t0=0.0, hc=0.7, tmin=0.1, n_worlds=None, want_traj=False):
         """hsl_fall_sweep_host: n_worlds copies of the reference's position-control loop with one torso kick each

@@ -62,6 +62,7 @@ struct HslModel {
   bool sim_ok = false;
   double total_mass;
   int fb = 64, maxreg = 128;
+  int fall_variant = 1;  // fall sweep: 1 = a warp per world (hsl_fall_warp.cuh), 0 = a thread per world (hsl_fall_world.h)
   int64_t max_slots = (int64_t)1 << 26;  // frame slots per launch (hsl_set_max_slots)
   int64_t launches = 0;
   bool rec_on = false;           // pergensetup::rec_transform_flag
@@ -176,6 +177,11 @@ int hsl_get_tuning(const HslModel* m, int* fb, int* maxreg) {
   if (!m) return set_err(HSL_ERR_ARG, "null model");
   if (fb) *fb = m->fb;
   if (maxreg) *maxreg = m->maxreg;
+  return HSL_OK;
+}
+int hsl_set_fall_variant(HslModel* m, int variant) {
+  if (!m || (variant != 0 && variant != 1)) return set_err(HSL_ERR_ARG, "fall sweep kernel: 0 (a thread per world) or 1 (a warp per world)");
+  m->fall_variant = variant;
   return HSL_OK;
 }
 int hsl_set_max_slots(HslModel* m, int64_t max_slots) {
@@ -833,7 +839,7 @@ int hsl_fall_sweep_host(HslModel* m, int64_t n_worlds, const double* params, dou
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   HSL_CUDA_F(cudaEventCreate(&e0)); HSL_CUDA_F(cudaEventCreate(&e1));
   HSL_CUDA_F(cudaEventRecord(e0, st));
-  cudaError_t le = hsl_launch_fall(m->sim, A, st);
+  cudaError_t le = hsl_launch_fall(m->sim, A, m->fall_variant, st);
   cudaEventRecord(e1, st);
   m->launches += 3;
   if (le == cudaSuccess) le = cudaStreamSynchronize(st);

@@ -24,6 +24,7 @@
 #include <stdint.h>
 
 #include "hsl_fall_world.h"
+#include "hsl_fall_warp.cuh"
 
 namespace {
 
@@ -45,7 +46,12 @@ __global__ void hsl_fall_ctrl_kernel(int n_t, int nmotor, double dt, const doubl
 }
 
 }  // namespace
-cudaError_t hsl_launch_fall(const HslSimPod& S, const HslFallArgs& A, cudaStream_t st) {
+cudaError_t hsl_launch_fall(const HslSimPod& S, const HslFallArgs& A, int variant, cudaStream_t st) {
+  if (variant == 1) {
+    const int64_t blocks = (A.n_worlds + hsl_fall_warp::WARPS_PER_BLOCK - 1) / hsl_fall_warp::WARPS_PER_BLOCK;
+    hsl_fall_warp::hsl_fall_warp_kernel<<<(unsigned)blocks, 32 * hsl_fall_warp::WARPS_PER_BLOCK, 0, st>>>(S, A);
+    return cudaGetLastError();
+  }
   const int64_t blocks = (A.n_worlds + HSL_FALL_THREADS - 1) / HSL_FALL_THREADS;
   cudaError_t e = cudaFuncSetAttribute(hsl_fall_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0);  // all of it to L1: local memory is the working set
   (void)e;

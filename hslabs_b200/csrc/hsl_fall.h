@@ -28,6 +28,6 @@ typedef struct HslFallArgs {
   double* traj;                  // optional [W][n_steps][3] torso COM after every step
 } HslFallArgs;
 
-cudaError_t hsl_launch_fall(const HslSimPod& S, const HslFallArgs& A, cudaStream_t st);
+cudaError_t hsl_launch_fall(const HslSimPod& S, const HslFallArgs& A, int variant, cudaStream_t st);  // 1: a warp per world, 0: a thread per world
 cudaError_t hsl_launch_fall_ctrl(int n_t, int nmotor, double dt, const double* q_cm, const double* tau_cm, double* ctrl, cudaStream_t st);
 void hsl_sim_state_from_frames(const HslSimPod* sim, const double* A, double* pos, double* quat);

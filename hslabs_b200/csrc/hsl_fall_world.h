@@ -218,10 +218,8 @@ HSL_HD void fall_world(const HslSimPod& S, const HslFallArgs& A, int64_t wi, Wor
         w.rkind[m] = R_HANG; w.rown[m] = (unsigned char)j; w.rk[m] = 0; w.rhs[m] = kerp * dot3(bb, w.jp[j]); m++;
         w.rkind[m] = R_HANG; w.rown[m] = (unsigned char)j; w.rk[m] = 1; w.rhs[m] = kerp * dot3(bb, w.jq[j]); m++;
       } else {
-        double nofs[3] = {-J.offset[0], -J.offset[1], -J.offset[2]};
         double ofs_w[3];
         rot(w.q[b1], J.offset, ofs_w);  // ofs = R1 * offset, offset = R1^T (p1 - p2) in the zero configuration
-        (void)nofs;
         for (int k = 0; k < 3; k++) w.ja1[j][k] = ofs_w[k];
         for (int k = 0; k < 3; k++) {
           w.rkind[m] = R_FPOS; w.rown[m] = (unsigned char)j; w.rk[m] = (unsigned char)k;

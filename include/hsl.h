@@ -192,6 +192,9 @@ int hsl_get_tuning(const HslModel* m, int* fb, int* maxreg);  /* the variant in 
  * slots (a candidate takes n_t + 4); default 2^26 (~2 GB of per-frame workspace), bounds 5 .. 2^31 - 1.  Results do
  * not depend on the chunking. */
 int hsl_set_max_slots(HslModel* m, int64_t max_slots);
+/* hsl_fall_sweep_host kernel: 1 (default) a warp per world with the world in registers, 0 a thread per world (the
+ * host-emulatable form tests/hostcheck runs on the CPU); same arithmetic and row order, results agree world by world. */
+int hsl_set_fall_variant(HslModel* m, int variant);
 int64_t hsl_launch_count(const HslModel* m);                  /* kernels launched through this handle so far */
 /* Measurement: with timing on, hsl_eval_gaits* brackets its three kernels (candidate setup, per-frame kernel, per-candidate
  * finish) with CUDA events on the launching stream; hsl_last_kernel_ms waits for the last chunk evaluated on this handle and

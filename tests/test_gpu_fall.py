@@ -81,3 +81,29 @@ def test_fall_statistics_against_the_cpu_stepper(hsl, tmp_path):
     assert not calm["fell"].any() and np.abs(calm["final_z"] - 0.8).max() < 0.02
     hard = hsl.Model(xml).fall_sweep(params, n_steps, np.full(4, 20, np.int32), np.tile([0.0, 40.0, 0.0], (4, 1)))
     assert hard["fell"].all()
+
+
+@pytest.mark.parametrize("pid", [8, 1])
+def test_warp_per_world_kernel_equals_the_thread_per_world_kernel(hsl, pid):
+    """The two kernels of the sweep (a warp per world with the world in registers, hsl_fall_warp.cuh; a thread per world,
+    hsl_fall_world.h -- the source the CPU tier emulates) state the same arithmetic in the same order: same torso paths."""
+    params, name = hsl.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    rng = np.random.default_rng(77 + pid)
+    w, n_steps = 96, 200
+    mag, th = rng.uniform(0, 16, w), rng.uniform(0, 2 * np.pi, w)
+    kicks = np.stack([mag * np.cos(th), mag * np.sin(th), rng.uniform(-2, 2, w)], axis=1)
+    ks = rng.integers(5, 150, w).astype(np.int32)
+    ks[:3] = -1
+    m = hsl.Model(xml)
+    m.set_fall_variant(0)
+    a = m.fall_sweep(params, n_steps, ks, kicks, want_traj=True)
+    m.set_fall_variant(1)
+    b = m.fall_sweep(params, n_steps, ks, kicks, want_traj=True)
+    d = np.abs(a["traj"] - b["traj"]).max()
+    print("preset %d: max |traj difference| %.3g over %d worlds x %d steps; kernel %.2f ms (thread) vs %.2f ms (warp)" %
+          (pid, d, w, n_steps, a["kernel_ms"], b["kernel_ms"]))
+    assert np.array_equal(a["fell"], b["fell"]) and np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["t_end"], b["t_end"])
+    assert d < 1e-9
+    assert a["fell"].any() and not a["fell"].all()
