@@ -47,9 +47,12 @@ __global__ void hsl_fall_ctrl_kernel(int n_t, int nmotor, double dt, const doubl
 
 }  // namespace
 cudaError_t hsl_launch_fall(const HslSimPod& S, const HslFallArgs& A, int variant, cudaStream_t st) {
-  if (variant == 1) {
+  if (variant >= 1) {
     const int64_t blocks = (A.n_worlds + hsl_fall_warp::WARPS_PER_BLOCK - 1) / hsl_fall_warp::WARPS_PER_BLOCK;
-    hsl_fall_warp::hsl_fall_warp_kernel<<<(unsigned)blocks, 32 * hsl_fall_warp::WARPS_PER_BLOCK, 0, st>>>(S, A);
+    const unsigned th = 32 * hsl_fall_warp::WARPS_PER_BLOCK;
+    if (variant == 1) hsl_fall_warp::hsl_fall_warp_kernel<2><<<(unsigned)blocks, th, 0, st>>>(S, A);
+    else if (variant == 2) hsl_fall_warp::hsl_fall_warp_kernel<3><<<(unsigned)blocks, th, 0, st>>>(S, A);
+    else hsl_fall_warp::hsl_fall_warp_kernel<4><<<(unsigned)blocks, th, 0, st>>>(S, A);
     return cudaGetLastError();
   }
   const int64_t blocks = (A.n_worlds + HSL_FALL_THREADS - 1) / HSL_FALL_THREADS;

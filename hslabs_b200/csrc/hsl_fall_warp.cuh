@@ -31,8 +31,8 @@ constexpr int MAXR = 6 * HSL_MAX_BODIES + 3 * HSL_FALL_MAX_CONTACTS;  // 240 row
 
 struct WorldSmem {
   double rhs[MAXR], Ad[MAXR], lam[MAXR];
-  unsigned char kind[MAXR], owner[MAXR], comp[MAXR];
-  short order[MAXR];
+  uint32_t sched[MAXR];       // the visiting order: row | owner lane << 8 | parent lane << 13 | case << 18, shuffled in place
+  unsigned char swp[MAXR];    // the swap partners of one shuffle
 };
 
 __device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
@@ -41,9 +41,110 @@ __device__ __forceinline__ double sel3(const double* v, int k) { return k == 0 ?
 __device__ __forceinline__ void add_at(double* v, int k, double x) { v[0] += (k == 0) ? x : 0.0; v[1] += (k == 1) ? x : 0.0; v[2] += (k == 2) ? x : 0.0; }
 __device__ __forceinline__ void unit(int k, double* e) { e[0] = (k == 0); e[1] = (k == 1); e[2] = (k == 2); }
 
-enum { R_BALL = 0, R_HANG = 1, R_FPOS = 2, R_FANG = 3, R_CONT = 4 };
+// Row cases of the sweep: kind and component in one number, so that every case is straight-line code on named registers.
+enum { C_BALL = 0, C_HANG = 3, C_FPOS = 5, C_FANG = 8, C_CONT = 11 };
+__device__ __forceinline__ uint32_t pack(int row, int owner, int parent, int cs) { return (uint32_t)row | ((uint32_t)owner << 8) | ((uint32_t)parent << 13) | ((uint32_t)cs << 18); }
 
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK)
+// What a lane keeps of its body during the sweep.  A joint row couples the lane that owns it (the child body) with the
+// parent's lane: the owner reads the parent's accumulator components it needs through shuffles, updates lambda and its own
+// accumulator, and hands the parent its finished increments (the owner knows the parent's inverse mass / inertia).
+// The expressions are those of hsl_fall_world.h's row_dot / row_apply with the unit vector e_k multiplied out:
+// (a x e_k) has components 0, a[k+2], -a[k+1] at k, k+1, k+2 (cyclic), (e_k x a) the negatives.
+struct Lane {
+  double fcl[3], fca[3];                 // constraint-force accumulator (M^-1 J^T lambda): linear, angular
+  double ga[3], gb[3], gp[3], gq[3];     // hinge: anchors a1 (own), a2 (parent), plane-space vectors; fixed: ga = ofs
+  double cc[3];                          // contact lever arm
+  double im, ii, pim, pii;               // inverse mass / inertia: own, parent's
+};
+
+__device__ __forceinline__ double sor_delta(WorldSmem& W, int i, double cfm, double jf, double& lam) {
+  const double Ad = W.Ad[i];
+  lam = W.lam[i];
+  return W.rhs[i] - lam * (Ad * cfm) - Ad * jf;
+}
+
+template <int K>
+__device__ __forceinline__ void row_ball(Lane& L, WorldSmem& W, int i, int lane, int own, int po, double cfm) {
+  constexpr int K1 = (K + 1) % 3, K2 = (K + 2) % 3;
+  const double pl = shfl(L.fcl[K], po), pa1 = shfl(L.fca[K1], po), pa2 = shfl(L.fca[K2], po);
+  double x0 = 0, x1 = 0, x2 = 0;
+  if (lane == own) {
+    const double t = L.fca[K1] * L.ga[K2] - L.fca[K2] * L.ga[K1];
+    const double tp = pa1 * L.gb[K2] - pa2 * L.gb[K1];
+    double lam;
+    const double delta = sor_delta(W, i, cfm, (L.fcl[K] + t) - pl - tp, lam);
+    W.lam[i] = lam + delta;
+    L.fcl[K] += L.im * delta;
+    L.fca[K1] += L.ii * L.ga[K2] * delta;
+    L.fca[K2] -= L.ii * L.ga[K1] * delta;
+    x0 = L.pim * delta; x1 = L.pii * L.gb[K2] * delta; x2 = L.pii * L.gb[K1] * delta;
+  }
+  x0 = shfl(x0, own); x1 = shfl(x1, own); x2 = shfl(x2, own);
+  if (lane == po) { L.fcl[K] -= x0; L.fca[K1] -= x1; L.fca[K2] += x2; }
+}
+__device__ __forceinline__ void row_hang(Lane& L, const double (&u)[3], WorldSmem& W, int i, int lane, int own, int po, double cfm) {
+  double pa[3], x[3] = {0, 0, 0};
+  shfl3(L.fca, po, pa);
+  if (lane == own) {
+    double lam;
+    const double delta = sor_delta(W, i, cfm, dot3(u, L.fca) - dot3(u, pa), lam);
+    W.lam[i] = lam + delta;
+#pragma unroll
+    for (int c = 0; c < 3; c++) { L.fca[c] += L.ii * u[c] * delta; x[c] = L.pii * u[c] * delta; }
+  }
+  double y[3];
+  shfl3(x, own, y);
+  if (lane == po) { L.fca[0] -= y[0]; L.fca[1] -= y[1]; L.fca[2] -= y[2]; }
+}
+template <int K>
+__device__ __forceinline__ void row_fpos(Lane& L, WorldSmem& W, int i, int lane, int own, int po, double cfm) {
+  constexpr int K1 = (K + 1) % 3, K2 = (K + 2) % 3;
+  const double pl = shfl(L.fcl[K], po), pa1 = shfl(L.fca[K1], po), pa2 = shfl(L.fca[K2], po);
+  double x0 = 0, x1 = 0, x2 = 0;
+  if (lane == own) {   // owner = b2 (the child), parent = b1; ga = ofs
+    const double t = L.ga[K1] * pa2 - L.ga[K2] * pa1;
+    double lam;
+    const double delta = sor_delta(W, i, cfm, pl + t - L.fcl[K], lam);
+    W.lam[i] = lam + delta;
+    L.fcl[K] -= delta * L.im;
+    x0 = delta * L.pim; x1 = L.ga[K2] * delta * L.pii; x2 = L.ga[K1] * delta * L.pii;
+  }
+  x0 = shfl(x0, own); x1 = shfl(x1, own); x2 = shfl(x2, own);
+  if (lane == po) { L.fcl[K] += x0; L.fca[K1] -= x1; L.fca[K2] += x2; }
+}
+template <int K>
+__device__ __forceinline__ void row_fang(Lane& L, WorldSmem& W, int i, int lane, int own, int po, double cfm) {
+  const double pa = shfl(L.fca[K], po);
+  double x0 = 0;
+  if (lane == own) {
+    double lam;
+    const double delta = sor_delta(W, i, cfm, pa - L.fca[K], lam);
+    W.lam[i] = lam + delta;
+    L.fca[K] -= delta * L.ii;
+    x0 = delta * L.pii;
+  }
+  x0 = shfl(x0, own);
+  if (lane == po) L.fca[K] += x0;
+}
+// contact with the plane z = 0: directions n = (0,0,1), t1 = (0,-1,0), t2 = (1,0,0) (dPlaneSpace of n); one body, no exchange
+template <int K>
+__device__ __forceinline__ void row_cont(Lane& L, WorldSmem& W, int i, double cfm) {
+  double jf;
+  if (K == 0) jf = L.fcl[2] + (L.cc[1] * L.fca[0] - L.cc[0] * L.fca[1]);
+  else if (K == 1) jf = -L.fcl[1] + (L.cc[2] * L.fca[0] - L.cc[0] * L.fca[2]);
+  else jf = L.fcl[0] + (L.cc[2] * L.fca[1] - L.cc[1] * L.fca[2]);
+  double lam;
+  double delta = sor_delta(W, i, cfm, jf, lam);
+  double nl = lam + delta;
+  if (K == 0 && nl < 0) { delta = -lam; nl = 0; }   // lo = 0 on the normal row; friction rows unbounded (mu = infinity)
+  W.lam[i] = nl;
+  if (K == 0) { L.fcl[2] += delta * L.im; L.fca[0] += L.cc[1] * delta * L.ii; L.fca[1] -= L.cc[0] * delta * L.ii; }
+  else if (K == 1) { L.fcl[1] -= delta * L.im; L.fca[0] += L.cc[2] * delta * L.ii; L.fca[2] -= L.cc[0] * delta * L.ii; }
+  else { L.fcl[0] += delta * L.im; L.fca[1] += L.cc[2] * delta * L.ii; L.fca[2] -= L.cc[1] * delta * L.ii; }
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MINB)
 hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant__ HslFallArgs A) {
   __shared__ WorldSmem smem[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -79,20 +180,24 @@ hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant_
   if (A.kick_dv) for (int k = 0; k < 3; k++) kick[k] = A.kick_dv[3 * wi + k];
   const double h = A.play_dt, fps = 1.0 / h, kerp = fps * A.erp, wcfm = A.cfm * fps, scfm = A.soft_cfm * fps, sor_w = 1.3;
   double play_t = A.play_t0;
-  uint32_t seed = 0;
+  uint32_t seed = 0, lcg_a = 1, lcg_c = 0;   // ODE's dRand: seed' = a seed + c; after lane + 1 draws: lcg_a seed + lcg_c
+  for (int j = 0; j <= lane; j++) { lcg_c = 1664525u * lcg_c + 1013904223u; lcg_a *= 1664525u; }
   int fell = 0, status = 0, step = 0;
   double t_fall = 0;
   for (; step < A.n_steps; step++) {
     const double z0 = shfl(pos[2], 0);
     if (play_t >= A.tmin && z0 < A.hc) { fell = 1; t_fall = play_t; break; }   // fall_check (warp-uniform)
     double fel[3] = {0, 0, -sb.mass * A.gravity}, fea[3] = {0, 0, 0};          // external force / torque on this body
-    double fcl[3] = {0, 0, 0}, fca[3] = {0, 0, 0};                              // constraint-force accumulator (M^-1 J^T lambda)
+    Lane L;
+    L.im = im; L.ii = ii; L.pim = pim; L.pii = pii;
+    double (&fcl)[3] = L.fcl, (&fca)[3] = L.fca, (&ga)[3] = L.ga, (&gb)[3] = L.gb, (&gp)[3] = L.gp, (&gq)[3] = L.gq, (&cc)[3] = L.cc;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { fcl[k] = 0; fca[k] = 0; ga[k] = 0; gb[k] = 0; gp[k] = 0; gq[k] = 0; cc[k] = 0; }
     // ---- joint rows of this lane (all joints at once): geometry, control torque, right-hand sides
     double ppos[3], pq[4], pav[3];
     shfl3(pos, par, ppos);
     pq[0] = shfl(q[0], par); pq[1] = shfl(q[1], par); pq[2] = shfl(q[2], par); pq[3] = shfl(q[3], par);
     shfl3(av, par, pav);
-    double ga[3] = {0, 0, 0}, gb[3] = {0, 0, 0}, gp[3] = {0, 0, 0}, gq[3] = {0, 0, 0};  // hinge: a1, a2, p, q ; fixed: ga = ofs
     double crow[6] = {0, 0, 0, 0, 0, 0};                                               // c of this joint's rows
     double tq[3] = {0, 0, 0};                                                           // torque this lane's hinge puts on its parent (negated below)
     const int tsi = (int)(play_t / h + .5), tm = tsi % A.n_t;
@@ -146,7 +251,7 @@ hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant_
     if (lane == 0 && step == kick_step) { fel[0] += kick[0] * fps; fel[1] += kick[1] * fps; fel[2] += kick[2] * fps; }
     // ---- contact of this body with the ground plane z = 0
     bool hasc = false;
-    double cc[3] = {0, 0, 0}, cnorm = 0;
+    double cnorm = 0;
     if (body && sb.geom != 0) {
       double e0[3], p[3];
       if (sb.geom == 2) {
@@ -201,7 +306,7 @@ hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant_
         diag += pim + dot3(u, u) / pinertia;
         const double Ad = sor_w / (diag + wcfm);
         W.Ad[rbase + k] = Ad; W.rhs[rbase + k] = (crow[k] * fps - acc) * Ad; W.lam[rbase + k] = 0;
-        W.kind[rbase + k] = R_BALL; W.owner[rbase + k] = (unsigned char)lane; W.comp[rbase + k] = (unsigned char)k;
+        W.sched[rbase + k] = pack(rbase + k, lane, par, C_BALL + k);
       }
 #pragma unroll
       for (int r = 0; r < 2; r++) {
@@ -209,7 +314,7 @@ hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant_
         const double acc = dot3(u, va) - dot3(u, pva);
         const double Ad = sor_w / ((ii + pii) + wcfm);
         W.Ad[rbase + 3 + r] = Ad; W.rhs[rbase + 3 + r] = (crow[3 + r] * fps - acc) * Ad; W.lam[rbase + 3 + r] = 0;
-        W.kind[rbase + 3 + r] = R_HANG; W.owner[rbase + 3 + r] = (unsigned char)lane; W.comp[rbase + 3 + r] = (unsigned char)r;
+        W.sched[rbase + 3 + r] = pack(rbase + 3 + r, lane, par, C_HANG + r);
       }
     } else if (jkind == 2) {
       double t1[3];
@@ -223,14 +328,14 @@ hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant_
         const double diag = pim + dot3(u, u) / pinertia + im;
         const double Ad = sor_w / (diag + wcfm);
         W.Ad[rbase + k] = Ad; W.rhs[rbase + k] = (crow[k] * fps - acc) * Ad; W.lam[rbase + k] = 0;
-        W.kind[rbase + k] = R_FPOS; W.owner[rbase + k] = (unsigned char)lane; W.comp[rbase + k] = (unsigned char)k;
+        W.sched[rbase + k] = pack(rbase + k, lane, par, C_FPOS + k);
       }
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         const double acc = pva[k] - va[k];
         const double Ad = sor_w / ((pii + ii) + wcfm);
         W.Ad[rbase + 3 + k] = Ad; W.rhs[rbase + 3 + k] = (crow[3 + k] * fps - acc) * Ad; W.lam[rbase + 3 + k] = 0;
-        W.kind[rbase + 3 + k] = R_FANG; W.owner[rbase + 3 + k] = (unsigned char)lane; W.comp[rbase + 3 + k] = (unsigned char)k;
+        W.sched[rbase + 3 + k] = pack(rbase + 3 + k, lane, par, C_FANG + k);
       }
     }
     if (hasc) {
@@ -243,113 +348,51 @@ hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant_
         const double cfm = (k == 0) ? scfm : wcfm;
         const double Ad = sor_w / (diag + cfm);
         W.Ad[cbase + k] = Ad; W.rhs[cbase + k] = (((k == 0) ? cnorm : 0.0) * fps - acc) * Ad; W.lam[cbase + k] = 0;
-        W.kind[cbase + k] = R_CONT; W.owner[cbase + k] = (unsigned char)lane; W.comp[cbase + k] = (unsigned char)k;
+        W.sched[cbase + k] = pack(cbase + k, lane, lane, C_CONT + k);
       }
     }
-    for (int i = lane; i < m; i += 32) W.order[i] = (short)i;
     __syncwarp();
     // ---- SOR projected Gauss-Seidel over the rows in ODE's order.  Inside the sweep x / mass is written x * (1 / mass):
     // the same bits for the unit masses and inertias every reference body has (dynrec.cpp:62-68 never sets a mass), one
     // rounding apart otherwise, and no division routine on the sequential path.
     for (int it = 0; it < A.iterations; it++) {
       if ((it & 7) == 0) {
+        // ODE's shuffle: for i = 1 .. m-1 swap order[i] with order[dRandInt(i + 1)].  The m - 1 draws of the LCG come from all
+        // lanes at once (jump-ahead constants per lane), the swaps themselves are a chain and stay on lane 0.
+        for (int base = 0; base + 1 < m; base += 32) {
+          const int i = base + lane + 1;
+          const uint32_t si = lcg_a * seed + lcg_c;                       // the seed after lane + 1 more draws
+          if (i < m) W.swp[i] = (unsigned char)(int)((double)si * ((double)(i + 1) / 4294967296.0));
+          const int last = (m - 1 - base < 32) ? (m - 2 - base) : 31;    // lane that made the last draw of this round
+          seed = __shfl_sync(FULL, si, last);
+        }
+        __syncwarp();
         if (lane == 0) {
           for (int i = 1; i < m; i++) {
-            seed = 1664525u * seed + 1013904223u;   // ODE dRand
-            const int s = (int)((double)seed * ((double)(i + 1) / 4294967296.0));
-            const short tmp = W.order[i]; W.order[i] = W.order[s]; W.order[s] = tmp;
+            const int s = W.swp[i];
+            const uint32_t tmp = W.sched[i]; W.sched[i] = W.sched[s]; W.sched[s] = tmp;
           }
         }
-        seed = __shfl_sync(FULL, seed, 0);
         __syncwarp();
       }
       for (int oi = 0; oi < m; oi++) {
-        const int i = W.order[oi];
-        const int kind = W.kind[i], own = W.owner[i], k = W.comp[i];
-        const bool mine = (lane == own);
-        double delta = 0;
-        if (kind == R_CONT) {   // one body: no exchange
-          if (mine) {
-            double t[3];
-            cross3(cc, cdir[k], t);
-            const double jf = dot3(cdir[k], fcl) + dot3(t, fca);
-            const double Ad = W.Ad[i], lam = W.lam[i];
-            delta = W.rhs[i] - lam * (Ad * ((k == 0) ? scfm : wcfm)) - Ad * jf;
-            double nl = lam + delta;
-            if (k == 0 && nl < 0) { delta = -lam; nl = 0; }
-            W.lam[i] = nl;
-#pragma unroll
-            for (int c = 0; c < 3; c++) { fcl[c] += cdir[k][c] * delta * im; fca[c] += t[c] * delta * ii; }
-          }
-          continue;
-        }
-        const int po = __shfl_sync(FULL, par, own);          // the owner's parent lane
-        double pfl[3], pfa[3];
-        shfl3(fcl, po, pfl);
-        shfl3(fca, po, pfa);
-        double gv[3] = {0, 0, 0};                             // what the parent needs for its share of the update
-        if (mine) {
-          double jf;
-          if (kind == R_BALL) {
-            double t1[3], t2[3];
-            cross3(fca, ga, t1);
-            cross3(pfa, gb, t2);
-            jf = (sel3(fcl, k) + sel3(t1, k)) - sel3(pfl, k) - sel3(t2, k);
-            gv[0] = gb[0]; gv[1] = gb[1]; gv[2] = gb[2];
-          } else if (kind == R_HANG) {
-            const double* u = k ? gq : gp;
-            jf = dot3(u, fca) - dot3(u, pfa);
-            gv[0] = u[0]; gv[1] = u[1]; gv[2] = u[2];
-          } else if (kind == R_FPOS) {
-            double t1[3];
-            cross3(ga, pfa, t1);
-            jf = sel3(pfl, k) + sel3(t1, k) - sel3(fcl, k);
-            gv[0] = ga[0]; gv[1] = ga[1]; gv[2] = ga[2];
-          } else {
-            jf = sel3(pfa, k) - sel3(fca, k);
-          }
-          const double Ad = W.Ad[i], lam = W.lam[i];
-          delta = W.rhs[i] - lam * (Ad * wcfm) - Ad * jf;
-          W.lam[i] = lam + delta;                             // joint rows are unbounded
-          // the owner's share of fc += M^-1 J^T delta
-          double e[3], t[3];
-          unit(k, e);
-          if (kind == R_BALL) {
-            add_at(fcl, k, im * delta);
-            cross3(ga, e, t);
-#pragma unroll
-            for (int c = 0; c < 3; c++) fca[c] += ii * t[c] * delta;
-          } else if (kind == R_HANG) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) fca[c] += ii * gv[c] * delta;
-          } else if (kind == R_FPOS) {
-            add_at(fcl, k, -(delta * im));
-          } else {
-            add_at(fca, k, -(delta * ii));
-          }
-        }
-        delta = shfl(delta, own);
-        double g3[3];
-        shfl3(gv, own, g3);
-        if (lane == po) {   // the parent's share
-          double e[3], t[3];
-          unit(k, e);
-          if (kind == R_BALL) {
-            add_at(fcl, k, -(im * delta));
-            cross3(e, g3, t);
-#pragma unroll
-            for (int c = 0; c < 3; c++) fca[c] += ii * t[c] * delta;
-          } else if (kind == R_HANG) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) fca[c] -= ii * g3[c] * delta;
-          } else if (kind == R_FPOS) {
-            add_at(fcl, k, delta * im);
-            cross3(e, g3, t);
-#pragma unroll
-            for (int c = 0; c < 3; c++) fca[c] += t[c] * delta * ii;
-          } else {
-            add_at(fca, k, delta * ii);
-          }
+        const uint32_t d = W.sched[oi];
+        const int i = d & 255, own = (d >> 8) & 31, po = (d >> 13) & 31;
+        switch (d >> 18) {
+          case C_BALL + 0: row_ball<0>(L, W, i, lane, own, po, wcfm); break;
+          case C_BALL + 1: row_ball<1>(L, W, i, lane, own, po, wcfm); break;
+          case C_BALL + 2: row_ball<2>(L, W, i, lane, own, po, wcfm); break;
+          case C_HANG + 0: row_hang(L, L.gp, W, i, lane, own, po, wcfm); break;
+          case C_HANG + 1: row_hang(L, L.gq, W, i, lane, own, po, wcfm); break;
+          case C_FPOS + 0: row_fpos<0>(L, W, i, lane, own, po, wcfm); break;
+          case C_FPOS + 1: row_fpos<1>(L, W, i, lane, own, po, wcfm); break;
+          case C_FPOS + 2: row_fpos<2>(L, W, i, lane, own, po, wcfm); break;
+          case C_FANG + 0: row_fang<0>(L, W, i, lane, own, po, wcfm); break;
+          case C_FANG + 1: row_fang<1>(L, W, i, lane, own, po, wcfm); break;
+          case C_FANG + 2: row_fang<2>(L, W, i, lane, own, po, wcfm); break;
+          case C_CONT + 0: if (lane == own) row_cont<0>(L, W, i, scfm); break;
+          case C_CONT + 1: if (lane == own) row_cont<1>(L, W, i, wcfm); break;
+          default: if (lane == own) row_cont<2>(L, W, i, wcfm); break;
         }
       }
     }

@@ -16,7 +16,7 @@ for w in (int(a) for a in (sys.argv[1:] or ["16384", "131072"])):
     mag, th = rng.uniform(0, 16, w), rng.uniform(0, 2 * np.pi, w)
     kicks = np.stack([mag * np.cos(th), mag * np.sin(th), np.zeros(w)], axis=1)
     ks = rng.integers(5, 45, w).astype(np.int32)
-    for variant in (0, 1):
+    for variant in [int(v) for v in os.environ.get("FALL_VARIANTS", "0,1").split(",")]:
         m.set_fall_variant(variant)
         m.fall_sweep(params, 50, ks[:256], kicks[:256])
         r = m.fall_sweep(params, 50, ks, kicks)
