@@ -449,7 +449,7 @@ def main():
     if not args.no_extras:
         fm = hsl.Model(hsl.model_path("hexapod"))
         fparams, _ = hsl.load_preset(os.path.join(ROOT, "hslabs_b200", "models", "pgs_presets.txt"), 8)
-        fw, fsteps = 131072, 50                      # worlds per GPU (fills 148 SMs x 7 blocks x 128 threads), steps of 0.02 s
+        fw, fsteps = 131072, 50                      # worlds per GPU (55 waves of 148 SMs x 16 warps, a warp per world), steps of 0.02 s
         frng = np.random.default_rng(SEED + 77 + rank)
         mag, th = frng.uniform(0, 16, fw), frng.uniform(0, 2 * np.pi, fw)
         fk = np.stack([mag * np.cos(th), mag * np.sin(th), np.zeros(fw)], axis=1)
@@ -462,7 +462,7 @@ def main():
             line["fall_sweep"] = {"workload": "hexapod.xml preset 8 under PD position control, %d worlds per GPU x %d steps of 0.02 s, one random torso kick each (BASELINE configs[4])" % (fw, fsteps),
                                   "value": world * fw * fsteps / (f_ms * 1e-3), "unit": "world-steps/s", "kernel_ms": f_ms,
                                   "fall_rate": float(fres["fell"].mean()), "status_all_zero": bool((fres["status"] == 0).all()),
-                                  "note": "one thread per world; bound by the L2 / HBM traffic of the thread-local working set (DESIGN.md section 9)"}
+                                  "note": "one warp per world, lane = body, the world in registers; bound by the dependent chain of a Gauss-Seidel row update (DESIGN.md section 9)"}
         del fm
 
     # ------------------------------------------------------------------ CPU arm + parity of the timed batch (N = 1 only)

@@ -180,7 +180,7 @@ int hsl_get_tuning(const HslModel* m, int* fb, int* maxreg) {
   return HSL_OK;
 }
 int hsl_set_fall_variant(HslModel* m, int variant) {
-  if (!m || (variant < 0 || variant > 3)) return set_err(HSL_ERR_ARG, "fall sweep kernel: 0 (a thread per world) or 1 (a warp per world)");
+  if (!m || (variant != 0 && variant != 1)) return set_err(HSL_ERR_ARG, "fall sweep kernel: 0 (a thread per world) or 1 (a warp per world)");
   m->fall_variant = variant;
   return HSL_OK;
 }

@@ -143,8 +143,16 @@ __device__ __forceinline__ void row_cont(Lane& L, WorldSmem& W, int i, double cf
   else { L.fcl[0] += delta * L.im; L.fca[1] += L.cc[2] * delta * L.ii; L.fca[2] -= L.cc[1] * delta * L.ii; }
 }
 
-template <int MINB>
-__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, MINB)
+// Blocks of 4 warps, HSL_FALL_MINB of them per SM.  Measured on 32768 hexapod worlds x 50 steps (world-steps/s):
+//   2 blocks (255 registers, no spills) 1.77e6 | 3 (168) 2.07e6 | 4 (128) 2.56e6 | 5 (96) 2.92e6 | 6 (80) 3.21e6 | 7 (72) 3.30e6 |
+//   8 (64) 3.33e6.
+// A row update is a chain of dependent shuffles, shared-memory loads and FP64 operations, so warps in flight buy more than
+// registers do -- the state the sweep does not touch (pose, velocities, external forces) is what ptxas spills -- until
+// the issue slots fill (~75 % at 6..8 blocks; ~100 warp instructions per row update, 2.5e5 per world-step, profiles/r02_optimisation_log.md).
+#ifndef HSL_FALL_MINB
+#define HSL_FALL_MINB 6
+#endif
+__global__ void __launch_bounds__(32 * WARPS_PER_BLOCK, HSL_FALL_MINB)
 hsl_fall_warp_kernel(const __grid_constant__ HslSimPod S, const __grid_constant__ HslFallArgs A) {
   __shared__ WorldSmem smem[WARPS_PER_BLOCK];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

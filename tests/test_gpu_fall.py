@@ -56,12 +56,13 @@ def test_short_horizon_follows_the_cpu_stepper(hsl, tmp_path):
 
 
 def test_fall_statistics_against_the_cpu_stepper(hsl, tmp_path):
-    """1024 random kicks (direction uniform in the horizontal plane, |dv| U[0, 16], kick time U[0.5 s, 3.5 s)): fall rate and
-    time-to-fall histogram of the sweep kernel against the CPU stepper on the same kicks."""
+    """10240 random kicks (direction uniform in the horizontal plane, |dv| U[0, 16], kick time U[0.5 s, 3.5 s)): fall rate and
+    time-to-fall histogram of the sweep kernel against the CPU stepper on the same kicks (about 2 min of CPU stepping on the
+    16 host cores of the GPU box; HSL_FALL_STAT_WORLDS overrides the count)."""
     params, name = hsl.load_preset(PRESETS, 8)
     xml = model_xml(name)
     rng = np.random.default_rng(20261019)
-    w, n_steps = 1024, 300
+    w, n_steps = int(os.environ.get("HSL_FALL_STAT_WORLDS", "10240")), 300
     mag, th = rng.uniform(0, 16, w), rng.uniform(0, 2 * np.pi, w)
     kicks = np.stack([mag * np.cos(th), mag * np.sin(th), np.zeros(w)], axis=1)
     ks = rng.integers(25, 175, w).astype(np.int32)
