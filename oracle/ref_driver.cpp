@@ -651,9 +651,49 @@ int ref_load_preset(void* hv, const char* file, int id, double* params, char* xm
 // on the ODE shim's world stepper (oracle/shim/ode_step.cpp), driven step by step instead of through drawstuff's loop
 // so that the kick (kick_torso, player.cpp:585-605: a force dv/dt on the torso for one step) and the fall check
 // (fall_check, player.cpp:669-681: torso z < hc once play_t >= tmin) take their parameters from the caller.
+}  // extern "C" (reopened below)
+
 // params[13] as everywhere; kick_dv[3] = velocity change of the kick applied at step kick_step (< 0: never).
 // out[4] = fell (0/1), time of the fall (or end time), final torso z, steps simulated; traj (optional)
 // [n_steps][3] torso position after every step.  Needs a process in which only this model was loaded.
+namespace {
+// position_control_test up to the first step (player.cpp:358-360, 370-382): evaluates the gait, poses the robot at t0
+void fall_setup(Handle* h, const double* params, double play_dt, double t0) {
+  modelplayer* mp = h->mp;
+  mp->set_play_dt(play_dt);
+  pergensetup* pgs = make_pgs(h, params);
+  mp->ignore_reach();                          // set_fall_test does (player.cpp:785)
+  mp->set_flag("position_control", true);
+  mp->setup_per_controller(pgs, t0);
+}
+// the loop of one world from that state; b[4 + 3 n_steps]
+void fall_loop(Handle* h, double play_dt, int n_steps, int kick_step, const double* kick_dv, double hc, double tmin, double* b, bool want_traj) {
+  modelplayer* mp = h->mp;
+  dShimSeedRandom(0);                           // a fresh ODE process
+  dBodyID torso = mp->get_torso_odebody();
+  int fell = 0, step = 0;
+  double t_fall = 0;
+  for (; step < n_steps; step++) {
+    const dReal* pos = dBodyGetPosition(torso);
+    if (mp->play_t >= tmin && pos[2] < hc) { fell = 1; t_fall = mp->play_t; break; }   // fall_check
+    if (step == kick_step) {
+      double f[3] = {kick_dv[0] / play_dt, kick_dv[1] / play_dt, kick_dv[2] / play_dt};
+      mp->get_vis()->add_force(torso, f);
+    }
+    mp->step();                                 // case 6: simulate_ode()
+    if (want_traj) {
+      pos = dBodyGetPosition(torso);
+      for (int k = 0; k < 3; k++) b[4 + 3 * step + k] = pos[k];
+    }
+  }
+  b[0] = fell;
+  b[1] = fell ? t_fall : mp->play_t;
+  b[2] = dBodyGetPosition(torso)[2];
+  b[3] = step;
+}
+}  // namespace
+
+extern "C" {
 int ref_fall_run(void* hv, const double* params, double play_dt, double t0, int n_steps, int kick_step, const double* kick_dv, double hc,
                  double tmin, double* out, double* traj) {
   Handle* h = (Handle*)hv;
@@ -663,32 +703,8 @@ int ref_fall_run(void* hv, const double* params, double play_dt, double t0, int 
       nd * sizeof(double),
       [&](char* shm) {
         Quiet q;
-        double* b = (double*)shm;
-        modelplayer* mp = h->mp;
-        mp->set_play_dt(play_dt);
-        pergensetup* pgs = make_pgs(h, params);
-        mp->ignore_reach();                          // set_fall_test does (player.cpp:785)
-        mp->set_flag("position_control", true);      // position_control_test, player.cpp:358-360
-        mp->setup_per_controller(pgs, t0);
-        dShimSeedRandom(0);                           // a fresh ODE process
-        dBodyID torso = mp->get_torso_odebody();
-        int fell = 0, step = 0;
-        double t_fall = 0;
-        for (; step < n_steps; step++) {
-          const dReal* pos = dBodyGetPosition(torso);
-          if (mp->play_t >= tmin && pos[2] < hc) { fell = 1; t_fall = mp->play_t; break; }   // fall_check
-          if (step == kick_step) {
-            double f[3] = {kick_dv[0] / play_dt, kick_dv[1] / play_dt, kick_dv[2] / play_dt};
-            mp->get_vis()->add_force(torso, f);
-          }
-          mp->step();                                 // case 6: simulate_ode()
-          pos = dBodyGetPosition(torso);
-          for (int k = 0; k < 3; k++) b[4 + 3 * step + k] = pos[k];
-        }
-        b[0] = fell;
-        b[1] = fell ? t_fall : mp->play_t;
-        b[2] = dBodyGetPosition(torso)[2];
-        b[3] = step;
+        fall_setup(h, params, play_dt, t0);
+        fall_loop(h, play_dt, n_steps, kick_step, kick_dv, hc, tmin, (double*)shm, true);
       },
       [&](const char* shm) {
         const double* b = (const double*)shm;
@@ -697,42 +713,43 @@ int ref_fall_run(void* hv, const double* params, double play_dt, double t0, int 
       });
 }
 
-// W fall runs on `nprocs` forked workers (each world is its own reference process, like run_fall_test.sh's loop).
-// fell / t_end / final_z: [W].
+// W fall runs on `nprocs` forked workers.  A worker evaluates the gait and poses the robot once (the part of
+// position_control_test every world shares), then forks per world: each world steps its own copy of that pristine state,
+// as the separate runs of run_fall_test.sh's loop would.  fell / t_end / final_z: [W].
 int ref_fall_batch(void* hv, const double* params, long W, double play_dt, double t0, int n_steps, const int* kick_step, const double* kick_dv,
                    double hc, double tmin, unsigned char* fell, double* t_end, double* final_z, int nprocs) {
+  Handle* h = (Handle*)hv;
   if (g_models_loaded != 1) return -3;
   if (nprocs < 1) nprocs = 1;
   Shm shm((size_t)W * 4 * sizeof(double));
   if (!shm.p) return -1;
   double* b = (double*)shm.p;
   for (long i = 0; i < 4 * W; i++) b[i] = NAN;
-  bool was = g_isolate;
   fflush(0);
   std::vector<pid_t> pids;
   for (int w = 0; w < nprocs; w++) {
     pid_t pid = fork();
     if (pid == 0) {
       child_signals();
-      g_isolate = false;  // already in a child: run the worlds of this worker in-process, one after the other
+      Quiet q;
+      fall_setup(h, params, play_dt, t0);
+      const double zero[3] = {0, 0, 0};
       for (long i = w; i < W; i += nprocs) {
-        // every world needs the pristine post-load state: fork once more per world
         pid_t p2 = fork();
         if (p2 == 0) {
           double out[4];
-          int rc = ref_fall_run(hv, params, play_dt, t0, n_steps, kick_step ? kick_step[i] : -1, kick_dv ? kick_dv + 3 * i : params, hc, tmin, out, 0);
-          if (rc == 0) for (int k = 0; k < 4; k++) b[4 * i + k] = out[k];
-          _exit(rc == 0 ? 0 : 1);
+          fall_loop(h, play_dt, n_steps, kick_step ? kick_step[i] : -1, kick_dv ? kick_dv + 3 * i : zero, hc, tmin, out, false);
+          for (int k = 0; k < 4; k++) b[4 * i + k] = out[k];
+          _exit(0);
         }
         int st = 0;
-        waitpid(p2, &st, 0);
+        if (p2 > 0) waitpid(p2, &st, 0);
       }
       _exit(0);
     }
     if (pid > 0) pids.push_back(pid);
   }
   for (size_t i = 0; i < pids.size(); i++) { int st = 0; waitpid(pids[i], &st, 0); }
-  g_isolate = was;
   for (long i = 0; i < W; i++) { fell[i] = (unsigned char)(b[4 * i] == 1.0); t_end[i] = b[4 * i + 1]; final_z[i] = b[4 * i + 2]; }
   return 0;
 }

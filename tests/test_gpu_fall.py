@@ -57,8 +57,7 @@ def test_short_horizon_follows_the_cpu_stepper(hsl, tmp_path):
 
 def test_fall_statistics_against_the_cpu_stepper(hsl, tmp_path):
     """10240 random kicks (direction uniform in the horizontal plane, |dv| U[0, 16], kick time U[0.5 s, 3.5 s)): fall rate and
-    time-to-fall histogram of the sweep kernel against the CPU stepper on the same kicks (about 2 min of CPU stepping on the
-    16 host cores of the GPU box; HSL_FALL_STAT_WORLDS overrides the count)."""
+    time-to-fall histogram of the sweep kernel against the CPU stepper on the same kicks (HSL_FALL_STAT_WORLDS overrides the count)."""
     params, name = hsl.load_preset(PRESETS, 8)
     xml = model_xml(name)
     rng = np.random.default_rng(20261019)
