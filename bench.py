@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--fb", type=int, default=0, help="frame slots per block (32/64), 0 = library default")
     ap.add_argument("--maxreg", type=int, default=0, help="register cap of the cost-only kernel variant (1 = pipelined), 0 = library default")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: costs all-gathered by the finish kernel over NVLink peer memory (hsl_eval_gaits_gather) or by NCCL after it")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained and config3 sub-records")
     args = ap.parse_args()
@@ -262,9 +263,15 @@ def main():
             self.d_work = torch.empty(self.per, dtype=torch.float64, device=dev)
             self.d_status = torch.zeros(self.per, dtype=torch.int32, device=dev)
             self.gathered = torch.empty(ranks * self.per, dtype=torch.float64, device=dev) if ranks > 1 else None
+            self.peer = api.torch_gather(dist, self.per) if (ranks > 1 and args.gather == "peer") else None   # collective: every rank builds the same jobs
             self.best = torch.empty(1, dtype=torch.int64, device=dev)
 
         def step(self):
+            if self.peer is not None:   # evaluation + all-gather in the same launches; selection on every rank
+                p_cot, _ = self.model.eval_gaits_gather(self.peer, self.n_local, self.n_t, self.d_params.data_ptr() if self.n_local else 0,
+                                                        self.d_cot.data_ptr(), self.d_work.data_ptr(), 0, 0, self.d_status.data_ptr(), 0, stream)
+                api.select_best_device(p_cot, self.ranks * self.per, self.best.data_ptr(), 0, stream)
+                return self.best
             if self.n_local:
                 self.model.eval_gaits_device(self.n_local, self.n_t, self.d_params.data_ptr(), self.d_cot.data_ptr(), self.d_work.data_ptr(),
                                              0, 0, self.d_status.data_ptr(), 0, stream)
@@ -378,7 +385,7 @@ def main():
             "config": {"workload": head.w["name"] % (head.w["n_cand"] if not args.candidates else args.candidates, n_t),
                        "seed": SEED, "n_t": n_t, "candidates_per_gpu": head.per, "candidates_total": head.n_total,
                        "l2": "flushed between timed iterations (256 MiB fill)",
-                       "parallelism": "candidates sharded, costs all-gathered (NCCL), argmin on every rank" if world > 1 else "single GPU",
+                       "parallelism": ("candidates sharded, costs all-gathered (%s), argmin on every rank" % ("by the finish kernel over NVLink peer memory" if args.gather == "peer" else "NCCL")) if world > 1 else "single GPU",
                        "mean_contacts": kbar, "kernel_variant": {"frame_slots_per_block": fb, "maxreg": mr,
                                                                  "kernel": "hsl_gait_pipe_kernel" if mr == 1 else "hsl_frames_kernel"}},
             "gpu_launches": launches,

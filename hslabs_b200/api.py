@@ -89,6 +89,10 @@ def _load():
     lib.hsl_fall_sweep_host.argtypes = [vp, i64, vp, C.c_double, C.c_double, i32, vp, vp, C.c_double, C.c_double] + [vp] * 6
     lib.hsl_select_topk.argtypes = [vp, i64, i32, vp, vp, vp]
     lib.hsl_set_fall_variant.argtypes = [vp, i32]
+    lib.hsl_gather_create.argtypes = [i32, i32, i64, vp, vp]
+    lib.hsl_gather_connect.argtypes = [vp, vp]
+    lib.hsl_gather_free.argtypes = [vp]
+    lib.hsl_eval_gaits_gather.argtypes = [vp, vp, i64, i32, vp, i32] + [vp] * 8
     _lib = lib
     return lib
 
@@ -99,7 +103,8 @@ def exported_symbols():
             "hsl_device_count", "hsl_eval_gaits", "hsl_eval_gaits_host", "hsl_eval_gaits_detail_host",
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_get_tuning", "hsl_set_kernel_timing", "hsl_last_kernel_ms", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
-            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host", "hsl_set_fall_variant"]
+            "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host", "hsl_set_fall_variant",
+            "hsl_gather_create", "hsl_gather_connect", "hsl_gather_free", "hsl_eval_gaits_gather"]
 
 
 class _Pinned:
@@ -370,6 +375,17 @@ class Model:
                                       d_min_cfz or None, d_max_mu or None, d_status or None, stream or None))
 
 
+    def eval_gaits_gather(self, gather, n_cand, n_t, d_params, d_cot=0, d_work=0, d_min_cfz=0, d_max_mu=0, d_status=0, flags=0, stream=0):
+        """hsl_eval_gaits_gather: evaluate this rank's n_cand candidates and all-gather costs and status over peer memory in
+        the same launches.  Returns the integer device addresses of the [world][n_per_rank] cost (float64) and status (int32)
+        arrays in this rank's gather buffer; they are complete for work queued on `stream` afterwards and stay valid until
+        the second-next call on `gather`."""
+        all_cot, all_st = C.c_void_p(), C.c_void_p()
+        _check(_load().hsl_eval_gaits_gather(self._h, gather._g, n_cand, n_t, d_params or None, flags, d_cot or None, d_work or None,
+                                             d_min_cfz or None, d_max_mu or None, d_status or None, C.byref(all_cot), C.byref(all_st),
+                                             stream or None))
+        return all_cot.value, all_st.value
+
     def eval_trajectories_device(self, n_cand, n_t, d_traj, d_dt, d_work=0, d_min_cfz=0, d_max_mu=0, d_status=0, d_x=0, d_z=0, d_tau=0,
                                  stream=0):
         """hsl_eval_trajectories: the L2 entry on device-resident trajectories (integer device addresses, row-major layouts of
@@ -382,6 +398,38 @@ class Model:
         """hsl_solve_frames: the L1 entry on device-resident dynrecord arrays (integer device addresses)."""
         _check(_load().hsl_solve_frames(self._h, n_frames, d_pos, d_jpos, d_jzaxis, d_mom_rate, d_ang_mom_rate, d_fpos, d_contacts,
                                         d_x or None, d_z or None, d_tau or None, d_status or None, stream or None))
+
+
+class Gather:
+    """The peer-memory all-gather of the costs (hsl_gather_create / _connect): this rank's gather buffer for `n_per_rank`
+    candidates per rank, mapped by every rank of the job over NVLink.  `exchange(handle_bytes) -> [handle_bytes of every
+    rank, in rank order]` is the launcher's side channel (torch.distributed.all_gather_object, MPI, files ...); it also acts
+    as the barrier between creating and mapping the buffers."""
+
+    def __init__(self, rank, world, n_per_rank, exchange):
+        self._g = C.c_void_p()
+        mine = (C.c_char * 64)()
+        _check(_load().hsl_gather_create(world, rank, n_per_rank, C.byref(self._g), mine))
+        self.rank, self.world, self.n_per_rank = rank, world, int(n_per_rank)
+        handles = exchange(bytes(mine.raw))
+        if len(handles) != world or any(len(h) != 64 for h in handles):
+            raise HslError("exchange() must return the 64-byte handle of every rank")
+        _check(_load().hsl_gather_connect(self._g, (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))))
+
+    def free(self):
+        """Unmap and free.  All ranks must be done with the buffers (barrier before)."""
+        if self._g:
+            _check(_load().hsl_gather_free(self._g))
+            self._g = C.c_void_p()
+
+
+def torch_gather(dist, n_per_rank):
+    """Gather object for the ranks of an initialised torch.distributed job (handles exchanged with all_gather_object)."""
+    def exchange(mine):
+        box = [None] * dist.get_world_size()
+        dist.all_gather_object(box, mine)
+        return box
+    return Gather(dist.get_rank(), dist.get_world_size(), n_per_rank, exchange)
 
 
 class NcclComm:

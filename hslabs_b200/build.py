@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libhsl_b200.so")
-SOURCES = ["hsl_kernels.cu", "hsl_select.cu", "hsl_fall.cu", "hsl_capi.cu", "hsl_model_load.cpp"]
+SOURCES = ["hsl_kernels.cu", "hsl_select.cu", "hsl_fall.cu", "hsl_gather.cu", "hsl_capi.cu", "hsl_model_load.cpp"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh", ".hpp"))) + [os.path.join("..", "..", "include", "hsl.h")]  # every header counts as a dependency
 # hsl_fall.cu: no FMA contraction.  The sweep kernel is bound by its thread-local working set, not by FP64 issue, and the
 # contact set of a step hangs on the sign of depths that are zero up to round-off (the gait puts stance feet exactly at

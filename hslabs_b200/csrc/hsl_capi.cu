@@ -57,11 +57,13 @@ struct PinBuf {  // grow-only pinned host buffer
 }  // namespace
 
 struct HslModel {
+  HslModel() { peers.n = 0; }
   HslModelPod pod;
   HslSimPod sim;        // constants of the fall sweep (hsl_fall.cu)
   bool sim_ok = false;
   double total_mass;
   int fb = 64, maxreg = 128;
+  HslPeerOut peers;      // set for the duration of hsl_eval_gaits_gather: where the finish kernel also stores the costs
   int fall_variant = 1;  // fall sweep: 1 = a warp per world (hsl_fall_warp.cuh), 0 = a thread per world (hsl_fall_world.h)
   int64_t max_slots = (int64_t)1 << 26;  // frame slots per launch (hsl_set_max_slots)
   int64_t launches = 0;
@@ -301,7 +303,7 @@ static int eval_gaits_chunk(HslModel* m, int64_t C, int n_t, const double* d_par
   }
 #endif
   HSL_CUDA(hsl_launch_finish(C, n_t, m->total_mass, (const HslCand*)m->cand.p, nullptr, A.wframe, A.fmin_cfz, A.fmax_mu, st_buf,
-                             d_cot, d_work, d_min, d_max, st));
+                             d_cot, d_work, d_min, d_max, st, m->peers.n ? &m->peers : nullptr));
   if (m->timing) { HSL_CUDA(cudaEventRecord(m->tev[3], st)); m->tev_valid = true; }
   m->launches += 3;
   return HSL_OK;
@@ -336,6 +338,7 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
     const int rc = eval_gaits_chunk(m, cc, n_t, d_params + c0 * HSL_NPARAM, flags, d_cot ? d_cot + c0 : nullptr, d_work ? d_work + c0 : nullptr,
                                     d_min ? d_min + c0 : nullptr, d_max ? d_max + c0 : nullptr, d_status ? d_status + c0 : nullptr, dump, st);
     if (rc) return rc;
+    for (int r = 0; r < m->peers.n; r++) { m->peers.cot[r] += cc; m->peers.status[r] += cc; }  // the next chunk's place in the gather buffers
   }
   return HSL_OK;
 }
@@ -354,6 +357,92 @@ int hsl_select_best(const double* d_cost, int64_t n, int64_t* d_index, double* d
 int hsl_select_topk(const double* d_cost, int64_t n, int k, int64_t* d_index, double* d_value, void* stream) {
   if (!d_cost || n < 1 || n > 0x7fffffff || k < 1 || k > n || (!d_index && !d_value)) return set_err(HSL_ERR_ARG, "bad argument (1 <= k <= n < 2^31)");
   HSL_CUDA(hsl_launch_topk(d_cost, n, k, d_index, d_value, (cudaStream_t)stream));
+  return HSL_OK;
+}
+
+// ---------------------------------------------------------------- peer-memory all-gather of the costs (hsl_gather.cu)
+struct HslGather {
+  int nranks = 0, rank = 0;
+  int64_t per = 0;
+  size_t off_status = 0, off_flags = 0, bytes = 0;
+  char* local = nullptr;
+  char* peer[HSL_MAX_PEERS] = {};   // peer[rank] == local
+  bool connected = false;
+  unsigned long long epoch = 0;
+};
+static size_t up256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int hsl_gather_create(int nranks, int rank, int64_t n_per_rank, HslGather** out, HslIpcHandle* mine) {
+  if (!out || !mine || nranks < 1 || nranks > HSL_MAX_PEERS || rank < 0 || rank >= nranks || n_per_rank < 1)
+    return set_err(HSL_ERR_ARG, "bad argument (1 <= nranks <= 16, 0 <= rank < nranks, n_per_rank >= 1)");
+  static_assert(sizeof(HslIpcHandle) == sizeof(cudaIpcMemHandle_t), "HslIpcHandle carries a cudaIpcMemHandle_t");
+  HslGather* g = new HslGather;
+  g->nranks = nranks; g->rank = rank; g->per = n_per_rank;
+  const size_t n = (size_t)nranks * n_per_rank;
+  g->off_status = up256(2 * n * sizeof(double));
+  g->off_flags = g->off_status + up256(2 * n * sizeof(int32_t));
+  g->bytes = g->off_flags + up256(HSL_MAX_PEERS * sizeof(unsigned long long));
+  cudaError_t e = cudaMalloc((void**)&g->local, g->bytes);   // plain cudaMalloc: stream-ordered pool memory cannot be exported
+  if (e == cudaSuccess) e = cudaMemset(g->local, 0xff, g->off_status);                       // costs: NaN
+  if (e == cudaSuccess) e = cudaMemset(g->local + g->off_status, 0, g->bytes - g->off_status);  // status and flags: 0
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  if (e == cudaSuccess && nranks > 1) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)mine, g->local);
+  if (e != cudaSuccess) { if (g->local) cudaFree(g->local); delete g; return set_err(HSL_ERR_CUDA, "CUDA: %s", cudaGetErrorString(e)); }
+  g->peer[rank] = g->local;
+  g->connected = (nranks == 1);
+  *out = g;
+  return HSL_OK;
+}
+int hsl_gather_connect(HslGather* g, const HslIpcHandle* all) {
+  if (!g || (!all && g->nranks > 1)) return set_err(HSL_ERR_ARG, "bad argument");
+  if (g->connected) return HSL_OK;
+  for (int r = 0; r < g->nranks; r++) {
+    if (r == g->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, &all[r], sizeof h);
+    cudaError_t e = cudaIpcOpenMemHandle((void**)&g->peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return set_err(HSL_ERR_CUDA, ("cudaIpcOpenMemHandle of rank " + std::to_string(r) + "'s buffer: %s").c_str(), cudaGetErrorString(e));
+  }
+  g->connected = true;
+  return HSL_OK;
+}
+int hsl_gather_free(HslGather* g) {
+  if (!g) return HSL_OK;
+  cudaDeviceSynchronize();
+  for (int r = 0; r < g->nranks; r++) if (r != g->rank && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
+  if (g->local) cudaFree(g->local);
+  delete g;
+  return HSL_OK;
+}
+int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                          double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot, const int32_t** d_all_status,
+                          void* stream) {
+  if (!m || !g || !g->connected || n_cand < 0 || n_cand > g->per || n_t < 1 || (n_cand > 0 && !d_params))
+    return set_err(HSL_ERR_ARG, "bad argument (connected gather object, 0 <= n_cand <= n_per_rank)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned long long epoch = ++g->epoch;
+  const size_t n = (size_t)g->nranks * g->per, par = (size_t)(epoch & 1);
+  HslPeerOut po;
+  memset(&po, 0, sizeof po);
+  po.n = g->nranks;
+  unsigned long long* flag_at_peer[HSL_MAX_PEERS] = {};
+  for (int r = 0; r < g->nranks; r++) {
+    po.cot[r] = (double*)g->peer[r] + par * n + (size_t)g->rank * g->per;
+    po.status[r] = (int32_t*)(g->peer[r] + g->off_status) + par * n + (size_t)g->rank * g->per;
+    flag_at_peer[r] = (unsigned long long*)(g->peer[r] + g->off_flags) + g->rank;
+  }
+  int rc = HSL_OK;
+  if (n_cand > 0) {
+    m->peers = po;
+    rc = eval_gaits_dev(m, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, false, st);
+    m->peers.n = 0;
+    if (rc) return rc;
+  }
+  HSL_CUDA(hsl_launch_gather_signal(po, n_cand, g->per, flag_at_peer, epoch, st));
+  HSL_CUDA(hsl_launch_gather_wait((const unsigned long long*)(g->local + g->off_flags), g->nranks, epoch, st));
+  m->launches += 2;
+  if (d_all_cot) *d_all_cot = (const double*)g->local + par * n;
+  if (d_all_status) *d_all_status = (const int32_t*)(g->local + g->off_status) + par * n;
   return HSL_OK;
 }
 

@@ -14,9 +14,22 @@ cudaError_t hsl_launch_ik_records(const HslModelPod& M, int64_t n, int flags, co
                                   cudaStream_t st);
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
                              int32_t* status, cudaStream_t st);
+// Where the finish kernel also stores a candidate's cost and status: one gather buffer per rank of the job, reached over
+// NVLink peer mappings (hsl_gather.cu).  n = 0: nowhere.
+#define HSL_MAX_PEERS 16
+struct HslPeerOut {
+  int32_t n, pad;
+  double* cot[HSL_MAX_PEERS];      // each already offset to this rank's segment (+ the chunk's first candidate)
+  int32_t* status[HSL_MAX_PEERS];
+};
 cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
                               const double* wframe, const double* fmin, const double* fmax, const int32_t* status, double* cot,
-                              double* work, double* min_cfz, double* max_mu, cudaStream_t st);
+                              double* work, double* min_cfz, double* max_mu, cudaStream_t st, const HslPeerOut* peers = nullptr);
+// hsl_gather.cu: pad the unused tail of this rank's segment with NaN at every peer, then raise this rank's flag there;
+// wait until every rank's flag of this epoch has arrived here
+cudaError_t hsl_launch_gather_signal(const HslPeerOut& peers, int64_t n_used, int64_t n_per_rank, unsigned long long* const* flag_at_peer,
+                                     unsigned long long epoch, cudaStream_t st);
+cudaError_t hsl_launch_gather_wait(const unsigned long long* flags, int nranks, unsigned long long epoch, cudaStream_t st);
 cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, double* out, cudaStream_t st);
 cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st);
 int hsl_topk_launches(int64_t n);  // kernels hsl_launch_topk issues for n costs

@@ -384,7 +384,7 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
                                   const double* __restrict__ dt_in, const double* __restrict__ wframe,
                                   const double* __restrict__ fmin_in, const double* __restrict__ fmax_in,
                                   const int32_t* __restrict__ status, double* __restrict__ cot, double* __restrict__ work,
-                                  double* __restrict__ min_cfz, double* __restrict__ max_mu) {
+                                  double* __restrict__ min_cfz, double* __restrict__ max_mu, const __grid_constant__ HslPeerOut peers) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x & 31;
   if (c >= n_cand) return;
@@ -401,15 +401,19 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
     mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
   }
+  const int st = status ? status[c] : 0;
+  const bool fatal = (st & (HSL_ST_BAD_PARAMS | HSL_ST_UNREACHABLE)) != 0;  // the reference exit(1)s here
+  const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+  const double cv = (fatal || !cand) ? nanv : w / (total_mass * cand[c].step_length);
   if (lane == 0) {
-    const int st = status ? status[c] : 0;
-    const bool fatal = (st & (HSL_ST_BAD_PARAMS | HSL_ST_UNREACHABLE)) != 0;  // the reference exit(1)s here
-    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
     if (work) work[c] = fatal ? nanv : w;
-    if (cot) cot[c] = (fatal || !cand) ? nanv : w / (total_mass * cand[c].step_length);
+    if (cot) cot[c] = cv;
     if (min_cfz) min_cfz[c] = fatal ? nanv : mn;
     if (max_mu) max_mu[c] = fatal ? nanv : mx;
   }
+  // the all-gather of the costs, fused: lane r stores this candidate's cost and status into rank r's gather buffer (peer
+  // memory over NVLink; the rank's own buffer among them).  hsl_gather_signal_kernel publishes them.
+  if (lane < peers.n) { peers.cot[lane][c] = cv; peers.status[lane][c] = st; }
 }
 
 // Selection (argmin / top-k over the all-gathered costs) lives in hsl_select.cu.
@@ -630,11 +634,13 @@ cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, cons
 
 cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const HslCand* cand, const double* dt_in,
                               const double* wframe, const double* fmin_in, const double* fmax_in, const int32_t* status, double* cot,
-                              double* work, double* min_cfz, double* max_mu, cudaStream_t st) {
+                              double* work, double* min_cfz, double* max_mu, cudaStream_t st, const HslPeerOut* peers) {
   const int tpb = 256;
   const int64_t threads = n_cand * 32;
+  HslPeerOut none;
+  none.n = 0;
   hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
-                                                                         fmax_in, status, cot, work, min_cfz, max_mu);
+                                                                         fmax_in, status, cot, work, min_cfz, max_mu, peers ? *peers : none);
   return cudaGetLastError();
 }
 

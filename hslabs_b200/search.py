@@ -29,15 +29,37 @@ def grid_candidates(base, axes):
     return cand
 
 
-class DeviceEvaluator:
-    """Evaluates candidate rows resident on the device; shards over ranks when torch.distributed is initialised."""
+class _DeviceArray:
+    """A device address as a CUDA-array-interface object (so that torch can wrap memory owned by the C library)."""
 
-    def __init__(self, model, n_t, flags=0):
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(ptr, False), version=3)
+
+
+class DeviceEvaluator:
+    """Evaluates candidate rows resident on the device; shards over ranks when torch.distributed is initialised.
+    gather="peer" (default): costs and status are all-gathered by the evaluation's own finish kernel over NVLink peer
+    memory (hsl_eval_gaits_gather); gather="nccl": two torch.distributed all-gathers after it."""
+
+    def __init__(self, model, n_t, flags=0, gather="peer"):
         import torch
         self.torch, self.model, self.n_t, self.flags = torch, model, n_t, flags
         self.dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
         self.world = self.dist.get_world_size() if self.dist else 1
         self.rank = self.dist.get_rank() if self.dist else 0
+        if gather not in ("peer", "nccl"):
+            raise ValueError("gather must be 'peer' or 'nccl'")
+        self.gather = gather
+        self._gathers = {}   # candidates per rank -> api.Gather
+
+    def close(self):
+        """Frees the peer gather buffers (collective: every rank calls it)."""
+        if self._gathers:
+            self.torch.cuda.synchronize()
+            self.dist.barrier()
+            for g in self._gathers.values():
+                g.free()
+            self._gathers = {}
 
     def __call__(self, cand):
         """cand: float64 CUDA tensor [C][13] (identical on every rank).  Returns (cot[C], status[C]) CUDA tensors."""
@@ -45,6 +67,18 @@ class DeviceEvaluator:
         c = cand.shape[0]
         per = -(-c // self.world)
         lo, hi = min(self.rank * per, c), min(self.rank * per + per, c)
+        if self.dist and self.gather == "peer":
+            from . import api
+            g = self._gathers.get(per)
+            if g is None:
+                g = self._gathers[per] = api.torch_gather(self.dist, per)
+            local = cand[lo:hi].contiguous() if hi > lo else None
+            p_cot, p_st = self.model.eval_gaits_gather(g, hi - lo, self.n_t, local.data_ptr() if hi > lo else 0, flags=self.flags,
+                                                       stream=torch.cuda.current_stream().cuda_stream)
+            n = self.world * per   # the views live in the gather buffer and are overwritten two calls later: hand out copies
+            cot = torch.as_tensor(_DeviceArray(p_cot, n, "<f8"), device=cand.device).clone()
+            st = torch.as_tensor(_DeviceArray(p_st, n, "<i4"), device=cand.device).clone()
+            return cot[:c], st[:c]
         cot = torch.full((per,), float("nan"), dtype=torch.float64, device=cand.device)
         st = torch.zeros(per, dtype=torch.int32, device=cand.device)
         if hi > lo:

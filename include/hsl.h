@@ -180,6 +180,28 @@ int hsl_allgather_costs(void* nccl_comm, const double* d_local, int64_t n_per_ra
  * e.g. the C++ mirror's sharded measure_cot_sweep. */
 int hsl_allgather_costs_host(void* nccl_comm, int nranks, const double* local, int64_t n_per_rank, double* all);
 
+/* The same collective over NVLink peer memory, fused into the evaluation (hsl_gather.cu): every rank owns a gather buffer
+ * that all ranks of the job map through CUDA IPC (one process per GPU, one node); the finish kernel of the gait evaluation
+ * stores each candidate's cost and status straight into all of them, and a flag per rank (release after the stores,
+ * acquire before the selection reads) is all that is left of the all-gather.
+ *   hsl_gather_create   allocates this rank's buffer for n_per_rank candidates per rank and returns its IPC handle;
+ *   hsl_gather_connect  maps the other ranks' buffers from their handles (all[nranks], exchanged by whatever means the
+ *                       launcher has); every rank must have created its buffer before any rank connects;
+ *   hsl_eval_gaits_gather = hsl_eval_gaits of this rank's n_cand <= n_per_rank candidates (0 allowed: an empty shard) +
+ *                       the gather: *d_all_cot / *d_all_status point at [nranks][n_per_rank] arrays in this rank's
+ *                       buffer (unused tail entries NaN / 0), complete for work queued on `stream` after the call and
+ *                       valid until the second-next call on this object (two buffers alternate).  Every rank of the
+ *                       job must make the same sequence of calls.
+ *   hsl_gather_free     unmaps and frees; all ranks must have finished using the buffers (barrier first). */
+typedef struct HslGather HslGather;
+typedef struct HslIpcHandle { char internal[64]; } HslIpcHandle; /* cudaIpcMemHandle_t */
+int hsl_gather_create(int nranks, int rank, int64_t n_per_rank, HslGather** g, HslIpcHandle* mine);
+int hsl_gather_connect(HslGather* g, const HslIpcHandle* all);
+int hsl_gather_free(HslGather* g);
+int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot,
+                          double* d_work, double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot,
+                          const int32_t** d_all_status, void* stream);
+
 /* Page-locked host memory for input / output arrays of the *_host entries (they copy straight from / into the caller's
  * buffers; pageable memory works too, at the driver's staged-copy rate).  NULL on failure. */
 void* hsl_pinned_alloc(size_t bytes);

@@ -28,10 +28,28 @@ def main(out_dir):
     p[17, 2] = 0.4                         # unreachable: NaN cost on every rank
     single = model.eval_gaits(p, n_t)
     cand = torch.from_numpy(p).to(dev)
-    cot, st = search.DeviceEvaluator(model, n_t)(cand)   # sharded over the ranks, all-gathered
+    ev = search.DeviceEvaluator(model, n_t)               # sharded over the ranks; costs gathered over NVLink peer memory
+    cot, st = ev(cand)
     got = cot.cpu().numpy()
     assert np.array_equal(got, single["cot"], equal_nan=True), "sharded costs differ from the single-GPU evaluation"
     assert np.array_equal(st.cpu().numpy(), single["status"])
+    cot_n, st_n = search.DeviceEvaluator(model, n_t, gather="nccl")(cand)   # the same through torch.distributed's all-gather
+    assert torch.equal(cot_n.nan_to_num(nan=-1.0), cot.nan_to_num(nan=-1.0)) and torch.equal(st_n, st)
+    # run-ahead: 40 back-to-back gathers of changing batches, one rank delayed every few calls; every result is checked
+    # after the loop, so a rank that overwrote a buffer still in use would show
+    outs = []
+    for it in range(40):
+        if it % 7 == rank % 7:
+            torch.cuda._sleep(20_000_000)
+        sub = cand[(it * 13) % 200:(it * 13) % 200 + 257 + it]
+        outs.append((sub, ev(sub)[0]))
+    for sub, c in outs:
+        want = model.eval_gaits(sub.cpu().numpy(), n_t)["cot"]
+        assert np.array_equal(c.cpu().numpy(), want, equal_nan=True), "gathered costs differ after back-to-back calls"
+    # an empty shard (fewer candidates than ranks) and a batch of one
+    for k in (1, world - 1 if world > 1 else 1):
+        c1, _ = ev(cand[:k])
+        assert np.array_equal(c1.cpu().numpy(), single["cot"][:k], equal_nan=True)
     idx, val = search.top_k(cot, 5)
     key = np.where(np.isnan(single["cot"]), np.inf, single["cot"])
     assert list(idx.cpu().numpy()) == list(np.argsort(key, kind="stable")[:5])
@@ -42,6 +60,7 @@ def main(out_dir):
     # the C-ABI collective (hsl_allgather_costs over an ncclComm_t created from a broadcast unique id)
     if hasattr(hsl.api, "nccl_allgather_selftest"):
         hsl.api.nccl_allgather_selftest(rank, world, dist, dev)
+    ev.close()
     dist.barrier()
     open(os.path.join(out_dir, "rank%d.ok" % rank), "w").write("ok\n")
     dist.destroy_process_group()

@@ -89,3 +89,36 @@ def test_fk_records(hsl, orc, refb, name):
     assert (t["masses"] == 1).all()
     assert np.array_equal(t["com_offset"], cons["A_body_geom"][:, 12:15])
     assert np.array_equal(t["foot_offset"], cons["capsule_to_pos"][cons["limb_foot"]])
+
+
+def test_gather_object_with_one_rank(hsl):
+    """hsl_eval_gaits_gather on a job of one rank (no peer to map): the gather buffer holds this rank's costs and status,
+    NaN / 0 behind them, the two buffers alternate, and an empty shard leaves only padding."""
+    import torch
+    from hslabs_b200 import api
+    from hslabs_b200.search import _DeviceArray
+    rng = np.random.default_rng(5)
+    n, per, n_t = 37, 50, 24
+    p = np.zeros((n, 13))
+    p[:, 2] = rng.uniform(-0.15, -0.05, n); p[:, 6] = rng.uniform(0, 1, n); p[:, 7] = rng.uniform(1, 6, n)
+    p[:, 8] = rng.uniform(0.1, 0.5, n); p[:, 9] = rng.uniform(0.02, 0.12, n); p[:, 11] = -1
+    p[5, 2] = 0.4   # unreachable
+    m = hsl.Model(hsl.model_path("hexapod"))
+    want = m.eval_gaits(p, n_t)
+    g = api.Gather(0, 1, per, lambda h: [h])
+    d = torch.from_numpy(p).cuda()
+    cot = torch.empty(n, dtype=torch.float64, device="cuda")
+    ptrs = []
+    for k in (n, 0, 11):
+        pc, ps = m.eval_gaits_gather(g, k, n_t, d.data_ptr() if k else 0, d_cot=cot.data_ptr() if k else 0, stream=torch.cuda.current_stream().cuda_stream)
+        ptrs.append(pc)
+        allc = torch.as_tensor(_DeviceArray(pc, per, "<f8"), device="cuda").cpu().numpy()
+        alls = torch.as_tensor(_DeviceArray(ps, per, "<i4"), device="cuda").cpu().numpy()
+        assert np.array_equal(allc[:k], want["cot"][:k], equal_nan=True) and np.isnan(allc[k:]).all()
+        assert np.array_equal(alls[:k], want["status"][:k]) and (alls[k:] == 0).all()
+        if k:
+            assert np.array_equal(cot.cpu().numpy()[:k], want["cot"][:k], equal_nan=True)
+    assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]
+    with pytest.raises(hsl.HslError):
+        m.eval_gaits_gather(g, per + 1, n_t, d.data_ptr())
+    g.free()
