@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--fb", type=int, default=0, help="frame slots per block (32/64), 0 = library default")
     ap.add_argument("--maxreg", type=int, default=0, help="register cap of the cost-only kernel variant (1 = pipelined), 0 = library default")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"], help="N > 1: costs all-gathered by the finish kernel over NVLink peer memory (hsl_eval_gaits_gather) or by NCCL after it")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"], help="N > 1: costs all-gathered by the finish kernel over NVLink peer memory (hsl_eval_gaits_gather) or by NCCL after it; none = diagnostic only (no collective: shows the ranks' own step times), its line is not a bench result")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained and config3 sub-records")
     args = ap.parse_args()
@@ -268,15 +268,15 @@ def main():
 
         def step(self):
             if self.peer is not None:   # evaluation + all-gather in the same launches; selection on every rank
-                p_cot, _ = self.model.eval_gaits_gather(self.peer, self.n_local, self.n_t, self.d_params.data_ptr() if self.n_local else 0,
-                                                        self.d_cot.data_ptr(), self.d_work.data_ptr(), 0, 0, self.d_status.data_ptr(), 0, stream)
-                api.select_best_device(p_cot, self.ranks * self.per, self.best.data_ptr(), 0, stream)
+                self.model.eval_gaits_scatter(self.peer, self.n_local, self.n_t, self.d_params.data_ptr() if self.n_local else 0,
+                                              self.d_cot.data_ptr(), self.d_work.data_ptr(), 0, 0, self.d_status.data_ptr(), 0, stream)
+                self.peer.select_best(self.best.data_ptr(), 0, stream)   # its first instructions wait for the ranks' flags
                 return self.best
             if self.n_local:
                 self.model.eval_gaits_device(self.n_local, self.n_t, self.d_params.data_ptr(), self.d_cot.data_ptr(), self.d_work.data_ptr(),
                                              0, 0, self.d_status.data_ptr(), 0, stream)
             costs = self.d_cot
-            if self.ranks > 1:
+            if self.ranks > 1 and args.gather != "none":
                 dist.all_gather_into_tensor(self.gathered, self.d_cot)
                 costs = self.gathered
             api.select_best_device(costs.data_ptr(), costs.numel(), self.best.data_ptr(), 0, stream)   # selection on every rank
@@ -320,6 +320,8 @@ def main():
     head = Job(args.workload, n_total=args.candidates or None, n_t=args.frames or None)
     n_t = head.n_t
     step_ms, clocks, launches, _ = head.timed(args.steps, args.warmup)
+    if world > 1 and os.environ.get("HSL_BENCH_RANK_TIMES"):
+        sys.stderr.write("[rank %d] own ms per step: mean %.4f min %.4f max %.4f\n" % (rank, float(np.mean(step_ms)), min(step_ms), max(step_ms)))
     ms_total = max_over_ranks(sum(step_ms))
     frames_per_step = head.n_total * n_t
     value = frames_per_step * args.steps / (ms_total * 1e-3)

@@ -93,6 +93,9 @@ def _load():
     lib.hsl_gather_connect.argtypes = [vp, vp]
     lib.hsl_gather_free.argtypes = [vp]
     lib.hsl_eval_gaits_gather.argtypes = [vp, vp, i64, i32, vp, i32] + [vp] * 8
+    lib.hsl_eval_gaits_scatter.argtypes = [vp, vp, i64, i32, vp, i32] + [vp] * 6
+    lib.hsl_gather_wait.argtypes = [vp, vp, vp, vp]
+    lib.hsl_gather_select_best.argtypes = [vp, vp, vp, vp]
     _lib = lib
     return lib
 
@@ -104,7 +107,8 @@ def exported_symbols():
             "hsl_eval_trajectories_host", "hsl_solve_frames_host", "hsl_gait_records_host", "hsl_ik_records_host", "hsl_solve_forces_host", "hsl_solve_forces_gait_host", "hsl_set_rec_transform", "hsl_set_tuning", "hsl_get_tuning", "hsl_set_kernel_timing", "hsl_last_kernel_ms", "hsl_set_max_slots", "hsl_pinned_alloc", "hsl_pinned_free", "hsl_launch_count",
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
             "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host", "hsl_set_fall_variant",
-            "hsl_gather_create", "hsl_gather_connect", "hsl_gather_free", "hsl_eval_gaits_gather"]
+            "hsl_gather_create", "hsl_gather_connect", "hsl_gather_free", "hsl_eval_gaits_gather", "hsl_eval_gaits_scatter",
+            "hsl_gather_wait", "hsl_gather_select_best"]
 
 
 class _Pinned:
@@ -375,6 +379,12 @@ class Model:
                                       d_min_cfz or None, d_max_mu or None, d_status or None, stream or None))
 
 
+    def eval_gaits_scatter(self, gather, n_cand, n_t, d_params, d_cot=0, d_work=0, d_min_cfz=0, d_max_mu=0, d_status=0, flags=0, stream=0):
+        """hsl_eval_gaits_scatter: evaluate this rank's candidates; the finish kernel stores costs and status into every rank's
+        gather buffer and raises this rank's flags.  Read with gather.select_best() or gather.wait()."""
+        _check(_load().hsl_eval_gaits_scatter(self._h, gather._g, n_cand, n_t, d_params or None, flags, d_cot or None, d_work or None,
+                                              d_min_cfz or None, d_max_mu or None, d_status or None, stream or None))
+
     def eval_gaits_gather(self, gather, n_cand, n_t, d_params, d_cot=0, d_work=0, d_min_cfz=0, d_max_mu=0, d_status=0, flags=0, stream=0):
         """hsl_eval_gaits_gather: evaluate this rank's n_cand candidates and all-gather costs and status over peer memory in
         the same launches.  Returns the integer device addresses of the [world][n_per_rank] cost (float64) and status (int32)
@@ -415,6 +425,16 @@ class Gather:
         if len(handles) != world or any(len(h) != 64 for h in handles):
             raise HslError("exchange() must return the 64-byte handle of every rank")
         _check(_load().hsl_gather_connect(self._g, (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))))
+
+    def select_best(self, d_index=0, d_value=0, stream=0):
+        """hsl_gather_select_best: argmin over the costs of the latest scatter; the kernel itself waits for the ranks' flags."""
+        _check(_load().hsl_gather_select_best(self._g, d_index or None, d_value or None, stream or None))
+
+    def wait(self, stream=0):
+        """hsl_gather_wait: device addresses of the gathered [world][n_per_rank] cost / status arrays of the latest scatter."""
+        all_cot, all_st = C.c_void_p(), C.c_void_p()
+        _check(_load().hsl_gather_wait(self._g, C.byref(all_cot), C.byref(all_st), stream or None))
+        return all_cot.value, all_st.value
 
     def free(self):
         """Unmap and free.  All ranks must be done with the buffers (barrier before)."""

@@ -335,10 +335,14 @@ static int eval_gaits_dev(HslModel* m, int64_t C, int n_t, const double* d_param
   }
   for (int64_t c0 = 0; c0 < C; c0 += cmax) {
     const int64_t cc = (C - c0 < cmax) ? C - c0 : cmax;
+    m->peers.signal = (c0 + cc >= C);   // the finish kernel of the last chunk completes this rank's segment of the gather
     const int rc = eval_gaits_chunk(m, cc, n_t, d_params + c0 * HSL_NPARAM, flags, d_cot ? d_cot + c0 : nullptr, d_work ? d_work + c0 : nullptr,
                                     d_min ? d_min + c0 : nullptr, d_max ? d_max + c0 : nullptr, d_status ? d_status + c0 : nullptr, dump, st);
     if (rc) return rc;
-    for (int r = 0; r < m->peers.n; r++) { m->peers.cot[r] += cc; m->peers.status[r] += cc; }  // the next chunk's place in the gather buffers
+    if (m->peers.n) {  // the next chunk's place in the gather buffers
+      for (int r = 0; r < m->peers.n; r++) { m->peers.cot[r] += cc; m->peers.status[r] += cc; }
+      m->peers.pad_lo -= cc; m->peers.pad_hi -= cc;
+    }
   }
   return HSL_OK;
 }
@@ -381,7 +385,7 @@ int hsl_gather_create(int nranks, int rank, int64_t n_per_rank, HslGather** out,
   const size_t n = (size_t)nranks * n_per_rank;
   g->off_status = up256(2 * n * sizeof(double));
   g->off_flags = g->off_status + up256(2 * n * sizeof(int32_t));
-  g->bytes = g->off_flags + up256(HSL_MAX_PEERS * sizeof(unsigned long long));
+  g->bytes = g->off_flags + up256(HSL_MAX_PEERS * sizeof(unsigned long long) + sizeof(unsigned int));   // flags, then the finish kernel's block counter
   cudaError_t e = cudaMalloc((void**)&g->local, g->bytes);   // plain cudaMalloc: stream-ordered pool memory cannot be exported
   if (e == cudaSuccess) e = cudaMemset(g->local, 0xff, g->off_status);                       // costs: NaN
   if (e == cudaSuccess) e = cudaMemset(g->local + g->off_status, 0, g->bytes - g->off_status);  // status and flags: 0
@@ -414,9 +418,9 @@ int hsl_gather_free(HslGather* g) {
   delete g;
   return HSL_OK;
 }
-int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
-                          double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot, const int32_t** d_all_status,
-                          void* stream) {
+// evaluation whose finish kernel stores costs and status into every rank's gather buffer and raises this rank's flags
+int hsl_eval_gaits_scatter(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                           double* d_min_cfz, double* d_max_mu, int32_t* d_status, void* stream) {
   if (!m || !g || !g->connected || n_cand < 0 || n_cand > g->per || n_t < 1 || (n_cand > 0 && !d_params))
     return set_err(HSL_ERR_ARG, "bad argument (connected gather object, 0 <= n_cand <= n_per_rank)");
   cudaStream_t st = (cudaStream_t)stream;
@@ -425,25 +429,51 @@ int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, co
   HslPeerOut po;
   memset(&po, 0, sizeof po);
   po.n = g->nranks;
-  unsigned long long* flag_at_peer[HSL_MAX_PEERS] = {};
+  po.epoch = epoch;
+  po.ticket = (unsigned int*)(g->local + g->off_flags + HSL_MAX_PEERS * sizeof(unsigned long long));
   for (int r = 0; r < g->nranks; r++) {
     po.cot[r] = (double*)g->peer[r] + par * n + (size_t)g->rank * g->per;
     po.status[r] = (int32_t*)(g->peer[r] + g->off_status) + par * n + (size_t)g->rank * g->per;
-    flag_at_peer[r] = (unsigned long long*)(g->peer[r] + g->off_flags) + g->rank;
+    po.flag[r] = (unsigned long long*)(g->peer[r] + g->off_flags) + g->rank;
   }
-  int rc = HSL_OK;
-  if (n_cand > 0) {
-    m->peers = po;
-    rc = eval_gaits_dev(m, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, false, st);
-    m->peers.n = 0;
-    if (rc) return rc;
+  po.pad_lo = n_cand; po.pad_hi = g->per;   // eval_gaits_dev rebases them per chunk and sets `signal` on the last one
+  if (n_cand == 0) {
+    po.signal = 1;
+    HSL_CUDA(hsl_launch_gather_signal(po, st));
+    m->launches += 1;
+    return HSL_OK;
   }
-  HSL_CUDA(hsl_launch_gather_signal(po, n_cand, g->per, flag_at_peer, epoch, st));
-  HSL_CUDA(hsl_launch_gather_wait((const unsigned long long*)(g->local + g->off_flags), g->nranks, epoch, st));
-  m->launches += 2;
+  m->peers = po;
+  const int rc = eval_gaits_dev(m, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, false, st);
+  m->peers.n = 0;
+  return rc;
+}
+static void gather_views(const HslGather* g, const double** d_all_cot, const int32_t** d_all_status) {
+  const size_t n = (size_t)g->nranks * g->per, par = (size_t)(g->epoch & 1);
   if (d_all_cot) *d_all_cot = (const double*)g->local + par * n;
   if (d_all_status) *d_all_status = (const int32_t*)(g->local + g->off_status) + par * n;
+}
+int hsl_gather_wait(HslGather* g, const double** d_all_cot, const int32_t** d_all_status, void* stream) {
+  if (!g || !g->connected || g->epoch == 0) return set_err(HSL_ERR_ARG, "no scatter on this gather object yet");
+  HSL_CUDA(hsl_launch_gather_wait((const unsigned long long*)(g->local + g->off_flags), g->nranks, g->epoch, (cudaStream_t)stream));
+  gather_views(g, d_all_cot, d_all_status);
   return HSL_OK;
+}
+int hsl_gather_select_best(HslGather* g, int64_t* d_index, double* d_value, void* stream) {
+  if (!g || !g->connected || g->epoch == 0 || (!d_index && !d_value)) return set_err(HSL_ERR_ARG, "no scatter on this gather object yet, or no output");
+  const double* all = nullptr;
+  gather_views(g, &all, nullptr);
+  HSL_CUDA(hsl_launch_argmin_gathered(all, (int64_t)g->nranks * g->per, d_index, d_value, (const unsigned long long*)(g->local + g->off_flags),
+                                      g->nranks, g->epoch, (cudaStream_t)stream));
+  return HSL_OK;
+}
+int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot, double* d_work,
+                          double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot, const int32_t** d_all_status,
+                          void* stream) {
+  const int rc = hsl_eval_gaits_scatter(m, g, n_cand, n_t, d_params, flags, d_cot, d_work, d_min_cfz, d_max_mu, d_status, stream);
+  if (rc) return rc;
+  if (m) m->launches += 1;
+  return hsl_gather_wait(g, d_all_cot, d_all_status, stream);
 }
 
 static int ensure_stream(HslModel* m) {

@@ -387,7 +387,10 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
                                   double* __restrict__ min_cfz, double* __restrict__ max_mu, const __grid_constant__ HslPeerOut peers) {
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x & 31;
-  if (c >= n_cand) return;
+  if (c >= n_cand) {   // a whole warp
+    if (peers.n && peers.signal) hsl_gather_publish(peers);
+    return;
+  }
   const double dt = cand ? cand[c].dt : dt_in[c];
   double w = 0, mn = 1e10, mx = -1e10;  // periodic.cpp:380
   for (int f = lane; f < n_t; f += 32) {
@@ -412,8 +415,9 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
     if (max_mu) max_mu[c] = fatal ? nanv : mx;
   }
   // the all-gather of the costs, fused: lane r stores this candidate's cost and status into rank r's gather buffer (peer
-  // memory over NVLink; the rank's own buffer among them).  hsl_gather_signal_kernel publishes them.
+  // memory over NVLink; the rank's own buffer among them); the last block to finish raises this rank's flag at every peer.
   if (lane < peers.n) { peers.cot[lane][c] = cv; peers.status[lane][c] = st; }
+  if (peers.n && peers.signal) hsl_gather_publish(peers);
 }
 
 // Selection (argmin / top-k over the all-gathered costs) lives in hsl_select.cu.

@@ -23,9 +23,17 @@ __device__ __forceinline__ bool hsl_better(double v, long long i, double bv, lon
   return i >= 0 && (bidx < 0 || v < bv || (v == bv && i < bidx));
 }
 
-__global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, int64_t* __restrict__ out_index, double* __restrict__ out_value) {
+// GATHERED: the costs are a peer-memory gather buffer (hsl_gather.cu): wait for every rank's flag first (acquire), and read
+// the costs past L1 (they were written by other GPUs).
+template <bool GATHERED>
+__global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, int64_t* __restrict__ out_index, double* __restrict__ out_value,
+                                  const unsigned long long* flags, int nranks, unsigned long long epoch) {
   __shared__ double sv[32];
   __shared__ long long si[32];
+  if (GATHERED) {
+    if (threadIdx.x < nranks) while (hsl_ld_acquire_sys(flags + threadIdx.x) < epoch) __nanosleep(50);
+    __syncthreads();
+  }
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   double best = inf;
   long long bi = -1;
@@ -36,7 +44,7 @@ __global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, in
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int64_t i = base + (int64_t)u * blockDim.x;
-      c[u] = (i < n) ? cost[i] : inf;   // independent loads: one round trip per U candidates
+      c[u] = (i < n) ? (GATHERED ? __ldcg(cost + i) : cost[i]) : inf;   // independent loads: one round trip per U candidates
     }
 #pragma unroll
     for (int u = 0; u < U; u++)
@@ -191,7 +199,12 @@ __global__ void hsl_topk_emit_kernel(const uint64_t* __restrict__ keys, const ui
 }  // namespace
 
 cudaError_t hsl_launch_argmin(const double* cost, int64_t n, int64_t* out_index, double* out_value, cudaStream_t st) {
-  hsl_argmin_kernel<<<1, 1024, 0, st>>>(cost, n, out_index, out_value);
+  hsl_argmin_kernel<false><<<1, 1024, 0, st>>>(cost, n, out_index, out_value, nullptr, 0, 0);
+  return cudaGetLastError();
+}
+cudaError_t hsl_launch_argmin_gathered(const double* cost, int64_t n, int64_t* out_index, double* out_value, const unsigned long long* flags,
+                                       int nranks, unsigned long long epoch, cudaStream_t st) {
+  hsl_argmin_kernel<true><<<1, 1024, 0, st>>>(cost, n, out_index, out_value, flags, nranks, epoch);
   return cudaGetLastError();
 }
 

@@ -187,17 +187,26 @@ int hsl_allgather_costs_host(void* nccl_comm, int nranks, const double* local, i
  *   hsl_gather_create   allocates this rank's buffer for n_per_rank candidates per rank and returns its IPC handle;
  *   hsl_gather_connect  maps the other ranks' buffers from their handles (all[nranks], exchanged by whatever means the
  *                       launcher has); every rank must have created its buffer before any rank connects;
- *   hsl_eval_gaits_gather = hsl_eval_gaits of this rank's n_cand <= n_per_rank candidates (0 allowed: an empty shard) +
- *                       the gather: *d_all_cot / *d_all_status point at [nranks][n_per_rank] arrays in this rank's
- *                       buffer (unused tail entries NaN / 0), complete for work queued on `stream` after the call and
- *                       valid until the second-next call on this object (two buffers alternate).  Every rank of the
- *                       job must make the same sequence of calls.
+ *   hsl_eval_gaits_scatter = hsl_eval_gaits of this rank's n_cand <= n_per_rank candidates (0 allowed: an empty shard)
+ *                       whose finish kernel also stores cost and status into every rank's buffer; its last block
+ *                       raises this rank's flag everywhere.  No extra launch.  Every rank of the job must make the same
+ *                       sequence of scatter calls.  The reading side, one of:
+ *   hsl_gather_wait     one small kernel that waits for all ranks' flags of the latest scatter; *d_all_cot /
+ *                       *d_all_status point at [nranks][n_per_rank] arrays in this rank's buffer (unused tail entries
+ *                       NaN / 0), complete for work queued on `stream` afterwards and valid until the second-next
+ *                       scatter on this object (two buffers alternate);
+ *   hsl_gather_select_best  hsl_select_best over the gathered costs with the wait as the kernel's first instructions;
+ *   hsl_eval_gaits_gather = scatter + wait.
  *   hsl_gather_free     unmaps and frees; all ranks must have finished using the buffers (barrier first). */
 typedef struct HslGather HslGather;
 typedef struct HslIpcHandle { char internal[64]; } HslIpcHandle; /* cudaIpcMemHandle_t */
 int hsl_gather_create(int nranks, int rank, int64_t n_per_rank, HslGather** g, HslIpcHandle* mine);
 int hsl_gather_connect(HslGather* g, const HslIpcHandle* all);
 int hsl_gather_free(HslGather* g);
+int hsl_eval_gaits_scatter(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot,
+                           double* d_work, double* d_min_cfz, double* d_max_mu, int32_t* d_status, void* stream);
+int hsl_gather_wait(HslGather* g, const double** d_all_cot, const int32_t** d_all_status, void* stream);
+int hsl_gather_select_best(HslGather* g, int64_t* d_index, double* d_value, void* stream);
 int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot,
                           double* d_work, double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot,
                           const int32_t** d_all_status, void* stream);

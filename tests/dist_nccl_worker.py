@@ -46,6 +46,24 @@ def main(out_dir):
     for sub, c in outs:
         want = model.eval_gaits(sub.cpu().numpy(), n_t)["cot"]
         assert np.array_equal(c.cpu().numpy(), want, equal_nan=True), "gathered costs differ after back-to-back calls"
+    # the fused form the bench uses: scatter (no extra launch) + an argmin kernel that waits for the flags itself
+    from hslabs_b200 import api
+    per = -(-n // world)
+    lo, hi = min(rank * per, n), min(rank * per + per, n)
+    g = api.torch_gather(dist, per)
+    best = torch.empty(1, dtype=torch.int64, device=dev)
+    bval = torch.empty(1, dtype=torch.float64, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    key = np.where(np.isnan(single["cot"]), np.inf, single["cot"])
+    for it in range(10):
+        if it % 3 == rank % 3:
+            torch.cuda._sleep(10_000_000)
+        model.eval_gaits_scatter(g, hi - lo, n_t, cand[lo:hi].contiguous().data_ptr(), stream=s)
+        g.select_best(best.data_ptr(), bval.data_ptr(), s)
+        assert int(best.item()) == int(np.argmin(key)) and float(bval.item()) == float(key.min())
+    torch.cuda.synchronize()
+    dist.barrier()
+    g.free()
     # an empty shard (fewer candidates than ranks) and a batch of one
     for k in (1, world - 1 if world > 1 else 1):
         c1, _ = ev(cand[:k])

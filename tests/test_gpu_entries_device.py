@@ -119,6 +119,12 @@ def test_gather_object_with_one_rank(hsl):
         if k:
             assert np.array_equal(cot.cpu().numpy()[:k], want["cot"][:k], equal_nan=True)
     assert ptrs[0] != ptrs[1] and ptrs[0] == ptrs[2]
+    best = torch.empty(1, dtype=torch.int64, device="cuda")
+    bval = torch.empty(1, dtype=torch.float64, device="cuda")
+    m.eval_gaits_scatter(g, n, n_t, d.data_ptr())
+    g.select_best(best.data_ptr(), bval.data_ptr())
+    key = np.where(np.isnan(want["cot"]), np.inf, want["cot"])
+    assert int(best.item()) == int(np.argmin(key)) and float(bval.item()) == float(key.min())
     with pytest.raises(hsl.HslError):
         m.eval_gaits_gather(g, per + 1, n_t, d.data_ptr())
     g.free()
