@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0)
     ap.add_argument("--fb", type=int, default=0, help="frame slots per block (32/64), 0 = library default")
     ap.add_argument("--maxreg", type=int, default=0, help="register cap of the cost-only kernel variant (1 = pipelined), 0 = library default")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl", "none"], help="N > 1: costs all-gathered by the finish kernel over NVLink peer memory (hsl_eval_gaits_gather) or by NCCL after it; none = diagnostic only (no collective: shows the ranks' own step times), its line is not a bench result")
+    ap.add_argument("--gather", default="auto", choices=["auto", "peer", "nccl", "none"], help="N > 1: costs all-gathered by the finish kernel over NVLink peer memory (hsl_eval_gaits_gather) or by NCCL after it; none = diagnostic only (no collective: shows the ranks' own step times), its line is not a bench result")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and parity legs")
     ap.add_argument("--no-extras", action="store_true", help="skip the sustained and config3 sub-records")
     args = ap.parse_args()
@@ -263,7 +263,11 @@ def main():
             self.d_work = torch.empty(self.per, dtype=torch.float64, device=dev)
             self.d_status = torch.zeros(self.per, dtype=torch.int32, device=dev)
             self.gathered = torch.empty(ranks * self.per, dtype=torch.float64, device=dev) if ranks > 1 else None
-            self.peer = api.torch_gather(dist, self.per) if (ranks > 1 and args.gather == "peer") else None   # collective: every rank builds the same jobs
+            self.peer = None
+            if ranks > 1 and args.gather in ("auto", "peer"):   # collective: every rank builds the same jobs
+                self.peer = api.torch_gather(dist, self.per, fallback=(args.gather == "auto"))
+                if self.peer is None and my_rank == 0:
+                    sys.stderr.write("bench.py: the ranks cannot map each other's gather buffers; costs go through NCCL\n")
             self.best = torch.empty(1, dtype=torch.int64, device=dev)
 
         def step(self):
@@ -276,7 +280,7 @@ def main():
                 self.model.eval_gaits_device(self.n_local, self.n_t, self.d_params.data_ptr(), self.d_cot.data_ptr(), self.d_work.data_ptr(),
                                              0, 0, self.d_status.data_ptr(), 0, stream)
             costs = self.d_cot
-            if self.ranks > 1 and args.gather != "none":
+            if self.ranks > 1 and args.gather != "none":   # NCCL form
                 dist.all_gather_into_tensor(self.gathered, self.d_cot)
                 costs = self.gathered
             api.select_best_device(costs.data_ptr(), costs.numel(), self.best.data_ptr(), 0, stream)   # selection on every rank
@@ -340,10 +344,16 @@ def main():
 
     # end to end through the host-buffer C-ABI call (H2D of the candidates + D2H of the costs inside the timed region)
     e2e_t = []
+    pin_params = hsl.pinned_empty(head.params.shape)          # the step's inputs in pinned host memory, as the contract asks
+    pin_params[...] = head.params
+    pin_out = dict(cot=hsl.pinned_empty((head.n_local,)), work=hsl.pinned_empty((head.n_local,)), min_cfz=hsl.pinned_empty((head.n_local,)),
+                   max_mu=hsl.pinned_empty((head.n_local,)), status=hsl.pinned_empty((head.n_local,), np.int32))
     for i in range(max(3, min(args.steps, 10))):
         t0 = time.perf_counter()
-        out = head.model.eval_gaits(head.params, n_t)
+        out = head.model.eval_gaits(pin_params, n_t, out=pin_out)
         e2e_t.append(time.perf_counter() - t0)
+    if not np.array_equal(out["cot"], head.d_cot[:head.n_local].cpu().numpy()):
+        raise SystemExit("bench.py: the host-buffer call and the device-pointer call disagree on the costs")
     e2e_local = head.n_local * n_t / float(np.median(e2e_t[1:] if len(e2e_t) > 1 else e2e_t))
     if world > 1:
         t = torch.tensor([e2e_local], dtype=torch.float64, device=dev)
@@ -387,7 +397,7 @@ def main():
             "config": {"workload": head.w["name"] % (head.w["n_cand"] if not args.candidates else args.candidates, n_t),
                        "seed": SEED, "n_t": n_t, "candidates_per_gpu": head.per, "candidates_total": head.n_total,
                        "l2": "flushed between timed iterations (256 MiB fill)",
-                       "parallelism": ("candidates sharded, costs all-gathered (%s), argmin on every rank" % ("by the finish kernel over NVLink peer memory" if args.gather == "peer" else "NCCL")) if world > 1 else "single GPU",
+                       "parallelism": ("candidates sharded, costs all-gathered (%s), argmin on every rank" % ("by the finish kernel over NVLink peer memory" if head.peer is not None else "NCCL")) if world > 1 else "single GPU",
                        "mean_contacts": kbar, "kernel_variant": {"frame_slots_per_block": fb, "maxreg": mr,
                                                                  "kernel": "hsl_gait_pipe_kernel" if mr == 1 else "hsl_frames_kernel"}},
             "gpu_launches": launches,

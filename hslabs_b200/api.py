@@ -256,10 +256,13 @@ class Model:
         return buf
 
     # ---- batch evaluation, host buffers (the reference-facing call)
-    def eval_gaits(self, params, n_t, flags=0):
+    def eval_gaits(self, params, n_t, flags=0, out=None):
+        """hsl_eval_gaits_host.  params in page-locked memory (pinned_empty) are copied to the device from where they lie;
+        out: optional dict of preallocated result arrays."""
         params = np.ascontiguousarray(params, np.float64).reshape(-1, HSL_NPARAM)
         c = params.shape[0]
-        out = dict(cot=np.empty(c), work=np.empty(c), min_cfz=np.empty(c), max_mu=np.empty(c), status=np.empty(c, np.int32))
+        out = dict(cot=_out(out, "cot", (c,)), work=_out(out, "work", (c,)), min_cfz=_out(out, "min_cfz", (c,)), max_mu=_out(out, "max_mu", (c,)),
+                   status=_out(out, "status", (c,), np.int32))
         _check(_load().hsl_eval_gaits_host(self._h, c, n_t, _p(params), flags, _p(out["cot"]), _p(out["work"]),
                                            _p(out["min_cfz"]), _p(out["max_mu"]), _p(out["status"])))
         return out
@@ -419,12 +422,18 @@ class Gather:
     def __init__(self, rank, world, n_per_rank, exchange):
         self._g = C.c_void_p()
         mine = (C.c_char * 64)()
-        _check(_load().hsl_gather_create(world, rank, n_per_rank, C.byref(self._g), mine))
+        rc = _load().hsl_gather_create(world, rank, n_per_rank, C.byref(self._g), mine)
         self.rank, self.world, self.n_per_rank = rank, world, int(n_per_rank)
-        handles = exchange(bytes(mine.raw))
-        if len(handles) != world or any(len(h) != 64 for h in handles):
-            raise HslError("exchange() must return the 64-byte handle of every rank")
-        _check(_load().hsl_gather_connect(self._g, (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))))
+        handles = exchange(bytes(mine.raw) if rc == 0 else b"")   # a rank that failed still takes part in the exchange
+        _check(rc)
+        if len(handles) != world or any(h is None or len(h) != 64 for h in handles):
+            self.free()
+            raise HslError("exchange() must return the 64-byte handle of every rank (a rank failed to create its buffer?)")
+        rc = _load().hsl_gather_connect(self._g, (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles)))
+        if rc != 0:
+            msg = _load().hsl_last_error().decode()
+            self.free()
+            raise HslError("hsl error %d: %s" % (rc, msg))
 
     def select_best(self, d_index=0, d_value=0, stream=0):
         """hsl_gather_select_best: argmin over the costs of the latest scatter; the kernel itself waits for the ranks' flags."""
@@ -443,13 +452,29 @@ class Gather:
             self._g = C.c_void_p()
 
 
-def torch_gather(dist, n_per_rank):
-    """Gather object for the ranks of an initialised torch.distributed job (handles exchanged with all_gather_object)."""
+def torch_gather(dist, n_per_rank, fallback=False):
+    """Gather object for the ranks of an initialised torch.distributed job (handles exchanged with all_gather_object).
+    fallback=True: when any rank cannot create or map the buffers (no peer access between the GPUs, IPC not permitted in
+    the container ...) every rank frees what it has and None is returned, so that the caller can use the NCCL form --
+    the decision is collective.  fallback=False: raise on this rank."""
     def exchange(mine):
         box = [None] * dist.get_world_size()
         dist.all_gather_object(box, mine)
         return box
-    return Gather(dist.get_rank(), dist.get_world_size(), n_per_rank, exchange)
+    if not fallback:
+        return Gather(dist.get_rank(), dist.get_world_size(), n_per_rank, exchange)
+    g, err = None, None
+    try:
+        g = Gather(dist.get_rank(), dist.get_world_size(), n_per_rank, exchange)
+    except Exception as e:   # HslError, or a malformed exchange because another rank failed before it
+        err = e
+    oks = [None] * dist.get_world_size()
+    dist.all_gather_object(oks, err is None)
+    if all(oks):
+        return g
+    if g is not None:
+        g.free()
+    return None
 
 
 class NcclComm:

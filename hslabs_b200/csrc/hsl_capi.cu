@@ -494,6 +494,12 @@ static int fetch_transposed(HslModel* m, const void* dsrc, int comps, int64_t nf
   return HSL_OK;
 }
 
+static bool host_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 static int eval_gaits_host_impl(HslModel* m, int64_t C, int n_t, const double* params, int flags, double* cot, double* work,
                                 double* min_cfz, double* max_mu, int32_t* status, bool dump, double* traj, double* x, double* z,
                                 double* tau, uint8_t* contacts) {
@@ -504,11 +510,15 @@ static int eval_gaits_host_impl(HslModel* m, int64_t C, int n_t, const double* p
   if ((rc = ensure_stream(m))) return rc;
   cudaStream_t st = m->stream;
   const size_t pbytes = sizeof(double) * HSL_NPARAM * C;
-  HSL_CUDA(m->pin_in.need(pbytes));
   HSL_CUDA(m->params.need(pbytes));
   HSL_CUDA(m->out4.need(sizeof(double) * 4 * C + sizeof(int32_t) * C));
-  memcpy(m->pin_in.p, params, pbytes);
-  HSL_CUDA(cudaMemcpyAsync(m->params.p, m->pin_in.p, pbytes, cudaMemcpyHostToDevice, st));
+  const void* src = params;
+  if (!host_pinned(params)) {   // pageable input: stage it (a page-locked array, e.g. from hsl_pinned_alloc, is copied from where it lies)
+    HSL_CUDA(m->pin_in.need(pbytes));
+    memcpy(m->pin_in.p, params, pbytes);
+    src = m->pin_in.p;
+  }
+  HSL_CUDA(cudaMemcpyAsync(m->params.p, src, pbytes, cudaMemcpyHostToDevice, st));
   double* d4 = (double*)m->out4.p;
   int32_t* dst = (int32_t*)(d4 + 4 * C);
   rc = eval_gaits_dev(m, C, n_t, (const double*)m->params.p, flags, d4, d4 + C, d4 + 2 * C, d4 + 3 * C, dst, dump, st);

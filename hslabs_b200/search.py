@@ -38,17 +38,18 @@ class _DeviceArray:
 
 class DeviceEvaluator:
     """Evaluates candidate rows resident on the device; shards over ranks when torch.distributed is initialised.
-    gather="peer" (default): costs and status are all-gathered by the evaluation's own finish kernel over NVLink peer
-    memory (hsl_eval_gaits_gather); gather="nccl": two torch.distributed all-gathers after it."""
+    gather="peer": costs and status are all-gathered by the evaluation's own finish kernel over NVLink peer memory
+    (hsl_eval_gaits_gather); gather="nccl": two torch.distributed all-gathers after it; gather="auto" (default): peer memory,
+    or NCCL when the ranks cannot map each other's buffers (decided collectively, once per batch size)."""
 
-    def __init__(self, model, n_t, flags=0, gather="peer"):
+    def __init__(self, model, n_t, flags=0, gather="auto"):
         import torch
         self.torch, self.model, self.n_t, self.flags = torch, model, n_t, flags
         self.dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
         self.world = self.dist.get_world_size() if self.dist else 1
         self.rank = self.dist.get_rank() if self.dist else 0
-        if gather not in ("peer", "nccl"):
-            raise ValueError("gather must be 'peer' or 'nccl'")
+        if gather not in ("peer", "nccl", "auto"):
+            raise ValueError("gather must be 'auto', 'peer' or 'nccl'")
         self.gather = gather
         self._gathers = {}   # candidates per rank -> api.Gather
 
@@ -58,7 +59,8 @@ class DeviceEvaluator:
             self.torch.cuda.synchronize()
             self.dist.barrier()
             for g in self._gathers.values():
-                g.free()
+                if g is not None:
+                    g.free()
             self._gathers = {}
 
     def __call__(self, cand):
@@ -67,11 +69,13 @@ class DeviceEvaluator:
         c = cand.shape[0]
         per = -(-c // self.world)
         lo, hi = min(self.rank * per, c), min(self.rank * per + per, c)
-        if self.dist and self.gather == "peer":
+        g = None
+        if self.dist and self.gather != "nccl":
             from . import api
-            g = self._gathers.get(per)
-            if g is None:
-                g = self._gathers[per] = api.torch_gather(self.dist, per)
+            if per not in self._gathers:
+                self._gathers[per] = api.torch_gather(self.dist, per, fallback=(self.gather == "auto"))
+            g = self._gathers[per]
+        if g is not None:
             local = cand[lo:hi].contiguous() if hi > lo else None
             p_cot, p_st = self.model.eval_gaits_gather(g, hi - lo, self.n_t, local.data_ptr() if hi > lo else 0, flags=self.flags,
                                                        stream=torch.cuda.current_stream().cuda_stream)

@@ -64,6 +64,23 @@ def main(out_dir):
     torch.cuda.synchronize()
     dist.barrier()
     g.free()
+    # gather="auto" when a rank cannot map the buffers: every rank falls back to NCCL, same results
+
+    class _FailingLib:
+        def __getattr__(self, name):
+            if name == "hsl_gather_connect" and rank == world - 1:
+                return lambda *a: -4
+            return getattr(real_lib, name)
+    real_lib = api._load()
+    api._lib = _FailingLib()
+    try:
+        assert api.torch_gather(dist, 64, fallback=True) is None
+        ev_auto = search.DeviceEvaluator(model, n_t, gather="auto")
+        cot_a, st_a = ev_auto(cand)
+        assert ev_auto._gathers and all(v is None for v in ev_auto._gathers.values())
+        assert torch.equal(cot_a.nan_to_num(nan=-1.0), cot.nan_to_num(nan=-1.0)) and torch.equal(st_a, st)
+    finally:
+        api._lib = real_lib
     # an empty shard (fewer candidates than ranks) and a batch of one
     for k in (1, world - 1 if world > 1 else 1):
         c1, _ = ev(cand[:k])
