@@ -20,6 +20,7 @@
 
 #include "hsl_forces.h"
 #include "hsl_frame.h"
+#include "hsl_gather_dev.cuh"
 #include "hsl_internal.h"
 #include "hsl_pipe.h"
 

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "hsl_gather_dev.cuh"
 #include "hsl_internal.h"
 
 namespace {
