@@ -96,6 +96,9 @@ def _load():
     lib.hsl_eval_gaits_scatter.argtypes = [vp, vp, i64, i32, vp, i32] + [vp] * 6
     lib.hsl_gather_wait.argtypes = [vp, vp, vp, vp]
     lib.hsl_gather_select_best.argtypes = [vp, vp, vp, vp]
+    lib.hsl_gather_size.argtypes = [vp]
+    lib.hsl_gather_size.restype = i64
+    lib.hsl_eval_gaits_gather_host.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
     _lib = lib
     return lib
 
@@ -108,7 +111,7 @@ def exported_symbols():
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
             "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host", "hsl_set_fall_variant",
             "hsl_gather_create", "hsl_gather_connect", "hsl_gather_free", "hsl_eval_gaits_gather", "hsl_eval_gaits_scatter",
-            "hsl_gather_wait", "hsl_gather_select_best"]
+            "hsl_gather_wait", "hsl_gather_select_best", "hsl_gather_size", "hsl_eval_gaits_gather_host", "hsl_set_device"]
 
 
 class _Pinned:

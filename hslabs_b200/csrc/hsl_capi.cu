@@ -91,6 +91,10 @@ extern "C" {
 
 const char* hsl_last_error(void) { return g_err; }
 
+int hsl_set_device(int device) {
+  HSL_CUDA(cudaSetDevice(device));
+  return HSL_OK;
+}
 int hsl_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -410,6 +414,7 @@ int hsl_gather_connect(HslGather* g, const HslIpcHandle* all) {
   g->connected = true;
   return HSL_OK;
 }
+int64_t hsl_gather_size(const HslGather* g) { return g ? (int64_t)g->nranks * g->per : 0; }
 int hsl_gather_free(HslGather* g) {
   if (!g) return HSL_OK;
   cudaDeviceSynchronize();
@@ -475,6 +480,8 @@ int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, co
   if (m) m->launches += 1;
   return hsl_gather_wait(g, d_all_cot, d_all_status, stream);
 }
+
+static int ensure_stream(HslModel* m);
 
 static int ensure_stream(HslModel* m) {
   if (!m->stream) HSL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
@@ -542,6 +549,30 @@ static int eval_gaits_host_impl(HslModel* m, int64_t C, int n_t, const double* p
     if ((rc = fetch_transposed(m, m->dump_q.p, P.config_dim, C * (n_t + 4), traj, st))) return rc;
     if ((rc = fetch_transposed(m, m->dump_c.p, P.nf, nfr, contacts, st, 1))) return rc;
   }
+  return HSL_OK;
+}
+
+// HOST arrays in, the gathered HOST arrays out: for hosts that keep no device memory of their own (the C++ mirror's sharded
+// measure_cot_sweep).  Synchronous.
+int hsl_eval_gaits_gather_host(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* params, int flags, double* all_cot,
+                               int32_t* all_status) {
+  if (!m || !g || n_cand < 0 || (n_cand > 0 && !params)) return set_err(HSL_ERR_ARG, "bad argument");
+  int rc = ensure_stream(m);
+  if (rc) return rc;
+  cudaStream_t st = m->stream;
+  if (n_cand > 0) {
+    const size_t pbytes = sizeof(double) * HSL_NPARAM * n_cand;
+    HSL_CUDA(m->params.need(pbytes));
+    HSL_CUDA(cudaMemcpyAsync(m->params.p, params, pbytes, cudaMemcpyHostToDevice, st));
+  }
+  const double* d_all = nullptr;
+  const int32_t* d_st = nullptr;
+  rc = hsl_eval_gaits_gather(m, g, n_cand, n_t, (const double*)m->params.p, flags, nullptr, nullptr, nullptr, nullptr, nullptr, &d_all, &d_st, st);
+  if (rc) return rc;
+  const size_t n = (size_t)hsl_gather_size(g);
+  if (all_cot) HSL_CUDA(cudaMemcpyAsync(all_cot, d_all, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  if (all_status) HSL_CUDA(cudaMemcpyAsync(all_status, d_st, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  HSL_CUDA(cudaStreamSynchronize(st));
   return HSL_OK;
 }
 

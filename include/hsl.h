@@ -62,6 +62,8 @@ int hsl_model_tables(const HslModel* m, int32_t* parent, int32_t* footis, int32_
 size_t hsl_model_pod(const HslModel* m, void* dst, size_t cap);
 const char* hsl_last_error(void);
 int hsl_device_count(void);
+int hsl_set_device(int device);   /* cudaSetDevice for hosts that do not link the CUDA runtime themselves: handles, gather buffers and
+                                  * launches of the calling thread go to this device (one process per GPU: call it first) */
 
 /* Two deliberate differences from the reference's outputs, valid for every entry below:
  *  - min_cfz / max_mu are taken over the feet ON THE GROUND.  periodic::analyze_contforces (periodic.cpp:347-357) loops
@@ -197,7 +199,10 @@ int hsl_allgather_costs_host(void* nccl_comm, int nranks, const double* local, i
  *                       scatter on this object (two buffers alternate);
  *   hsl_gather_select_best  hsl_select_best over the gathered costs with the wait as the kernel's first instructions;
  *   hsl_eval_gaits_gather = scatter + wait.
- *   hsl_gather_free     unmaps and frees; all ranks must have finished using the buffers (barrier first). */
+ *   hsl_gather_free     unmaps and frees.  Safe once this rank has completed the reading side (wait / select_best /
+ *                       gather, stream synchronised) of the last scatter: by then every rank's stores into this rank's
+ *                       buffer have landed, and a rank only ever reads its own buffer.  A rank that scattered without
+ *                       reading must not free before the other ranks have read (barrier first). */
 typedef struct HslGather HslGather;
 typedef struct HslIpcHandle { char internal[64]; } HslIpcHandle; /* cudaIpcMemHandle_t */
 int hsl_gather_create(int nranks, int rank, int64_t n_per_rank, HslGather** g, HslIpcHandle* mine);
@@ -210,6 +215,11 @@ int hsl_gather_select_best(HslGather* g, int64_t* d_index, double* d_value, void
 int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* d_params, int flags, double* d_cot,
                           double* d_work, double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot,
                           const int32_t** d_all_status, void* stream);
+int64_t hsl_gather_size(const HslGather* g);   /* nranks * n_per_rank: entries of the gathered arrays */
+/* the same with HOST arrays (params [n_cand][13] in; all_cot / all_status [nranks * n_per_rank] out, either may be NULL);
+ * synchronous -- for hosts that keep no device memory of their own, e.g. the C++ mirror's sharded measure_cot_sweep */
+int hsl_eval_gaits_gather_host(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* params, int flags, double* all_cot,
+                               int32_t* all_status);
 
 /* Page-locked host memory for input / output arrays of the *_host entries (they copy straight from / into the caller's
  * buffers; pageable memory works too, at the driver's staged-copy rate).  NULL on failure. */

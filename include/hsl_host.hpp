@@ -470,10 +470,13 @@ inline void save_2d_array(double** array, int n, int m, const std::string& fname
 // modelplayer: the evaluation entry points (player.cpp:147-208, 230-285, 311-321, 619-655)
 // One process per GPU: rank / world and the NCCL communicator the costs are all-gathered over (hsl_nccl_comm_init or
 // the host application's own ncclComm_t).  world == 1: single GPU, no collective.
+// gather (optional): a connected HslGather of this job (hsl_gather_create / hsl_gather_connect) -- the costs then travel
+// over NVLink peer memory inside the evaluation instead of through NCCL after it.
 struct shard {
   int rank, world;
   void* nccl_comm;
-  shard() : rank(0), world(1), nccl_comm(nullptr) {}
+  HslGather* gather;
+  shard() : rank(0), world(1), nccl_comm(nullptr), gather(nullptr) {}
 };
 
 class modelplayer {
@@ -574,11 +577,17 @@ class modelplayer {
       const int64_t c = (int64_t)vals.size(), per = (c + shard_.world - 1) / shard_.world;
       const int64_t lo = std::min<int64_t>(shard_.rank * per, c), hi = std::min<int64_t>(lo + per, c);
       std::vector<double> local(per, std::nan("")), all((size_t)per * shard_.world);
+      if (shard_.gather) {   // per must equal the gather object's n_per_rank
+        if (hsl_gather_size(shard_.gather) != per * shard_.world) throw error("ERROR: the gather object is sized for another sweep");
+        check(hsl_eval_gaits_gather_host(model_.handle(), shard_.gather, hi - lo, n_t, hi > lo ? &rows[(size_t)lo * HSL_NPARAM] : nullptr, flags_,
+                                         all.data(), nullptr));
+      } else {
       if (hi > lo) {
         std::vector<int32_t> status(hi - lo);
         check(hsl_eval_gaits_host(model_.handle(), hi - lo, n_t, &rows[(size_t)lo * HSL_NPARAM], flags_, local.data(), nullptr, nullptr, nullptr, status.data()));
       }
       check(hsl_allgather_costs_host(shard_.nccl_comm, shard_.world, local.data(), per, all.data()));
+      }
       for (int64_t i = 0; i < c; i++) cot[i] = all[i];  // rank r's block starts at r*per: contiguous for all but the padding
     }
     if (shard_.rank == 0)

@@ -10,6 +10,7 @@
 int main(int argc, char** argv) {
   if (argc < 4) { std::fprintf(stderr, "usage: %s <presets> <model_dir> <preset_id> [traj_out]\n", argv[0]); return 2; }
   try {
+    if (const char* d = std::getenv("HSL_DEVICE")) hsl::check(hsl_set_device(std::atoi(d)));   // one process per GPU, all GPUs visible
     hsl::modelplayer player0;
     player0.set_play_dt(.02);
     hsl::pergensetup* pgs = player0.make_pergensu(argv[1], std::atoi(argv[3]), argv[2]);
@@ -134,6 +135,36 @@ int main(int argc, char** argv) {
       for (size_t i = 0; i < c2.size(); i++) std::printf(" %.17g", c2[i]);
       std::printf("\n");
       hsl::check(hsl_nccl_comm_destroy(sh.nccl_comm));
+      // the same sweep with the costs gathered over NVLink peer memory by the evaluation's own finish kernel: every rank
+      // publishes the IPC handle of its gather buffer as a file next to the NCCL id and maps the others'
+      if (std::getenv("HSL_GATHER_FILES")) {
+        const int64_t per = (16 + sh.world - 1) / sh.world;   // the sweep below has n_val + 1 = 16 points
+        HslIpcHandle mine;
+        std::vector<HslIpcHandle> all(sh.world);
+        hsl::check(hsl_gather_create(sh.world, sh.rank, per, &sh.gather, &mine));
+        {
+          const std::string fn = idf + ".ipc" + std::to_string(sh.rank);
+          FILE* f = std::fopen((fn + ".tmp").c_str(), "wb");
+          std::fwrite(&mine, sizeof mine, 1, f);
+          std::fclose(f);
+          std::rename((fn + ".tmp").c_str(), fn.c_str());
+        }
+        for (int r = 0; r < sh.world; r++) {
+          const std::string fn = idf + ".ipc" + std::to_string(r);
+          FILE* f = nullptr;
+          for (int tries = 0; tries < 600 && !(f = std::fopen(fn.c_str(), "rb")); tries++) { struct timespec ts = {0, 100000000}; nanosleep(&ts, nullptr); }
+          if (!f || std::fread(&all[r], sizeof(HslIpcHandle), 1, f) != 1) throw hsl::error("no gather handle from a rank");
+          std::fclose(f);
+        }
+        hsl::check(hsl_gather_connect(sh.gather, all.data()));
+        player0.set_shard(sh);
+        std::vector<double> v3, c3;
+        player0.measure_cot_sweep(pgs, 20, "period", 3, 18, 15, &v3, &c3);
+        std::printf("peer-gathered sweep rank %d:", sh.rank);
+        for (size_t i = 0; i < c3.size(); i++) std::printf(" %.17g", c3[i]);
+        std::printf("\n");
+        hsl::check(hsl_gather_free(sh.gather));   // safe: this rank has waited for every rank's flags of the last scatter
+      }
     }
     delete pgs;
   } catch (const std::exception& e) {

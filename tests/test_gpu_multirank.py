@@ -51,7 +51,7 @@ def test_cpp_mirror_sharded_sweep(hsl, orc, tmp_path):
     idf = str(tmp_path / "nccl_id.bin")
     procs = []
     for r in range(2):
-        env = dict(os.environ, HSL_RANK=str(r), HSL_WORLD="2", HSL_NCCL_ID_FILE=idf, CUDA_VISIBLE_DEVICES=str(r))
+        env = dict(os.environ, HSL_RANK=str(r), HSL_WORLD="2", HSL_NCCL_ID_FILE=idf, HSL_GATHER_FILES="1", HSL_DEVICE=str(r))   # both GPUs visible (peer mapping)
         procs.append(subprocess.Popen([exe, PRESETS, MODELS, "8"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = [p.communicate(timeout=500) for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
@@ -60,3 +60,5 @@ def test_cpp_mirror_sharded_sweep(hsl, orc, tmp_path):
     for r, (so, _) in enumerate(outs):
         got = np.array([float(v) for v in re.search(r"sharded sweep rank %d:(.*)" % r, so).group(1).split()])
         assert got.shape == (16,) and np.abs(got - cots).max() <= 1e-9 * np.abs(cots).max()
+        peer = np.array([float(v) for v in re.search(r"peer-gathered sweep rank %d:(.*)" % r, so).group(1).split()])
+        assert np.array_equal(peer, got)   # NVLink peer-memory gather: the same costs as through NCCL
