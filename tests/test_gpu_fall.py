@@ -107,3 +107,25 @@ def test_warp_per_world_kernel_equals_the_thread_per_world_kernel(hsl, pid):
     assert np.array_equal(a["t_end"], b["t_end"])
     assert d < 1e-9
     assert a["fell"].any() and not a["fell"].all()
+
+
+@pytest.mark.parametrize("pid,kick_max,hc", [(9, 16.0, 0.6), (24, 64.0, 0.4)])
+def test_fall_statistics_on_the_other_models(hsl, tmp_path, pid, kick_max, hc):
+    """The statistical comparison on the four-limbed myant and the spider (other hinge pattern, other body count): 2048
+    random kicks each, fall rate and per-world outcomes against the CPU stepper."""
+    params, name = hsl.load_preset(PRESETS, pid)
+    xml = model_xml(name)
+    rng = np.random.default_rng(1000 + pid)
+    w, n_steps = 2048, 300
+    mag, th = rng.uniform(0, kick_max, w), rng.uniform(0, 2 * np.pi, w)
+    kicks = np.stack([mag * np.cos(th), mag * np.sin(th), np.zeros(w)], axis=1)
+    ks = rng.integers(25, 175, w).astype(np.int32)
+    cpu = cpu_side(tmp_path, xml, params, n_steps, ks, kicks, hc=hc)
+    gpu = hsl.Model(xml).fall_sweep(params, n_steps, ks, kicks, hc=hc)
+    fr_c, fr_g = cpu["fell"].mean(), gpu["fell"].mean()
+    print("preset %d (%s): fall rate cpu %.4f gpu %.4f, per-world agreement %.4f, kernel %.1f ms" %
+          (pid, name, fr_c, fr_g, (cpu["fell"] == gpu["fell"]).mean(), gpu["kernel_ms"]))
+    assert (gpu["status"] == 0).all()
+    assert 0.03 < fr_c < 0.97
+    assert abs(fr_c - fr_g) <= 0.03
+    assert (cpu["fell"] == gpu["fell"]).mean() >= 0.95
