@@ -368,15 +368,35 @@ __global__ void hsl_fk_records_kernel(const __grid_constant__ HslModelPod M, int
 
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
                                  HslCand* __restrict__ cand, double* __restrict__ ttab, int32_t* __restrict__ status) {
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= n_cand) return;
-  double p[HSL_NPARAM];
+  // One warp per block, lane = candidate.  The frame times are an accumulated sum (t += dt, periodic.cpp:87-91), sequential
+  // per candidate; written lane by lane they would be 32 scattered 8-byte stores per step (the kernel then spends 18 us on
+  // 4096 x 260 of them), so the warp stages 32 steps of its 32 candidates in shared memory and writes whole 256-byte rows.
+  __shared__ double tile[32][33];
+  const int lane = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * 32, c = c0 + lane;
+  const bool valid = c < n_cand;
+  double dt = 0;
+  if (valid) {
+    double p[HSL_NPARAM];
 #pragma unroll
-  for (int k = 0; k < HSL_NPARAM; k++) p[k] = params[c * HSL_NPARAM + k];
-  HslCand cd;
-  setup_candidate(M, p, n_t, cd, ttab + c * (n_t + 4));
-  cand[c] = cd;
-  status[c] = cd.status;
+    for (int k = 0; k < HSL_NPARAM; k++) p[k] = params[c * HSL_NPARAM + k];
+    HslCand cd;
+    setup_candidate(M, p, n_t, cd, nullptr);
+    cand[c] = cd;
+    status[c] = cd.status;
+    dt = cd.dt;
+  }
+  const int per = n_t + 4;
+  const int rows = (int)((n_cand - c0 < 32) ? n_cand - c0 : 32);
+  double t = 0;
+  for (int i0 = 0; i0 < per; i0 += 32) {
+#pragma unroll 8
+    for (int j = 0; j < 32; j++) { tile[lane][j] = t; t += dt; }   // the same recurrence as setup_candidate's own table
+    __syncwarp();
+    if (i0 + lane < per)
+      for (int r = 0; r < rows; r++) ttab[(c0 + r) * per + i0 + lane] = tile[r][lane];
+    __syncwarp();
+  }
 }
 
 // One warp per candidate.  periodic::work_over_period (periodic.cpp:285-307) and modelplayer::measure_cot
@@ -394,10 +414,21 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
   }
   const double dt = cand ? cand[c].dt : dt_in[c];
   double w = 0, mn = 1e10, mx = -1e10;  // periodic.cpp:380
-  for (int f = lane; f < n_t; f += 32) {
-    w += wframe[c * n_t + f] * dt;
-    mn = fmin(mn, fmin_in[c * n_t + f]);
-    mx = fmax(mx, fmax_in[c * n_t + f]);
+  // four strides of loads in flight per lane (the kernel is a chain of L2 round trips otherwise); accumulated in the same order
+  for (int f0 = lane; f0 < n_t; f0 += 128) {
+    double a[4], b[4], d[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int f = f0 + 32 * u;
+      const bool in = f < n_t;
+      a[u] = in ? wframe[c * n_t + f] : 0.0;
+      b[u] = in ? fmin_in[c * n_t + f] : 1e10;
+      d[u] = in ? fmax_in[c * n_t + f] : -1e10;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (f0 + 32 * u < n_t) { w += a[u] * dt; mn = fmin(mn, b[u]); mx = fmax(mx, d[u]); }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
