@@ -137,46 +137,73 @@ def random_search(model, base, ranges, n_cand, n_t, seed=0, k=1, flags=0, device
     return dict(candidates=cand, cot=cot, status=st, best_index=idx, best_cot=best)
 
 
-def cem_search(model, base, ranges, n_t, pop=1024, elite=64, iters=8, seed=0, flags=0, device="cuda"):
+def cem_search(model, base, ranges, n_t, pop=1024, elite=64, iters=8, seed=0, flags=0, device="cuda", graph="auto"):
     """Cross-entropy method over the named parameters: sample a Gaussian population, evaluate, refit to the elite.
     The loop never synchronises with the host: population, costs, elite set, the Gaussian's moments and the running best
     stay on the device (an iteration without a single valid candidate leaves the distribution unchanged); results are
-    read back once at the end."""
+    read back once at the end.
+    graph: an iteration is ~40 small launches (sampling, the three evaluation kernels, the top-k sort, the refit), i.e.
+    launch bound for populations of a few thousand candidates (measured, 2048 candidates x 32 frames: 401 us per iteration);
+    with graph=True the second iteration is captured into a CUDA graph and the remaining ones are replays of it (213 us per
+    iteration, same random stream and results; capture and instantiation cost ~10 ms once, so "auto" switches it on from 64
+    iterations, on a single rank).  Multi-rank searches stay eager: the peer-memory gather numbers its calls on the host."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
     names = list(ranges)
     lo = torch.tensor([ranges[n][0] for n in names], dtype=torch.float64, device=device)
     hi = torch.tensor([ranges[n][1] for n in names], dtype=torch.float64, device=device)
-    mean, std = (lo + hi) / 2, (hi - lo) / 2
-    cols = [SWEEP_NAMES[n] for n in names]
+    mean, std = ((lo + hi) / 2).clone(), ((hi - lo) / 2).clone()
+    cols = torch.tensor([SWEEP_NAMES[n] for n in names], dtype=torch.int64, device=device)
     base_t = torch.from_numpy(np.asarray(base, np.float64)).to(device)
     ev = DeviceEvaluator(model, n_t, flags)
     inf = torch.tensor(float("inf"), dtype=torch.float64, device=device)
     best_cot = inf.clone()
     best_cand = torch.full((HSL_NPARAM,), float("nan"), dtype=torch.float64, device=device)
-    history = []
-    for _ in range(iters):
+    history = torch.full((max(iters, 1),), float("inf"), dtype=torch.float64, device=device)
+    it = torch.zeros(1, dtype=torch.int64, device=device)
+
+    def iteration():   # everything in place: the same function runs eagerly and under capture
         z = torch.randn(pop, len(names), dtype=torch.float64, device=device, generator=g)
         x = torch.minimum(torch.maximum(mean + std * z, lo), hi)
         cand = base_t.repeat(pop, 1)
-        cand[:, cols] = x
+        cand.index_copy_(1, cols, x)
         cot, st = ev(cand)
         idx, c = top_k(cot, elite, trim=False)          # padded with -1 / NaN past the valid candidates
         w = (idx >= 0).to(torch.float64)                  # elite membership weights
         cnt = w.sum()
-        el = x[idx.clamp(min=0)]
+        el = x.index_select(0, idx.clamp(min=0))
         m1 = (w[:, None] * el).sum(0) / cnt.clamp(min=1.0)
         var = (w[:, None] * (el - m1) ** 2).sum(0) / cnt.clamp(min=1.0)
         any_ok = cnt > 0
-        mean = torch.where(any_ok, m1, mean)
-        std = torch.where(any_ok, var.sqrt() + 1e-6 * (hi - lo), std)
+        mean.copy_(torch.where(any_ok, m1, mean))
+        std.copy_(torch.where(any_ok, var.sqrt() + 1e-6 * (hi - lo), std))
         cbest = torch.where(any_ok, c[0], inf)
-        history.append(cbest)
+        history.index_copy_(0, it, cbest.reshape(1))
+        it.add_(1)
         improved = cbest < best_cot
-        best_cand = torch.where(improved, cand[idx[0].clamp(min=0)], best_cand)
-        best_cot = torch.where(improved, cbest, best_cot)
-    hist = [float(v) for v in torch.stack(history).cpu()] if history else []   # the one read-back
+        first = cand.index_select(0, idx[:1].clamp(min=0))[0]   # (indexing with a 0-dim tensor would read it back on the host)
+        best_cand.copy_(torch.where(improved, first, best_cand))
+        best_cot.copy_(torch.where(improved, cbest, best_cot))
+
+    use_graph = (graph is True) or (graph == "auto" and ev.world == 1 and iters >= 64)
+    if use_graph and ev.world > 1:
+        raise ValueError("cem_search(graph=True) needs a single rank")
+    done = 0
+    if use_graph:
+        iteration()                                       # warm-up: grows every workspace the capture must not allocate
+        done = 1
+        cg = torch.cuda.CUDAGraph()
+        cg.register_generator_state(g)
+        with torch.cuda.graph(cg):
+            iteration()
+        for _ in range(iters - done):                     # capture does not execute: every remaining iteration is a replay
+            cg.replay()
+    else:
+        for _ in range(iters):
+            iteration()
+    hist = [float(v) for v in history[:iters].cpu()] if iters else []   # the one read-back
     hist = [v for v in hist if np.isfinite(v)]
     bc = float(best_cot)
+    ev.close() if ev.world > 1 else None
     return dict(best_cot=bc, best_candidate=best_cand if np.isfinite(bc) else None, history=hist, mean=mean, std=std)
