@@ -46,3 +46,25 @@ def torch_all_gather(dist, device=None):
         dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy()
     return fn
+
+
+def fall_sweep_sharded(sweep_fn, kick_step, kick_dv, world, rank, all_gather_fn):
+    """The fall / perturbation sweep over several ranks (BASELINE configs[4]: 1e6 perturbed worlds over 8 GPUs).  Worlds are
+    independent: rank r integrates its contiguous block of ceil(W/G) worlds with sweep_fn(kick_step, kick_dv) -> dict with
+    `fell`, `t_end`, `final_z` (Model.fall_sweep), and the three per-world results (17 B a world) are all-gathered.
+    all_gather_fn as in evaluate_sharded (float64 arrays).  Returns dict(fell uint8 [W], t_end [W], final_z [W])."""
+    ks = np.ascontiguousarray(kick_step, np.int32)
+    kv = np.ascontiguousarray(kick_dv, np.float64).reshape(-1, 3)
+    w = ks.shape[0]
+    lo, hi, per = shard_bounds(w, world, rank)
+    local = np.full((3, per), np.nan)
+    if hi > lo:
+        r = sweep_fn(ks[lo:hi], kv[lo:hi])
+        local[0, :hi - lo] = r["fell"]
+        local[1, :hi - lo] = r["t_end"]
+        local[2, :hi - lo] = r["final_z"]
+    out = []
+    for k in range(3):
+        g = np.asarray(all_gather_fn(local[k]), np.float64).reshape(world, per)
+        out.append(np.concatenate([g[q][:max(0, min(per, w - q * per))] for q in range(world)]))
+    return dict(fell=out[0].astype(np.uint8), t_end=out[1], final_z=out[2])

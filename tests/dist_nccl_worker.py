@@ -95,6 +95,18 @@ def main(out_dir):
     # the C-ABI collective (hsl_allgather_costs over an ncclComm_t created from a broadcast unique id)
     if hasattr(hsl.api, "nccl_allgather_selftest"):
         hsl.api.nccl_allgather_selftest(rank, world, dist, dev)
+    # the fall sweep sharded over the ranks: the same outcomes as all worlds on one GPU (worlds are independent)
+    from hslabs_b200.sharding import fall_sweep_sharded, torch_all_gather
+    fparams, _ = hsl.load_preset(os.path.join(ROOT, "hslabs_b200", "models", "pgs_presets.txt"), 8)
+    frng = np.random.default_rng(9)
+    fw = 67
+    fmag, fth = frng.uniform(0, 16, fw), frng.uniform(0, 2 * np.pi, fw)
+    fkv = np.stack([fmag * np.cos(fth), fmag * np.sin(fth), np.zeros(fw)], axis=1)
+    fks = frng.integers(5, 100, fw).astype(np.int32)
+    sh = fall_sweep_sharded(lambda a, b: model.fall_sweep(fparams, 200, a, b), fks, fkv, world, rank, torch_all_gather(dist, dev))
+    one = model.fall_sweep(fparams, 200, fks, fkv)
+    assert np.array_equal(sh["fell"], one["fell"]) and np.array_equal(sh["t_end"], one["t_end"]) and np.array_equal(sh["final_z"], one["final_z"])
+    assert one["fell"].any() and not one["fell"].all()
     ev.close()
     dist.barrier()
     open(os.path.join(out_dir, "rank%d.ok" % rank), "w").write("ok\n")

@@ -80,3 +80,34 @@ def test_selection_rule_matches_the_device_one():
     vals = np.array([2.0, np.nan, 1.0, 1.0])
     costs, best, order = evaluate_sharded(lambda p: vals, np.zeros((4, 13)), 1, 0, lambda x: x)
     assert best == 2 and list(order) == [2, 3, 0]
+
+
+def test_fall_sweep_sharding_logic():
+    """fall_sweep_sharded: contiguous blocks of worlds per rank, ragged and empty shards, results in world order."""
+    from hslabs_b200.sharding import fall_sweep_sharded, shard_bounds
+
+    def sweep(ks, kv):   # stands in for Model.fall_sweep on a rank's block
+        return dict(fell=(np.abs(kv[:, 1]) > 8).astype(np.uint8), t_end=ks * 0.02, final_z=kv[:, 0] + 0.5)
+    rng = np.random.default_rng(4)
+    for w, world in ((7, 2), (1, 4), (64, 8), (9, 4)):
+        ks = rng.integers(0, 100, w).astype(np.int32)
+        kv = rng.uniform(-16, 16, (w, 3))
+        want = sweep(ks, kv)
+        for rank in range(world):
+            def gather(local, _k=[0]):
+                k = _k[0] % 3
+                _k[0] += 1
+                per = local.shape[0]
+                rows = []
+                for q in range(world):
+                    lo, hi, _ = shard_bounds(w, world, q)
+                    row = np.full(per, np.nan)
+                    if hi > lo:
+                        r = sweep(ks[lo:hi], kv[lo:hi])
+                        row[:hi - lo] = (r["fell"], r["t_end"], r["final_z"])[k]
+                    rows.append(row)
+                assert np.array_equal(rows[rank], local, equal_nan=True)   # what this rank contributes is its own block
+                return np.concatenate(rows)
+            got = fall_sweep_sharded(sweep, ks, kv, world, rank, gather)
+            for key in ("fell", "t_end", "final_z"):
+                assert np.array_equal(got[key], want[key]), (w, world, rank, key)
