@@ -129,3 +129,30 @@ def test_fall_statistics_on_the_other_models(hsl, tmp_path, pid, kick_max, hc):
     assert 0.03 < fr_c < 0.97
     assert abs(fr_c - fr_g) <= 0.03
     assert (cpu["fell"] == gpu["fell"]).mean() >= 0.95
+
+
+def test_fall_sweep_argument_edges(hsl, tmp_path):
+    """No kicks at all (null arrays), a start inside the period (t0 > 0: initial pose from the gait's frame there), one world,
+    bad arguments; both kernels agree on each, and the t0 > 0 run follows the CPU stepper."""
+    params, name = hsl.load_preset(PRESETS, 8)
+    xml = model_xml(name)
+    m = hsl.Model(xml)
+    res = {}
+    for v in (0, 1):
+        m.set_fall_variant(v)
+        calm = m.fall_sweep(params, 80, n_worlds=3, want_traj=True)                 # kick_step = kick_dv = NULL
+        assert not calm["fell"].any() and np.array_equal(calm["traj"][0], calm["traj"][2])
+        late = m.fall_sweep(params, 120, [10], [[0.0, 12.0, 0.0]], t0=1.0, want_traj=True)   # one world, started at t = 1 s
+        res[v] = (calm, late)
+    assert np.array_equal(res[0][0]["traj"], res[1][0]["traj"]) and np.array_equal(res[0][1]["traj"], res[1][1]["traj"])
+    assert np.array_equal(res[0][1]["t_end"], res[1][1]["t_end"])
+    cpu = cpu_side(tmp_path, xml, params, 120, [10], [[0.0, 12.0, 0.0]], n_traj=1, t0=1.0)
+    n_ok = int(np.isfinite(cpu["traj"][0][:, 0]).sum())
+    assert np.abs(res[1][1]["traj"][0][:min(n_ok, 60)] - cpu["traj"][0][:min(n_ok, 60)]).max() < 1e-2
+    assert bool(res[1][1]["fell"][0]) == bool(cpu["fell"][0])
+    with pytest.raises(hsl.HslError):
+        m.fall_sweep(params, 0, [5], [[0, 1, 0]])
+    with pytest.raises(hsl.HslError):
+        m.fall_sweep(params, 10, [5], [[0, 1, 0]], play_dt=0.0)
+    with pytest.raises(hsl.HslError):
+        m.fall_sweep(params, 10, [5], [[0, 1, 0]], t0=100.0)             # beyond the recorded trajectory
