@@ -326,6 +326,8 @@ def main():
     step_ms, clocks, launches, _ = head.timed(args.steps, args.warmup)
     if world > 1 and os.environ.get("HSL_BENCH_RANK_TIMES"):
         sys.stderr.write("[rank %d] own ms per step: mean %.4f min %.4f max %.4f\n" % (rank, float(np.mean(step_ms)), min(step_ms), max(step_ms)))
+    if head.peer is not None:
+        head.peer.check()      # no wait of the peer-memory gather timed out
     ms_total = max_over_ranks(sum(step_ms))
     frames_per_step = head.n_total * n_t
     value = frames_per_step * args.steps / (ms_total * 1e-3)

@@ -97,6 +97,7 @@ def _load():
     lib.hsl_gather_wait.argtypes = [vp, vp, vp, vp]
     lib.hsl_gather_select_best.argtypes = [vp, vp, vp, vp]
     lib.hsl_gather_size.argtypes = [vp]
+    lib.hsl_gather_check.argtypes = [vp]
     lib.hsl_gather_size.restype = i64
     lib.hsl_eval_gaits_gather_host.argtypes = [vp, vp, i64, i32, vp, i32, vp, vp]
     _lib = lib
@@ -111,7 +112,7 @@ def exported_symbols():
             "hsl_dfma_probe", "hsl_math_selftest", "hsl_select_best", "hsl_select_topk", "hsl_eval_trajectories", "hsl_solve_frames",
             "hsl_fk_records_host", "hsl_nccl_unique_id", "hsl_nccl_comm_init", "hsl_nccl_comm_destroy", "hsl_allgather_costs", "hsl_allgather_costs_host", "hsl_model_tables", "hsl_fall_sweep_host", "hsl_set_fall_variant",
             "hsl_gather_create", "hsl_gather_connect", "hsl_gather_free", "hsl_eval_gaits_gather", "hsl_eval_gaits_scatter",
-            "hsl_gather_wait", "hsl_gather_select_best", "hsl_gather_size", "hsl_eval_gaits_gather_host", "hsl_set_device"]
+            "hsl_gather_wait", "hsl_gather_select_best", "hsl_gather_size", "hsl_eval_gaits_gather_host", "hsl_set_device", "hsl_gather_check"]
 
 
 class _Pinned:
@@ -447,6 +448,10 @@ class Gather:
         all_cot, all_st = C.c_void_p(), C.c_void_p()
         _check(_load().hsl_gather_wait(self._g, C.byref(all_cot), C.byref(all_st), stream or None))
         return all_cot.value, all_st.value
+
+    def check(self):
+        """hsl_gather_check: synchronises the device; raises if a wait on this object timed out (a rank never arrived)."""
+        _check(_load().hsl_gather_check(self._g))
 
     def free(self):
         """Unmap and free.  All ranks must be done with the buffers (barrier before)."""

@@ -389,7 +389,7 @@ int hsl_gather_create(int nranks, int rank, int64_t n_per_rank, HslGather** out,
   const size_t n = (size_t)nranks * n_per_rank;
   g->off_status = up256(2 * n * sizeof(double));
   g->off_flags = g->off_status + up256(2 * n * sizeof(int32_t));
-  g->bytes = g->off_flags + up256(HSL_MAX_PEERS * sizeof(unsigned long long) + sizeof(unsigned int));   // flags, then the finish kernel's block counter
+  g->bytes = g->off_flags + up256((HSL_MAX_PEERS + 2) * sizeof(unsigned long long));   // flags [16], the finish kernel's block counter, the time-out word
   cudaError_t e = cudaMalloc((void**)&g->local, g->bytes);   // plain cudaMalloc: stream-ordered pool memory cannot be exported
   if (e == cudaSuccess) e = cudaMemset(g->local, 0xff, g->off_status);                       // costs: NaN
   if (e == cudaSuccess) e = cudaMemset(g->local + g->off_status, 0, g->bytes - g->off_status);  // status and flags: 0
@@ -412,6 +412,15 @@ int hsl_gather_connect(HslGather* g, const HslIpcHandle* all) {
     if (e != cudaSuccess) return set_err(HSL_ERR_CUDA, ("cudaIpcOpenMemHandle of rank " + std::to_string(r) + "'s buffer: %s").c_str(), cudaGetErrorString(e));
   }
   g->connected = true;
+  return HSL_OK;
+}
+int hsl_gather_check(HslGather* g) {
+  if (!g) return set_err(HSL_ERR_ARG, "null gather object");
+  unsigned long long t = 0;
+  HSL_CUDA(cudaDeviceSynchronize());
+  HSL_CUDA(cudaMemcpy(&t, g->local + g->off_flags + (HSL_MAX_PEERS + 1) * sizeof(unsigned long long), sizeof t, cudaMemcpyDeviceToHost));
+  if (t) return set_err(HSL_ERR_CUDA, ("a rank's costs did not arrive within 30 s at gather call " + std::to_string(t) + ": %s").c_str(),
+                        "the ranks of the job must make the same sequence of scatter calls");
   return HSL_OK;
 }
 int64_t hsl_gather_size(const HslGather* g) { return g ? (int64_t)g->nranks * g->per : 0; }

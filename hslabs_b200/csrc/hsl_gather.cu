@@ -17,9 +17,7 @@ __global__ void hsl_gather_signal_kernel(const __grid_constant__ HslPeerOut peer
 
 // One block, thread r waits for rank r's flag.  Flags only grow.
 __global__ void hsl_gather_wait_kernel(const unsigned long long* flags, int nranks, unsigned long long epoch) {
-  if (threadIdx.x < nranks) {
-    while (hsl_ld_acquire_sys(flags + threadIdx.x) < epoch) __nanosleep(100);
-  }
+  if (threadIdx.x < nranks) hsl_wait_flag(flags + threadIdx.x, epoch, (unsigned long long*)(flags + HSL_MAX_PEERS + 1));
   __syncthreads();
   __threadfence_system();
 }

@@ -15,6 +15,23 @@ __device__ __forceinline__ unsigned long long hsl_ld_acquire_sys(const unsigned 
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// Wait until the flag has reached `epoch`.  Bounded: a rank that never arrives (crashed process, mismatched call sequence)
+// must not hang the GPU -- after HSL_GATHER_TIMEOUT_NS the wait gives up and records the epoch in *timed_out, which
+// hsl_gather_check reports on the host.
+#define HSL_GATHER_TIMEOUT_NS 30000000000ull
+__device__ __forceinline__ void hsl_wait_flag(const unsigned long long* flag, unsigned long long epoch, unsigned long long* timed_out) {
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  while (hsl_ld_acquire_sys(flag) < epoch) {
+    __nanosleep(50);
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > HSL_GATHER_TIMEOUT_NS) { *timed_out = epoch; break; }
+    }
+  }
+}
 // Tail of a kernel whose blocks stored into the peers' gather buffers: the block that finishes last pads the unused
 // entries, then raises this rank's flag at every peer (the threadFenceReduction pattern at system scope).  Every thread of
 // every block must call it.

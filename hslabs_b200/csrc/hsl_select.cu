@@ -32,7 +32,7 @@ __global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, in
   __shared__ double sv[32];
   __shared__ long long si[32];
   if (GATHERED) {
-    if (threadIdx.x < nranks) while (hsl_ld_acquire_sys(flags + threadIdx.x) < epoch) __nanosleep(50);
+    if (threadIdx.x < nranks) hsl_wait_flag(flags + threadIdx.x, epoch, (unsigned long long*)(flags + HSL_MAX_PEERS + 1));
     __syncthreads();
   }
   const double inf = __longlong_as_double(0x7ff0000000000000LL);

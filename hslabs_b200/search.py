@@ -60,6 +60,7 @@ class DeviceEvaluator:
             self.dist.barrier()
             for g in self._gathers.values():
                 if g is not None:
+                    g.check()
                     g.free()
             self._gathers = {}
 

@@ -216,6 +216,9 @@ int hsl_eval_gaits_gather(HslModel* m, HslGather* g, int64_t n_cand, int n_t, co
                           double* d_work, double* d_min_cfz, double* d_max_mu, int32_t* d_status, const double** d_all_cot,
                           const int32_t** d_all_status, void* stream);
 int64_t hsl_gather_size(const HslGather* g);   /* nranks * n_per_rank: entries of the gathered arrays */
+/* The waits on the device are bounded (30 s): a rank that never arrives must not hang the GPU.  hsl_gather_check synchronises
+ * the device and returns an error if any wait on this object gave up (its results are then incomplete). */
+int hsl_gather_check(HslGather* g);
 /* the same with HOST arrays (params [n_cand][13] in; all_cot / all_status [nranks * n_per_rank] out, either may be NULL);
  * synchronous -- for hosts that keep no device memory of their own, e.g. the C++ mirror's sharded measure_cot_sweep */
 int hsl_eval_gaits_gather_host(HslModel* m, HslGather* g, int64_t n_cand, int n_t, const double* params, int flags, double* all_cot,
