@@ -419,7 +419,7 @@ int hsl_gather_check(HslGather* g) {
   unsigned long long t = 0;
   HSL_CUDA(cudaDeviceSynchronize());
   HSL_CUDA(cudaMemcpy(&t, g->local + g->off_flags + (HSL_MAX_PEERS + 1) * sizeof(unsigned long long), sizeof t, cudaMemcpyDeviceToHost));
-  if (t) return set_err(HSL_ERR_CUDA, ("a rank's costs did not arrive within 30 s at gather call " + std::to_string(t) + ": %s").c_str(),
+  if (t) return set_err(HSL_ERR_CUDA, ("a rank's costs did not arrive within the time-out (30 s by default) at gather call " + std::to_string(t) + ": %s").c_str(),
                         "the ranks of the job must make the same sequence of scatter calls");
   return HSL_OK;
 }

@@ -18,7 +18,9 @@ __device__ __forceinline__ unsigned long long hsl_ld_acquire_sys(const unsigned 
 // Wait until the flag has reached `epoch`.  Bounded: a rank that never arrives (crashed process, mismatched call sequence)
 // must not hang the GPU -- after HSL_GATHER_TIMEOUT_NS the wait gives up and records the epoch in *timed_out, which
 // hsl_gather_check reports on the host.
+#ifndef HSL_GATHER_TIMEOUT_NS
 #define HSL_GATHER_TIMEOUT_NS 30000000000ull
+#endif
 __device__ __forceinline__ void hsl_wait_flag(const unsigned long long* flag, unsigned long long epoch, unsigned long long* timed_out) {
   unsigned long long t0 = 0;
   unsigned spins = 0;
