@@ -69,6 +69,7 @@ class HouseholderQR {
   Mat qr;    // R in the upper triangle, essential reflector parts below
   Vec beta;  // reflector coefficients
   std::vector<int> perm;  // column permutation (identity unless pivoted)
+  std::vector<std::vector<int> > vrows;  // per reflector: the rows below the diagonal in which v is non-zero
   int rank_;
   explicit HouseholderQR(const Mat& A, bool pivot = false) : qr(A), beta(A.c, 0.0), perm(A.c) {
     const int m = qr.r, n = qr.c;
@@ -82,6 +83,9 @@ class HouseholderQR {
     rank_ = n < m ? n : m;
     bool rank_set = false;
     const int steps = n < m ? n : m;
+    std::vector<int> nzr;
+    nzr.reserve(m);
+    vrows.assign(steps, std::vector<int>());
     for (int k = 0; k < steps; k++) {
       if (pivot) {
         int best = k;
@@ -104,39 +108,53 @@ class HouseholderQR {
       real nrm = orc::m_sqrt(a0 * a0 + s);
       real alpha = (a0 >= 0) ? -nrm : nrm;
       real v0 = a0 - alpha;
-      for (int i = k + 1; i < m; i++) qr(i, k) /= v0;  // v = [1; essential]
+      // The matrices of this path are sparse (block rows of a few entries), and so are most reflectors: only the rows in
+      // which v is non-zero take part.  Skipping the others drops terms that are exactly +-0, so every result keeps its bits.
+      nzr.clear();
+      for (int i = k + 1; i < m; i++) {
+        if (qr(i, k) != 0) { qr(i, k) /= v0; nzr.push_back(i); }  // v = [1; essential]
+      }
       beta[k] = -v0 / alpha;                            // H = I - beta v v^T
       qr(k, k) = alpha;
+      vrows[k] = nzr;
+      const size_t nn = nzr.size();
       for (int j = k + 1; j < n; j++) {
         real w = qr(k, j);
-        for (int i = k + 1; i < m; i++) w += qr(i, k) * qr(i, j);
+        for (size_t t = 0; t < nn; t++) w += qr(nzr[t], k) * qr(nzr[t], j);
+        if (w == 0) continue;
         w *= beta[k];
         qr(k, j) -= w;
-        for (int i = k + 1; i < m; i++) qr(i, j) -= w * qr(i, k);
+        for (size_t t = 0; t < nn; t++) qr(nzr[t], j) -= w * qr(nzr[t], k);
       }
     }
   }
   int rank() const { return rank_; }
   void apply_qt(Vec& b) const {  // b <- Q^T b
     const int m = qr.r, steps = qr.c < qr.r ? qr.c : qr.r;
+    (void)m;
     for (int k = 0; k < steps; k++) {
       if (beta[k] == 0) continue;
+      const std::vector<int>& nz = vrows[k];   // the other rows contribute exact zeros
       real w = b[k];
-      for (int i = k + 1; i < m; i++) w += qr(i, k) * b[i];
+      for (size_t t = 0; t < nz.size(); t++) w += qr(nz[t], k) * b[nz[t]];
+      if (w == 0) continue;
       w *= beta[k];
       b[k] -= w;
-      for (int i = k + 1; i < m; i++) b[i] -= w * qr(i, k);
+      for (size_t t = 0; t < nz.size(); t++) b[nz[t]] -= w * qr(nz[t], k);
     }
   }
   void apply_q(Vec& b) const {  // b <- Q b
     const int m = qr.r, steps = qr.c < qr.r ? qr.c : qr.r;
+    (void)m;
     for (int k = steps - 1; k >= 0; k--) {
       if (beta[k] == 0) continue;
+      const std::vector<int>& nz = vrows[k];
       real w = b[k];
-      for (int i = k + 1; i < m; i++) w += qr(i, k) * b[i];
+      for (size_t t = 0; t < nz.size(); t++) w += qr(nz[t], k) * b[nz[t]];
+      if (w == 0) continue;
       w *= beta[k];
       b[k] -= w;
-      for (int i = k + 1; i < m; i++) b[i] -= w * qr(i, k);
+      for (size_t t = 0; t < nz.size(); t++) b[nz[t]] -= w * qr(nz[t], k);
     }
   }
   // Basic least-squares solution (free variables = 0), like SparseQR::solve.
