@@ -37,6 +37,23 @@ cudaError_t hsl_launch_gather_wait(const unsigned long long* flags, int nranks, 
 cudaError_t hsl_launch_argmin_gathered(const double* cost, int64_t n, int64_t* out_index, double* out_value, const unsigned long long* flags,
                                        int nranks, unsigned long long epoch, cudaStream_t st);
 
+// Launch configuration with programmatic dependent launch allowed (sm_90+): the kernel's blocks may become resident while the
+// kernel in front of it on the stream is still draining; the kernel itself must execute griddepcontrol.wait before it
+// touches anything that kernel wrote (every kernel launched through this helper does, as its first instruction).
+struct HslPdlConfig {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[1];
+  HslPdlConfig(dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+    cfg = cudaLaunchConfig_t();
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+};
+#define HSL_GRID_DEP_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#define HSL_GRID_DEP_LAUNCH() asm volatile("griddepcontrol.launch_dependents;")
+
 cudaError_t hsl_launch_math_selftest(int n, const double* a, const double* b, double* out, cudaStream_t st);
 cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st);
 int hsl_topk_launches(int64_t n);  // kernels hsl_launch_topk issues for n costs

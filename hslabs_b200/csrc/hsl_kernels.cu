@@ -37,6 +37,8 @@ hsl_frames_kernel(const __grid_constant__ HslModelPod M, const __grid_constant__
   const int role = threadIdx.x / FB;
   HslSlot sl;
   sl.s = threadIdx.x % FB;
+  HSL_GRID_DEP_WAIT();     // inputs written by the kernel in front (candidate setup, transposes of the device-pointer entries)
+  HSL_GRID_DEP_LAUNCH();
   if (MODE == HSL_MODE_FIELDS) {
     const int64_t g = (int64_t)blockIdx.x * FB + sl.s;
     sl.valid = g < A.n_frames;
@@ -210,6 +212,8 @@ hsl_gait_pipe_kernel(const __grid_constant__ HslModelPod M, const __grid_constan
   sm.carve(hsl_smem_raw, M.ntrunk);
   const int role = threadIdx.x / FB;
   const int s = threadIdx.x % FB;
+  HSL_GRID_DEP_WAIT();     // the candidate constants and frame times of the setup kernel are complete
+  HSL_GRID_DEP_LAUNCH();   // the finish kernel may take the SMs this grid frees at its tail
   // p1 / p2 below: slots of the two previous tiles of this block (t-1, t-2)
 #ifdef HSL_PHASE_CLOCKS
   long long acc[4] = {0, 0, 0, 0};
@@ -372,6 +376,7 @@ __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t 
   // per candidate; written lane by lane they would be 32 scattered 8-byte stores per step (the kernel then spends 18 us on
   // 4096 x 260 of them), so the warp stages 32 steps of its 32 candidates in shared memory and writes whole 256-byte rows.
   __shared__ double tile[32][33];
+  HSL_GRID_DEP_LAUNCH();   // the per-frame kernel may start its prologue (it waits for this grid's end)
   const int lane = threadIdx.x;
   const int64_t c0 = (int64_t)blockIdx.x * 32, c = c0 + lane;
   const bool valid = c < n_cand;
@@ -406,6 +411,8 @@ __global__ void hsl_finish_kernel(int64_t n_cand, int n_t, double total_mass, co
                                   const double* __restrict__ fmin_in, const double* __restrict__ fmax_in,
                                   const int32_t* __restrict__ status, double* __restrict__ cot, double* __restrict__ work,
                                   double* __restrict__ min_cfz, double* __restrict__ max_mu, const __grid_constant__ HslPeerOut peers) {
+  HSL_GRID_DEP_WAIT();     // launched with programmatic dependent launch behind the per-frame kernel
+  HSL_GRID_DEP_LAUNCH();
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
   const int lane = threadIdx.x & 31;
   if (c >= n_cand) {   // a whole warp
@@ -530,8 +537,8 @@ cudaError_t launch_frames_t(const HslModelPod& M, const HslFrameArgs& A_in, cuda
     if (blocks < 1) blocks = 1;
   }
   if (blocks > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-  kern<<<(unsigned)blocks, (NF + 1) * FB, smem, st>>>(M, A);
-  return cudaGetLastError();
+  HslPdlConfig pc(dim3((unsigned)blocks), dim3((NF + 1) * FB), smem, st);   // programmatic dependent launch, as for the pipelined kernel
+  return cudaLaunchKernelEx(&pc.cfg, kern, M, A);
 }
 template <int NF, int FB>
 cudaError_t launch_frames_nf(const HslModelPod& M, const HslFrameArgs& A, int mode, bool dump, cudaStream_t st) {
@@ -572,8 +579,11 @@ cudaError_t launch_gait_pipe(const HslModelPod& M, const HslFrameArgs& A, cudaSt
   }
   int64_t grid = (int64_t)di.sms * di.per_sm;
   if (grid > n_tiles) grid = n_tiles;
-  kern<<<(unsigned)grid, HSL_PIPE_ROLES(NF) * FB, smem, st>>>(M, A, n_tiles);
-  return cudaGetLastError();
+  // Programmatic dependent launch: the blocks of this kernel become resident and run their prologue (shared-memory carve-up,
+  // slot arithmetic) while the candidate-setup kernel in front of it is still finishing; they wait for its results at
+  // griddepcontrol.wait.  In front of any other kernel the wait is an ordinary stream dependency.
+  HslPdlConfig pc(dim3((unsigned)grid), dim3(HSL_PIPE_ROLES(NF) * FB), smem, st);
+  return cudaLaunchKernelEx(&pc.cfg, kern, M, A, (int64_t)n_tiles);
 }
 
 // Cost-only evaluation (the headline path) comes in a few occupancy variants: fb = frame slots per block,
@@ -675,9 +685,9 @@ cudaError_t hsl_launch_finish(int64_t n_cand, int n_t, double total_mass, const 
   const int64_t threads = n_cand * 32;
   HslPeerOut none;
   none.n = 0;
-  hsl_finish_kernel<<<(unsigned)((threads + tpb - 1) / tpb), tpb, 0, st>>>(n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in,
-                                                                         fmax_in, status, cot, work, min_cfz, max_mu, peers ? *peers : none);
-  return cudaGetLastError();
+  HslPdlConfig pc(dim3((unsigned)((threads + tpb - 1) / tpb)), dim3(tpb), 0, st);
+  return cudaLaunchKernelEx(&pc.cfg, hsl_finish_kernel, n_cand, n_t, total_mass, cand, dt_in, wframe, fmin_in, fmax_in, status, cot, work, min_cfz,
+                            max_mu, peers ? *peers : none);
 }
 
 

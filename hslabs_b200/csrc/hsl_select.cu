@@ -31,6 +31,7 @@ __global__ void hsl_argmin_kernel(const double* __restrict__ cost, int64_t n, in
                                   const unsigned long long* flags, int nranks, unsigned long long epoch) {
   __shared__ double sv[32];
   __shared__ long long si[32];
+  HSL_GRID_DEP_WAIT();   // launched with programmatic dependent launch behind the kernel that wrote the costs
   if (GATHERED) {
     if (threadIdx.x < nranks) hsl_wait_flag(flags + threadIdx.x, epoch, (unsigned long long*)(flags + HSL_MAX_PEERS + 1));
     __syncthreads();
@@ -288,13 +289,13 @@ __global__ void hsl_topk_emit_kernel(const uint64_t* __restrict__ keys, const ui
 }  // namespace
 
 cudaError_t hsl_launch_argmin(const double* cost, int64_t n, int64_t* out_index, double* out_value, cudaStream_t st) {
-  hsl_argmin_kernel<false><<<1, 1024, 0, st>>>(cost, n, out_index, out_value, nullptr, 0, 0);
-  return cudaGetLastError();
+  HslPdlConfig pc(dim3(1), dim3(1024), 0, st);
+  return cudaLaunchKernelEx(&pc.cfg, hsl_argmin_kernel<false>, cost, n, out_index, out_value, (const unsigned long long*)nullptr, 0, 0ull);
 }
 cudaError_t hsl_launch_argmin_gathered(const double* cost, int64_t n, int64_t* out_index, double* out_value, const unsigned long long* flags,
                                        int nranks, unsigned long long epoch, cudaStream_t st) {
-  hsl_argmin_kernel<true><<<1, 1024, 0, st>>>(cost, n, out_index, out_value, flags, nranks, epoch);
-  return cudaGetLastError();
+  HslPdlConfig pc(dim3(1), dim3(1024), 0, st);
+  return cudaLaunchKernelEx(&pc.cfg, hsl_argmin_kernel<true>, cost, n, out_index, out_value, flags, nranks, epoch);
 }
 
 cudaError_t hsl_launch_topk(const double* cost, int64_t n, int k, int64_t* out_index, double* out_value, cudaStream_t st) {
