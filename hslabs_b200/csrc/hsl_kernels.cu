@@ -372,34 +372,44 @@ __global__ void hsl_fk_records_kernel(const __grid_constant__ HslModelPod M, int
 
 __global__ void hsl_setup_kernel(const __grid_constant__ HslModelPod M, int64_t n_cand, int n_t, const double* __restrict__ params,
                                  HslCand* __restrict__ cand, double* __restrict__ ttab, int32_t* __restrict__ status) {
-  // One warp per block, lane = candidate.  The frame times are an accumulated sum (t += dt, periodic.cpp:87-91), sequential
-  // per candidate; written lane by lane they would be 32 scattered 8-byte stores per step (the kernel then spends 18 us on
-  // 4096 x 260 of them), so the warp stages 32 steps of its 32 candidates in shared memory and writes whole 256-byte rows.
+  // Two warps per block, lane = candidate (32 candidates per block).  Warp 0 computes the candidate constants.  Warp 1 writes
+  // the frame times: an accumulated sum (t += dt, periodic.cpp:87-91), sequential per candidate; written lane by lane they
+  // would be 32 scattered 8-byte stores per step, so the warp stages 32 steps of its 32 candidates in shared memory and
+  // writes whole 256-byte rows.  The two run side by side (the kernel is a latency chain of one warp per SM otherwise).
   __shared__ double tile[32][33];
   HSL_GRID_DEP_LAUNCH();   // the per-frame kernel may start its prologue (it waits for this grid's end)
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const int64_t c0 = (int64_t)blockIdx.x * 32, c = c0 + lane;
   const bool valid = c < n_cand;
-  double dt = 0;
-  if (valid) {
-    double p[HSL_NPARAM];
+  if (threadIdx.x < 32) {
+    if (valid) {
+      double p[HSL_NPARAM];
 #pragma unroll
-    for (int k = 0; k < HSL_NPARAM; k++) p[k] = params[c * HSL_NPARAM + k];
-    HslCand cd;
-    setup_candidate(M, p, n_t, cd, nullptr);
-    cand[c] = cd;
-    status[c] = cd.status;
-    dt = cd.dt;
+      for (int k = 0; k < HSL_NPARAM; k++) p[k] = params[c * HSL_NPARAM + k];
+      HslCand cd;
+      setup_candidate(M, p, n_t, cd, nullptr);
+      cand[c] = cd;
+      status[c] = cd.status;
+    }
+    return;
   }
+  const double dt = valid ? params[c * HSL_NPARAM + 7] / n_t : 0.0;   // cd.dt = period / n_t, as setup_candidate computes it
   const int per = n_t + 4;
   const int rows = (int)((n_cand - c0 < 32) ? n_cand - c0 : 32);
   double t = 0;
   for (int i0 = 0; i0 < per; i0 += 32) {
-#pragma unroll 8
+#pragma unroll
     for (int j = 0; j < 32; j++) { tile[lane][j] = t; t += dt; }   // the same recurrence as setup_candidate's own table
     __syncwarp();
-    if (i0 + lane < per)
-      for (int r = 0; r < rows; r++) ttab[(c0 + r) * per + i0 + lane] = tile[r][lane];
+    if (i0 + lane < per) {
+      double* dst = ttab + c0 * per + i0 + lane;
+      if (rows == 32) {
+#pragma unroll
+        for (int r = 0; r < 32; r++) dst[(int64_t)r * per] = tile[r][lane];
+      } else {
+        for (int r = 0; r < rows; r++) dst[(int64_t)r * per] = tile[r][lane];
+      }
+    }
     __syncwarp();
   }
 }
@@ -673,8 +683,8 @@ cudaError_t hsl_launch_ik_records(const HslModelPod& M, int64_t n, int flags, co
 
 cudaError_t hsl_launch_setup(const HslModelPod& M, int64_t n_cand, int n_t, const double* params, HslCand* cand, double* ttab,
                              int32_t* status, cudaStream_t st) {
-  const int tpb = 32;  // one candidate per thread with a sequential time table: spread the candidates over many SMs
-  hsl_setup_kernel<<<(unsigned)((n_cand + tpb - 1) / tpb), tpb, 0, st>>>(M, n_cand, n_t, params, cand, ttab, status);
+  // 32 candidates per block (one per lane, sequential time tables): spread over many SMs; two warps: constants | time table
+  hsl_setup_kernel<<<(unsigned)((n_cand + 31) / 32), 64, 0, st>>>(M, n_cand, n_t, params, cand, ttab, status);
   return cudaGetLastError();
 }
 
