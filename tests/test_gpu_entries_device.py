@@ -128,3 +128,40 @@ def test_gather_object_with_one_rank(hsl):
     with pytest.raises(hsl.HslError):
         m.eval_gaits_gather(g, per + 1, n_t, d.data_ptr())
     g.free()
+
+
+def test_back_to_back_calls_on_one_stream(hsl):
+    """The kernels of a call are chained by programmatic dependent launch (the next kernel's blocks become resident before the
+    previous one has drained), and consecutive calls reuse the handle's workspace: 60 calls alternating between two batches of
+    different size, queued without any synchronisation, must each give exactly what the batch gives on its own."""
+    import torch
+    rng = np.random.default_rng(17)
+
+    def batch(n):
+        p = np.zeros((n, 13))
+        p[:, 2] = rng.uniform(-0.15, -0.05, n); p[:, 6] = rng.uniform(0, 1, n); p[:, 7] = rng.uniform(1, 6, n)
+        p[:, 8] = rng.uniform(0.1, 0.5, n); p[:, 9] = rng.uniform(0.02, 0.12, n); p[:, 11] = -1
+        return p
+    m = hsl.Model(hsl.model_path("hexapod"))
+    pa, pb = batch(777), batch(1501)
+    want = [m.eval_gaits(pa, 40), m.eval_gaits(pb, 24)]
+    da, db = torch.from_numpy(pa).cuda(), torch.from_numpy(pb).cuda()
+    outs = []
+    s = torch.cuda.current_stream().cuda_stream
+    best = torch.empty(60, dtype=torch.int64, device="cuda")
+    from hslabs_b200 import api
+    for it in range(60):
+        which = it % 2
+        d, n, n_t = (da, 777, 40) if which == 0 else (db, 1501, 24)
+        cot = torch.empty(n, dtype=torch.float64, device="cuda")
+        st = torch.empty(n, dtype=torch.int32, device="cuda")
+        m.eval_gaits_device(n, n_t, d.data_ptr(), cot.data_ptr(), 0, 0, 0, st.data_ptr(), 0, s)
+        api.select_best_device(cot.data_ptr(), n, best[it:].data_ptr(), 0, s)
+        outs.append((which, cot, st))
+    torch.cuda.synchronize()
+    for it, (which, cot, st) in enumerate(outs):
+        w = want[which]
+        assert np.array_equal(cot.cpu().numpy(), w["cot"], equal_nan=True), it
+        assert np.array_equal(st.cpu().numpy(), w["status"]), it
+        key = np.where(np.isnan(w["cot"]), np.inf, w["cot"])
+        assert int(best[it]) == int(np.argmin(key)), it
