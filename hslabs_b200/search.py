@@ -120,7 +120,9 @@ def top_k(cot, k, trim=True):
 def grid_search(model, base, axes, n_t, k=1, flags=0, device="cuda"):
     import torch
     cand = torch.from_numpy(grid_candidates(base, axes)).to(device)
-    cot, st = DeviceEvaluator(model, n_t, flags)(cand)
+    ev = DeviceEvaluator(model, n_t, flags)
+    cot, st = ev(cand)
+    ev.close()
     idx, best = top_k(cot, k)
     return dict(candidates=cand, cot=cot, status=st, best_index=idx, best_cot=best)
 
@@ -133,7 +135,9 @@ def random_search(model, base, ranges, n_cand, n_t, seed=0, k=1, flags=0, device
     cand = torch.from_numpy(np.asarray(base, np.float64)).to(device).repeat(n_cand, 1)
     for name, (lo, hi) in ranges.items():
         cand[:, SWEEP_NAMES[name]] = lo + (hi - lo) * torch.rand(n_cand, dtype=torch.float64, device=device, generator=g)
-    cot, st = DeviceEvaluator(model, n_t, flags)(cand)
+    ev = DeviceEvaluator(model, n_t, flags)
+    cot, st = ev(cand)
+    ev.close()
     idx, best = top_k(cot, k)
     return dict(candidates=cand, cot=cot, status=st, best_index=idx, best_cot=best)
 
@@ -206,5 +210,5 @@ def cem_search(model, base, ranges, n_t, pop=1024, elite=64, iters=8, seed=0, fl
     hist = [float(v) for v in history[:iters].cpu()] if iters else []   # the one read-back
     hist = [v for v in hist if np.isfinite(v)]
     bc = float(best_cot)
-    ev.close() if ev.world > 1 else None
+    ev.close()
     return dict(best_cot=bc, best_candidate=best_cand if np.isfinite(bc) else None, history=hist, mean=mean, std=std)

@@ -92,6 +92,9 @@ def main(out_dir):
     allbest = [None] * world
     dist.all_gather_object(allbest, float(res["best_cot"]))
     assert all(b == allbest[0] for b in allbest), "ranks disagree on the search result"
+    rs = search.random_search(model, p[0], {"period": (1.0, 6.0), "step_length": (0.1, 0.5)}, 300, n_t, seed=4, k=3)   # sharded, gather freed after
+    one = model.eval_gaits(rs["candidates"].cpu().numpy(), n_t)["cot"]
+    assert np.array_equal(rs["cot"].cpu().numpy(), one, equal_nan=True)
     # the C-ABI collective (hsl_allgather_costs over an ncclComm_t created from a broadcast unique id)
     if hasattr(hsl.api, "nccl_allgather_selftest"):
         hsl.api.nccl_allgather_selftest(rank, world, dist, dev)
